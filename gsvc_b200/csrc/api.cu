@@ -1,0 +1,275 @@
+// extern "C" boundary of libgsvc_rast.so (see include/gsvc_rast.h for the contract and the
+// reference call sites each entry point replaces).  No torch types, no allocation: raw device
+// pointers, sizes and a cudaStream_t.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace gsvc {
+
+static thread_local char g_err[512] = "";
+static thread_local long long g_launches = 0;
+
+void count_launch(int n) { g_launches += n; }
+
+static int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(expr, what)                                                                                       \
+    do {                                                                                                     \
+        cudaError_t e__ = (expr);                                                                            \
+        if (e__ != cudaSuccess) return fail(GSVC_RAST_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e__));    \
+        if (dbg) {                                                                                           \
+            e__ = cudaStreamSynchronize(stream);                                                             \
+            if (e__ != cudaSuccess)                                                                          \
+                return fail(GSVC_RAST_ERR_CUDA, "%s (debug sync): %s", what, cudaGetErrorString(e__));       \
+        }                                                                                                    \
+    } while (0)
+
+static int make_settings(const gsvc_rast_settings* st, int sh_M, DevSettings& d)
+{
+    if (!st) return fail(GSVC_RAST_ERR_INVALID, "settings is NULL");
+    if (st->image_width <= 0 || st->image_height <= 0) return fail(GSVC_RAST_ERR_INVALID, "image size must be positive");
+    if (!st->viewmatrix) return fail(GSVC_RAST_ERR_INVALID, "viewmatrix is NULL");
+    d.W = st->image_width; d.H = st->image_height;
+    d.gx = (d.W + TILE - 1) / TILE; d.gy = (d.H + TILE - 1) / TILE;
+    if (d.gx > 65535 || d.gy > 65535) return fail(GSVC_RAST_ERR_INVALID, "image too large for 16-bit tile coordinates");
+    d.x_min = st->x_min; d.y_min = st->y_min; d.scale = st->scale; d.threshold = st->threshold;
+    d.scale_modifier = st->scale_modifier;
+    d.bg = st->bg; d.V = st->viewmatrix; d.vs_r = st->vm_stride_r; d.vs_c = st->vm_stride_c;
+    d.sh_degree = st->sh_degree; d.sh_M = sh_M;
+    d.campos[0] = st->campos[0]; d.campos[1] = st->campos[1]; d.campos[2] = st->campos[2];
+    return 0;
+}
+
+static int check_inputs(int P, int sh_M, int sh_degree, const float* means3D, const float* shs,
+                        const float* colors_precomp, const float* opacities, const float* scales,
+                        const float* rotations, const float* cov3D_precomp, bool need_color)
+{
+    if (P < 0) return fail(GSVC_RAST_ERR_INVALID, "P must be >= 0");
+    if (P == 0) return 0;  // empty inputs carry NULL pointers
+    if (P > 0 && !means3D) return fail(GSVC_RAST_ERR_INVALID, "means3D is NULL");
+    const bool sr = scales && rotations;
+    if ((scales == nullptr) != (rotations == nullptr) || (sr == (cov3D_precomp != nullptr)))
+        return fail(GSVC_RAST_ERR_INVALID, "Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
+    if (need_color) {
+        if ((shs != nullptr) == (colors_precomp != nullptr))
+            return fail(GSVC_RAST_ERR_INVALID, "Please provide excatly one of either SHs or precomputed colors!");
+        if (P > 0 && !opacities) return fail(GSVC_RAST_ERR_INVALID, "opacities is NULL");
+        if (shs) {
+            if (sh_degree < 0 || sh_degree > 3) return fail(GSVC_RAST_ERR_INVALID, "sh_degree must be in 0..3");
+            if (sh_M < (sh_degree + 1) * (sh_degree + 1))
+                return fail(GSVC_RAST_ERR_INVALID, "shs has %d coefficients, sh_degree %d needs %d", sh_M, sh_degree,
+                            (sh_degree + 1) * (sh_degree + 1));
+        }
+    }
+    return 0;
+}
+
+static int render_stages(const DevSettings& d, int P, GeomView g, ImageView im, void* binning, long long cap,
+                         float* out_color, cudaStream_t stream, bool dbg)
+{
+    BinView b = bin_view(binning, cap);
+    CK(launch_scatter(d, P, g, im, b, cap, stream), "scatter");
+    CK(launch_sort_tiles(d, im, b, cap, stream), "sort_tiles");
+    CK(launch_render_forward(d, g, im, b, cap, out_color, stream), "render_forward");
+    return 0;
+}
+
+}  // namespace gsvc
+
+using namespace gsvc;
+
+extern "C" {
+
+int gsvc_rast_abi_version(void) { return GSVC_RAST_ABI_VERSION; }
+const char* gsvc_rast_last_error(void) { return g_err; }
+size_t gsvc_rast_geom_bytes(int32_t P, int32_t sh_M) { return geom_bytes(P < 1 ? 1 : P, sh_M); }
+size_t gsvc_rast_image_bytes(int32_t W, int32_t H) { return image_bytes(W < 1 ? 1 : W, H < 1 ? 1 : H); }
+size_t gsvc_rast_binning_bytes(int64_t cap) { return bin_bytes(cap < 1 ? 1 : cap); }
+size_t gsvc_rast_backward_scratch_bytes(int32_t P) { return bwd_scratch_bytes(P < 1 ? 1 : P); }
+int64_t gsvc_rast_launch_count(int32_t reset)
+{
+    const long long v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+
+int gsvc_rast_visible_filter(const gsvc_rast_settings* st, int32_t P, const float* means3D, const float* scales,
+                             const float* rotations, const float* cov3D_precomp, int32_t* radii, void* stream_)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DevSettings d;
+    int rc = make_settings(st, 0, d);
+    if (rc) return rc;
+    rc = check_inputs(P, 0, 0, means3D, nullptr, nullptr, nullptr, scales, rotations, cov3D_precomp, false);
+    if (rc) return rc;
+    if (P > 0 && !radii) return fail(GSVC_RAST_ERR_INVALID, "radii is NULL");
+    const bool dbg = st->debug != 0;
+    PreInputs in{P, means3D, nullptr, nullptr, nullptr, scales, rotations, cov3D_precomp};
+    CK(launch_visible_filter(d, in, radii, stream), "visible_filter");
+    return 0;
+}
+
+int gsvc_rast_forward_launch(const gsvc_rast_settings* st, int32_t P, int32_t sh_M, const float* means3D,
+                             const float* shs, const float* colors_precomp, const float* opacities,
+                             const float* scales, const float* rotations, const float* cov3D_precomp, void* geom,
+                             void* image, void* binning, int64_t capacity, float* out_color, int32_t* radii,
+                             int64_t* num_rendered_host, void* stream_)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DevSettings d;
+    int rc = make_settings(st, shs ? sh_M : 0, d);
+    if (rc) return rc;
+    rc = check_inputs(P, sh_M, st->sh_degree, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, true);
+    if (rc) return rc;
+    if (!st->bg) return fail(GSVC_RAST_ERR_INVALID, "bg is NULL");
+    if (!geom || !image || !out_color || (P > 0 && !radii))
+        return fail(GSVC_RAST_ERR_INVALID, "geom/image/out_color/radii must be non-NULL");
+    if (capacity > 0 && !binning) return fail(GSVC_RAST_ERR_INVALID, "binning is NULL");
+    const bool dbg = st->debug != 0;
+    GeomView g = geom_view(geom, P < 1 ? 1 : P, d.sh_M);
+    ImageView im = image_view(image, d.W, d.H);
+    PreInputs in{P, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp};
+    CK(launch_preprocess(d, in, radii, g, im, stream), "preprocess");
+    CK(launch_tile_scan(d, im, stream), "tile_scan");
+    if (num_rendered_host)
+        CK(cudaMemcpyAsync(num_rendered_host, &im.hdr->num_rendered, sizeof(int64_t), cudaMemcpyDeviceToHost, stream),
+           "num_rendered readback");
+    if (capacity > 0) {
+        rc = render_stages(d, P, g, im, binning, capacity, out_color, stream, dbg);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int gsvc_rast_forward_render(const gsvc_rast_settings* st, int32_t P, const void* geom, void* image, void* binning,
+                             int64_t capacity, float* out_color, void* stream_)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DevSettings d;
+    int rc = make_settings(st, 0, d);
+    if (rc) return rc;
+    if (!geom || !image || !binning || !out_color || capacity <= 0)
+        return fail(GSVC_RAST_ERR_INVALID, "geom/image/binning/out_color must be non-NULL and capacity > 0");
+    const bool dbg = st->debug != 0;
+    // sh_M only affects the tail of the geom layout (clamp flags), which these stages never touch
+    GeomView g = geom_view(const_cast<void*>(geom), P < 1 ? 1 : P, 0);
+    ImageView im = image_view(image, d.W, d.H);
+    // the scatter cursors were consumed by a previous attempt: reset them
+    CK(cudaMemsetAsync(im.tile_cursor, 0, (size_t)d.gx * d.gy * sizeof(unsigned int), stream), "cursor reset");
+    return render_stages(d, P, g, im, binning, capacity, out_color, stream, dbg);
+}
+
+int64_t gsvc_rast_forward(const gsvc_rast_settings* st, int32_t P, int32_t sh_M, const float* means3D,
+                          const float* shs, const float* colors_precomp, const float* opacities, const float* scales,
+                          const float* rotations, const float* cov3D_precomp, gsvc_rast_alloc_fn alloc, void* user,
+                          float* out_color, int32_t* radii, void* stream_)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!alloc) return fail(GSVC_RAST_ERR_INVALID, "alloc callback is NULL");
+    if (!st) return fail(GSVC_RAST_ERR_INVALID, "settings is NULL");
+    void* geom = alloc(user, 0, gsvc_rast_geom_bytes(P, shs ? sh_M : 0));
+    void* image = alloc(user, 2, gsvc_rast_image_bytes(st->image_width, st->image_height));
+    if (!geom || !image) return fail(GSVC_RAST_ERR_INVALID, "alloc callback returned NULL");
+    // phase A: preprocess + tile scan; the exact instance count sizes the binning buffer
+    int rc = gsvc_rast_forward_launch(st, P, sh_M, means3D, shs, colors_precomp, opacities, scales, rotations,
+                                      cov3D_precomp, geom, image, nullptr, 0, out_color, radii, nullptr, stream_);
+    if (rc) return rc;
+    ImageView im = image_view(image, st->image_width, st->image_height);
+    unsigned long long R = 0;
+    cudaError_t e = cudaMemcpyAsync(&R, &im.hdr->num_rendered, sizeof(R), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) return fail(GSVC_RAST_ERR_CUDA, "num_rendered readback: %s", cudaGetErrorString(e));
+    if (R > 0xFFFFFFFFull) return fail(GSVC_RAST_ERR_OVERFLOW, "num_rendered %llu exceeds 32-bit tile ranges", R);
+    const int64_t cap = R > 0 ? (int64_t)R : 1;
+    void* binning = alloc(user, 1, gsvc_rast_binning_bytes(cap));
+    if (!binning) return fail(GSVC_RAST_ERR_INVALID, "alloc callback returned NULL");
+    rc = gsvc_rast_forward_render(st, P, geom, image, binning, cap, out_color, stream_);
+    if (rc) return rc;
+    return (int64_t)R;
+}
+
+int gsvc_rast_backward(const gsvc_rast_settings* st, int32_t P, int32_t sh_M, int64_t capacity,
+                       const float* means3D, const float* shs, const float* colors_precomp, const float* scales,
+                       const float* rotations, const float* cov3D_precomp, const int32_t* radii, const void* geom,
+                       const void* image, const void* binning, void* scratch, const float* dL_dout,
+                       float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacities,
+                       float* dL_dscales, float* dL_drotations, float* dL_dcov3D, float* dL_dshs, void* stream_)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DevSettings d;
+    int rc = make_settings(st, shs ? sh_M : 0, d);
+    if (rc) return rc;
+    rc = check_inputs(P, sh_M, st->sh_degree, means3D, shs, colors_precomp, reinterpret_cast<const float*>(1), scales,
+                      rotations, cov3D_precomp, true);
+    if (rc) return rc;
+    if (!st->bg) return fail(GSVC_RAST_ERR_INVALID, "bg is NULL");
+    if (!geom || !image || !scratch || !dL_dout || (P > 0 && !radii))
+        return fail(GSVC_RAST_ERR_INVALID, "geom/image/scratch/dL_dout/radii must be non-NULL");
+    if (capacity <= 0 || !binning) return fail(GSVC_RAST_ERR_INVALID, "binning is NULL or capacity <= 0");
+    const bool dbg = st->debug != 0;
+    GeomView g = geom_view(const_cast<void*>(geom), P < 1 ? 1 : P, d.sh_M);
+    ImageView im = image_view(const_cast<void*>(image), d.W, d.H);
+    BinView b = bin_view(const_cast<void*>(binning), capacity);
+    float4* acc = static_cast<float4*>(scratch);
+    PreInputs in{P, means3D, shs, colors_precomp, nullptr, scales, rotations, cov3D_precomp};
+    CK(launch_render_backward(d, P, g, im, b, dL_dout, acc, stream), "render_backward");
+    BwdOutputs out{dL_dmeans3D, dL_dmeans2D, dL_dcolors, dL_dopacities, dL_dscales, dL_drotations, dL_dcov3D, dL_dshs};
+    CK(launch_preprocess_backward(d, in, radii, g, acc, out, stream), "preprocess_backward");
+    return 0;
+}
+
+int gsvc_rast_export_keys(const gsvc_rast_settings* st, int64_t capacity, const void* image, const void* binning,
+                          uint64_t* sorted_keys, uint32_t* point_list, uint32_t* ranges, void* stream_)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DevSettings d;
+    int rc = make_settings(st, 0, d);
+    if (rc) return rc;
+    if (!image || !binning) return fail(GSVC_RAST_ERR_INVALID, "image/binning is NULL");
+    const bool dbg = st->debug != 0;
+    ImageView im = image_view(const_cast<void*>(image), d.W, d.H);
+    BinView b = bin_view(const_cast<void*>(binning), capacity > 0 ? capacity : 1);
+    CK(launch_export_keys(d, im, b, capacity, reinterpret_cast<unsigned long long*>(sorted_keys), point_list,
+                          ranges, stream),
+       "export_keys");
+    return 0;
+}
+
+int gsvc_rast_export_geom(int32_t P, int32_t sh_M, const void* geom, float* depth, float* xy, float* conic_opacity,
+                          float* rgb, int32_t* rect, void* stream_)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!geom) return fail(GSVC_RAST_ERR_INVALID, "geom is NULL");
+    const bool dbg = false;
+    GeomView g = geom_view(const_cast<void*>(geom), P < 1 ? 1 : P, sh_M);
+    CK(launch_export_geom(P, g, depth, xy, conic_opacity, rgb, rect, stream), "export_geom");
+    return 0;
+}
+
+int gsvc_rast_export_image(const gsvc_rast_settings* st, const void* image, float* final_T, uint32_t* n_contrib,
+                           void* stream_)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DevSettings d;
+    int rc = make_settings(st, 0, d);
+    if (rc) return rc;
+    if (!image) return fail(GSVC_RAST_ERR_INVALID, "image is NULL");
+    const bool dbg = false;
+    ImageView im = image_view(const_cast<void*>(image), d.W, d.H);
+    const size_t N = (size_t)d.W * d.H;
+    if (final_T) CK(cudaMemcpyAsync(final_T, im.final_T, N * 4, cudaMemcpyDeviceToDevice, stream), "export final_T");
+    if (n_contrib) CK(cudaMemcpyAsync(n_contrib, im.n_contrib, N * 4, cudaMemcpyDeviceToDevice, stream), "export n_contrib");
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,187 @@
+// Shared device/host definitions for libgsvc_rast.so (sm_100a).
+// Layout of the three scratch buffers, the by-value kernel parameter block, and small helpers.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "../../include/gsvc_rast.h"
+
+namespace gsvc {
+
+constexpr int TILE = GSVC_RAST_TILE;          // 16x16 pixel tiles
+constexpr int TILE_PIX = TILE * TILE;
+constexpr float ALPHA_MIN = 1.0f / 255.0f;    // Appendix A.3
+constexpr float ALPHA_MAX = 0.99f;
+constexpr float T_STOP = 0.0001f;
+constexpr float LOWPASS = 0.3f;               // U5
+
+// Settings as the kernels see them (passed by value in the launch parameters).
+struct DevSettings {
+    int W, H, gx, gy;
+    float x_min, y_min, scale, threshold, scale_modifier;
+    const float* bg;
+    const float* V;
+    long long vs_r, vs_c;   // strides of the logical V[r][c] (renderer.py:77 passes a permuted view)
+    int sh_degree, sh_M;
+    float campos[3];
+};
+
+// ---- per-Gaussian state ("geom") -------------------------------------------------------------
+//  feat0 = (pix.x, pix.y, conic.A, conic.B)   feat1 = (conic.C, opacity, r, g)
+//  feat2 = (b, view depth, hx, hy)  with (hx,hy) the half extents of the alpha >= 1/255 ellipse's
+//  bounding box (exact-culling aid; 0 when the Gaussian can never reach 1/255)
+//  rect  = tile rectangle (minx, miny, maxx, maxy), max exclusive; all-zero when culled
+struct GeomView {
+    float4* feat0;
+    float4* feat1;
+    float4* feat2;
+    ushort4* rect;
+    uint8_t* clamped;  // [P,3], SH clamp flags (only when shs are given)
+};
+
+// ---- per-tile / per-pixel state ("image") -----------------------------------------------------
+struct ImageHeader {
+    unsigned long long num_rendered;  // R = sum of tile counts
+    unsigned int overflow;            // set by the scatter kernel when capacity was exceeded
+    unsigned int pad[29];
+};
+struct ImageView {
+    ImageHeader* hdr;
+    unsigned int* tile_count;   // [T] instances per tile (atomics in preprocess)
+    unsigned int* tile_offset;  // [T] exclusive scan of tile_count
+    unsigned int* tile_cursor;  // [T] scatter cursors
+    uint2* ranges;              // [T] (start,end) — (0,0) for untouched tiles, as identifyTileRanges leaves them
+    float* final_T;             // [H*W]
+    unsigned int* n_contrib;    // [H*W]
+};
+
+// ---- per-instance state ("binning") -----------------------------------------------------------
+struct BinView {
+    unsigned long long* inst;   // [cap] unsorted (depth_key << 32 | gaussian id), grouped by tile
+    unsigned int* point_list;   // [cap] sorted Gaussian ids
+    unsigned int* depth_keys;   // [cap] sorted depth keys (for export_keys)
+};
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+template <typename T>
+__host__ __device__ inline T* carve(char*& p, size_t count)
+{
+    T* r = reinterpret_cast<T*>(p);
+    p += align_up(count * sizeof(T), 256);
+    return r;
+}
+
+inline GeomView geom_view(void* buf, int P, int sh_M)
+{
+    char* p = static_cast<char*>(buf);
+    GeomView g;
+    g.feat0 = carve<float4>(p, P);
+    g.feat1 = carve<float4>(p, P);
+    g.feat2 = carve<float4>(p, P);
+    g.rect = carve<ushort4>(p, P);
+    g.clamped = sh_M > 0 ? carve<uint8_t>(p, (size_t)P * 3) : nullptr;
+    return g;
+}
+inline size_t geom_bytes(int P, int sh_M)
+{
+    char* p = nullptr;
+    carve<float4>(p, P); carve<float4>(p, P); carve<float4>(p, P); carve<ushort4>(p, P);
+    if (sh_M > 0) carve<uint8_t>(p, (size_t)P * 3);
+    return (size_t)p + 256;
+}
+inline ImageView image_view(void* buf, int W, int H)
+{
+    char* p = static_cast<char*>(buf);
+    size_t T = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+    size_t N = (size_t)W * H;
+    ImageView v;
+    v.hdr = carve<ImageHeader>(p, 1);
+    v.tile_count = carve<unsigned int>(p, T);
+    v.tile_offset = carve<unsigned int>(p, T);
+    v.tile_cursor = carve<unsigned int>(p, T);
+    v.ranges = carve<uint2>(p, T);
+    v.final_T = carve<float>(p, N);
+    v.n_contrib = carve<unsigned int>(p, N);
+    return v;
+}
+inline size_t image_bytes(int W, int H)
+{
+    char* p = nullptr;
+    size_t T = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+    size_t N = (size_t)W * H;
+    carve<ImageHeader>(p, 1); carve<unsigned int>(p, T); carve<unsigned int>(p, T); carve<unsigned int>(p, T);
+    carve<uint2>(p, T); carve<float>(p, N); carve<unsigned int>(p, N);
+    return (size_t)p + 256;
+}
+inline BinView bin_view(void* buf, long long cap)
+{
+    char* p = static_cast<char*>(buf);
+    BinView b;
+    b.inst = carve<unsigned long long>(p, (size_t)cap);
+    b.point_list = carve<unsigned int>(p, (size_t)cap);
+    b.depth_keys = carve<unsigned int>(p, (size_t)cap);
+    return b;
+}
+inline size_t bin_bytes(long long cap)
+{
+    char* p = nullptr;
+    carve<unsigned long long>(p, (size_t)cap); carve<unsigned int>(p, (size_t)cap); carve<unsigned int>(p, (size_t)cap);
+    return (size_t)p + 256;
+}
+
+// Per-Gaussian gradient accumulators written by the blend backward (3 float4 per Gaussian):
+//  acc0 = (dL/dpix.x, dL/dpix.y, dL/dA, dL/dB)  acc1 = (dL/dC, dL/dopacity, dL/dr, dL/dg)  acc2 = (dL/db,0,0,0)
+inline size_t bwd_scratch_bytes(int P) { return align_up((size_t)P * 48, 256) + 256; }
+
+// U2: order-preserving float -> uint32 (ascending key == ascending view depth, negatives included)
+__host__ __device__ inline unsigned int ordered_u32(float z)
+{
+#ifdef __CUDA_ARCH__
+    unsigned int u = __float_as_uint(z);
+#else
+    unsigned int u; memcpy(&u, &z, 4);
+#endif
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// ---- launch stages implemented in the .cu files ------------------------------------------------
+struct PreInputs {
+    int P;
+    const float* means3D;
+    const float* shs;
+    const float* colors_precomp;
+    const float* opacities;
+    const float* scales;
+    const float* rotations;
+    const float* cov3D_precomp;
+};
+
+cudaError_t launch_visible_filter(const DevSettings& s, const PreInputs& in, int32_t* radii, cudaStream_t st);
+cudaError_t launch_preprocess(const DevSettings& s, const PreInputs& in, int32_t* radii, GeomView g, ImageView im,
+                              cudaStream_t st);
+cudaError_t launch_tile_scan(const DevSettings& s, ImageView im, cudaStream_t st);
+cudaError_t launch_scatter(const DevSettings& s, int P, GeomView g, ImageView im, BinView b, long long cap,
+                           cudaStream_t st);
+cudaError_t launch_sort_tiles(const DevSettings& s, ImageView im, BinView b, long long cap, cudaStream_t st);
+cudaError_t launch_render_forward(const DevSettings& s, GeomView g, ImageView im, BinView b, long long cap,
+                                  float* out_color, cudaStream_t st);
+cudaError_t launch_render_backward(const DevSettings& s, int P, GeomView g, ImageView im, BinView b,
+                                   const float* dL_dout, float4* acc, cudaStream_t st);
+struct BwdOutputs {
+    float* dL_dmeans3D; float* dL_dmeans2D; float* dL_dcolors; float* dL_dopacities;
+    float* dL_dscales; float* dL_drotations; float* dL_dcov3D; float* dL_dshs;
+};
+cudaError_t launch_preprocess_backward(const DevSettings& s, const PreInputs& in, const int32_t* radii, GeomView g,
+                                       const float4* acc, BwdOutputs out, cudaStream_t st);
+cudaError_t launch_export_keys(const DevSettings& s, ImageView im, BinView b, long long R,
+                               unsigned long long* sorted_keys, unsigned int* point_list, unsigned int* ranges,
+                               cudaStream_t st);
+cudaError_t launch_export_geom(int P, GeomView g, float* depth, float* xy, float* conic_opacity, float* rgb,
+                               int32_t* rect, cudaStream_t st);
+
+void count_launch(int n = 1);
+
+}  // namespace gsvc

@@ -1,0 +1,215 @@
+// Kernel (1)/(1'): per-Gaussian preprocess for the orthographic TSW camera (SURVEY.md Appendix A.1;
+// call sites /root/reference/ortho_gaussian_renderer/renderer.py:90-98 and preprocess.py:99-104).
+//
+// THIS TRANSLATION UNIT IS COMPILED WITH -fmad=false: every product and sum below rounds
+// separately, in the written order, so radii / tile rectangles / depth keys — the integers the
+// binning stage is built from — are reproducible bit-for-bit by a scalar fp32 CPU restatement.
+// The kernel is a pure stream (56 B in, <= 60 B out per Gaussian): HBM-bound, FMA fusion buys nothing.
+#include "common.cuh"
+
+namespace gsvc {
+
+__device__ __forceinline__ float ldV(const DevSettings& s, int r, int c) { return __ldg(s.V + r * s.vs_r + c * s.vs_c); }
+
+// /root/reference/utils/sh_utils.py:26-43
+__device__ const float SH_C0 = 0.28209479177387814f;
+__device__ const float SH_C1 = 0.4886025119029199f;
+__device__ const float SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                   -1.0925484305920792f, 0.5462742152960396f};
+__device__ const float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                   0.3731763325901154f, -0.4570457994644658f, 1.445305721320277f,
+                                   -0.5900435899266435f};
+
+// Quaternion (r,x,y,z) -> rotation, convention of /root/reference/utils/general_utils.py:98-119,
+// used as given (callers normalise: guassian.py:287).
+__device__ __forceinline__ void quat_to_rot(const float4 q, float R[9])
+{
+    const float r = q.x, x = q.y, y = q.z, z = q.w;
+    R[0] = 1.f - 2.f * (y * y + z * z);
+    R[1] = 2.f * (x * y - r * z);
+    R[2] = 2.f * (x * z + r * y);
+    R[3] = 2.f * (x * y + r * z);
+    R[4] = 1.f - 2.f * (x * x + z * z);
+    R[5] = 2.f * (y * z - r * x);
+    R[6] = 2.f * (x * z - r * y);
+    R[7] = 2.f * (y * z + r * x);
+    R[8] = 1.f - 2.f * (x * x + y * y);
+}
+
+__device__ __forceinline__ void cov3d_from_scale_rot(const float* s3, float mod, const float4 q, float cov[6])
+{
+    float R[9], M[9];
+    quat_to_rot(q, R);
+    const float sx = mod * s3[0], sy = mod * s3[1], sz = mod * s3[2];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        M[3 * i + 0] = R[3 * i + 0] * sx;
+        M[3 * i + 1] = R[3 * i + 1] * sy;
+        M[3 * i + 2] = R[3 * i + 2] * sz;
+    }
+    cov[0] = M[0] * M[0] + M[1] * M[1] + M[2] * M[2];
+    cov[1] = M[0] * M[3] + M[1] * M[4] + M[2] * M[5];
+    cov[2] = M[0] * M[6] + M[1] * M[7] + M[2] * M[8];
+    cov[3] = M[3] * M[3] + M[4] * M[4] + M[5] * M[5];
+    cov[4] = M[3] * M[6] + M[4] * M[7] + M[5] * M[8];
+    cov[5] = M[6] * M[6] + M[7] * M[7] + M[8] * M[8];
+}
+
+// cov2D = scale^2 (W Sigma W^T)[0:2,0:2] + 0.3 I  — the orthographic Jacobian is scale*[I2|0] (no perspective term)
+__device__ __forceinline__ void cov2d_ortho(const float cov[6], const float w0[3], const float w1[3], float scale,
+                                            float& a, float& b, float& c)
+{
+    const float u00 = cov[0] * w0[0] + cov[1] * w0[1] + cov[2] * w0[2];
+    const float u01 = cov[1] * w0[0] + cov[3] * w0[1] + cov[4] * w0[2];
+    const float u02 = cov[2] * w0[0] + cov[4] * w0[1] + cov[5] * w0[2];
+    const float u10 = cov[0] * w1[0] + cov[1] * w1[1] + cov[2] * w1[2];
+    const float u11 = cov[1] * w1[0] + cov[3] * w1[1] + cov[4] * w1[2];
+    const float u12 = cov[2] * w1[0] + cov[4] * w1[1] + cov[5] * w1[2];
+    const float s2 = scale * scale;
+    a = s2 * (w0[0] * u00 + w0[1] * u01 + w0[2] * u02) + LOWPASS;
+    b = s2 * (w0[0] * u10 + w0[1] * u11 + w0[2] * u12);
+    c = s2 * (w1[0] * u10 + w1[1] * u11 + w1[2] * u12) + LOWPASS;
+}
+
+__device__ __forceinline__ void sh_to_rgb(int deg, const float* sh, const float p[3], const float campos[3],
+                                          float rgb[3], uint8_t clamped[3])
+{
+    const float dx = p[0] - campos[0], dy = p[1] - campos[1], dz = p[2] - campos[2];
+    const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+    const float x = dx * inv, y = dy * inv, z = dz * inv;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        float r = SH_C0 * sh[0 * 3 + c];
+        if (deg > 0) {
+            r = r - SH_C1 * y * sh[1 * 3 + c] + SH_C1 * z * sh[2 * 3 + c] - SH_C1 * x * sh[3 * 3 + c];
+            if (deg > 1) {
+                const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+                r = r + SH_C2[0] * xy * sh[4 * 3 + c] + SH_C2[1] * yz * sh[5 * 3 + c] +
+                    SH_C2[2] * (2.0f * zz - xx - yy) * sh[6 * 3 + c] + SH_C2[3] * xz * sh[7 * 3 + c] +
+                    SH_C2[4] * (xx - yy) * sh[8 * 3 + c];
+                if (deg > 2) {
+                    r = r + SH_C3[0] * y * (3.0f * xx - yy) * sh[9 * 3 + c] + SH_C3[1] * xy * z * sh[10 * 3 + c] +
+                        SH_C3[2] * y * (4.0f * zz - xx - yy) * sh[11 * 3 + c] +
+                        SH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh[12 * 3 + c] +
+                        SH_C3[4] * x * (4.0f * zz - xx - yy) * sh[13 * 3 + c] +
+                        SH_C3[5] * z * (xx - yy) * sh[14 * 3 + c] + SH_C3[6] * x * (xx - 3.0f * yy) * sh[15 * 3 + c];
+                }
+            }
+        }
+        r += 0.5f;
+        clamped[c] = (r < 0.0f);
+        rgb[c] = r < 0.0f ? 0.0f : r;
+    }
+}
+
+// FILTER = true: visible_filter (radii only).  FILTER = false: full preprocess + per-tile instance counting.
+template <bool FILTER>
+__global__ void __launch_bounds__(256) preprocess_kernel(DevSettings s, PreInputs in, int32_t* __restrict__ radii,
+                                                         GeomView geo, unsigned int* __restrict__ tile_count)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= in.P) return;
+
+    const float p[3] = {__ldg(in.means3D + 3 * g), __ldg(in.means3D + 3 * g + 1), __ldg(in.means3D + 3 * g + 2)};
+    const float w0[3] = {ldV(s, 0, 0), ldV(s, 0, 1), ldV(s, 0, 2)};
+    const float w1[3] = {ldV(s, 1, 0), ldV(s, 1, 1), ldV(s, 1, 2)};
+    const float vx = w0[0] * p[0] + w0[1] * p[1] + w0[2] * p[2] + ldV(s, 0, 3);
+    const float vy = w1[0] * p[0] + w1[1] * p[1] + w1[2] * p[2] + ldV(s, 1, 3);
+    const float vz = ldV(s, 2, 0) * p[0] + ldV(s, 2, 1) * p[1] + ldV(s, 2, 2) * p[2] + ldV(s, 2, 3);
+
+    int radius = 0;
+    int rminx = 0, rminy = 0, rmaxx = 0, rmaxy = 0;
+    float a = 0.f, b = 0.f, c = 0.f, det = 0.f, px = 0.f, py = 0.f;
+    // U6: TSW slab — keep |z_view| <= threshold (preprocess.py:109-116)
+    bool ok = !(fabsf(vz) > s.threshold);
+    if (ok) {
+        float cov[6];
+        if (in.cov3D_precomp) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) cov[k] = __ldg(in.cov3D_precomp + 6 * (size_t)g + k);
+        } else {
+            const float sc[3] = {__ldg(in.scales + 3 * g), __ldg(in.scales + 3 * g + 1), __ldg(in.scales + 3 * g + 2)};
+            const float4 q = __ldg(reinterpret_cast<const float4*>(in.rotations) + g);
+            cov3d_from_scale_rot(sc, s.scale_modifier, q, cov);
+        }
+        cov2d_ortho(cov, w0, w1, s.scale, a, b, c);
+        det = a * c - b * b;
+        ok = (det != 0.0f);
+    }
+    if (ok) {
+        const float mid = 0.5f * (a + c);
+        const float lam = mid + sqrtf(fmaxf(0.1f, mid * mid - det));
+        const float rad_f = ceilf(3.f * sqrtf(lam));
+        radius = (int)rad_f;
+        px = (vx - s.x_min) * s.scale - 0.5f;  // U1
+        py = (vy - s.y_min) * s.scale - 0.5f;
+        const float fgx = (float)s.gx, fgy = (float)s.gy, ft = (float)TILE;
+        rminx = (int)fminf(fgx, fmaxf(0.f, truncf((px - rad_f) / ft)));
+        rminy = (int)fminf(fgy, fmaxf(0.f, truncf((py - rad_f) / ft)));
+        rmaxx = (int)fminf(fgx, fmaxf(0.f, truncf((px + rad_f + (float)(TILE - 1)) / ft)));
+        rmaxy = (int)fminf(fgy, fmaxf(0.f, truncf((py + rad_f + (float)(TILE - 1)) / ft)));
+        ok = (rmaxx - rminx) * (rmaxy - rminy) > 0;
+    }
+    radii[g] = ok ? radius : 0;
+    if (FILTER) return;
+
+    if (!ok) {
+        geo.rect[g] = make_ushort4(0, 0, 0, 0);
+        return;
+    }
+    const float det_inv = 1.f / det;
+    const float cA = c * det_inv, cB = -b * det_inv, cC = a * det_inv;
+    const float op = __ldg(in.opacities + g);
+    float rgb[3];
+    if (in.colors_precomp) {
+        rgb[0] = __ldg(in.colors_precomp + 3 * g);
+        rgb[1] = __ldg(in.colors_precomp + 3 * g + 1);
+        rgb[2] = __ldg(in.colors_precomp + 3 * g + 2);
+    } else {
+        uint8_t cl[3];
+        sh_to_rgb(s.sh_degree, in.shs + (size_t)g * s.sh_M * 3, p, s.campos, rgb, cl);
+        geo.clamped[3 * (size_t)g] = cl[0];
+        geo.clamped[3 * (size_t)g + 1] = cl[1];
+        geo.clamped[3 * (size_t)g + 2] = cl[2];
+    }
+    // Exact-culling aid: alpha = op*exp(power) >= 1/255  <=>  1/2 d^T Q d <= tau, tau = ln(255 op).  The ellipse's
+    // axis-aligned half extents are sqrt(2 tau a), sqrt(2 tau c) (cov2D = Q^-1).  Inflated so that fp32 rounding
+    // in the blend kernels can never make a culled pixel pass the 1/255 test.
+    float hx = 0.f, hy = 0.f;
+    const float tau = logf(255.0f * op);
+    if (tau > 0.f) {
+        const float t2 = 2.0f * tau * 1.0001f + 1e-4f;
+        hx = sqrtf(t2 * a) * 1.0001f + 1e-3f;
+        hy = sqrtf(t2 * c) * 1.0001f + 1e-3f;
+    }
+    geo.feat0[g] = make_float4(px, py, cA, cB);
+    geo.feat1[g] = make_float4(cC, op, rgb[0], rgb[1]);
+    geo.feat2[g] = make_float4(rgb[2], vz, hx, hy);
+    geo.rect[g] = make_ushort4((unsigned short)rminx, (unsigned short)rminy, (unsigned short)rmaxx,
+                               (unsigned short)rmaxy);
+    for (int ty = rminy; ty < rmaxy; ty++)
+        for (int tx = rminx; tx < rmaxx; tx++) atomicAdd(tile_count + ty * s.gx + tx, 1u);
+}
+
+cudaError_t launch_visible_filter(const DevSettings& s, const PreInputs& in, int32_t* radii, cudaStream_t st)
+{
+    if (in.P <= 0) return cudaSuccess;
+    GeomView none{};
+    preprocess_kernel<true><<<(in.P + 255) / 256, 256, 0, st>>>(s, in, radii, none, nullptr);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_preprocess(const DevSettings& s, const PreInputs& in, int32_t* radii, GeomView g, ImageView im,
+                              cudaStream_t st)
+{
+    const size_t T = (size_t)s.gx * s.gy;
+    cudaError_t e = cudaMemsetAsync(im.tile_count, 0, T * sizeof(unsigned int), st);
+    if (e != cudaSuccess) return e;
+    if (in.P <= 0) return cudaSuccess;
+    preprocess_kernel<false><<<(in.P + 255) / 256, 256, 0, st>>>(s, in, radii, g, im.tile_count);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace gsvc

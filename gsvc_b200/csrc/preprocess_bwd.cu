@@ -1,0 +1,224 @@
+// Kernel (4'): per-Gaussian backward (second half).
+// (dL/dpix, dL/dconic, dL/dopacity, dL/drgb) accumulated by the blend backward  →
+// dL/dmeans3D, means2D.grad, dL/dscales, dL/drotations | dL/dcov3D, dL/dcolors | dL/dshs, dL/dopacities.
+// Under the orthographic camera the pixel position enters nothing but `pix`, so unlike the
+// perspective rasterizer there is no mean → cov2D term.
+// Pure stream over P Gaussians: HBM-bound (reads 4 P + ~100 V, writes 68 P bytes).
+#include "common.cuh"
+
+namespace gsvc {
+
+__device__ __forceinline__ float ldVb(const DevSettings& s, int r, int c) { return __ldg(s.V + r * s.vs_r + c * s.vs_c); }
+
+__constant__ float B_SH_C0 = 0.28209479177387814f;
+__constant__ float B_SH_C1 = 0.4886025119029199f;
+__constant__ float B_SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                 -1.0925484305920792f, 0.5462742152960396f};
+__constant__ float B_SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                 0.3731763325901154f, -0.4570457994644658f, 1.445305721320277f,
+                                 -0.5900435899266435f};
+
+// SH backward: basis derivatives of /root/reference/utils/sh_utils.py:57-110 w.r.t. coefficients and direction.
+__device__ void sh_backward(int deg, int M, const float* sh, float* dsh, const float p[3], const float campos[3],
+                            const float dL[3], float dmean[3])
+{
+    const float dxv = p[0] - campos[0], dyv = p[1] - campos[1], dzv = p[2] - campos[2];
+    const float len = sqrtf(dxv * dxv + dyv * dyv + dzv * dzv);
+    const float x = dxv / len, y = dyv / len, z = dzv / len;
+    float ddx = 0.f, ddy = 0.f, ddz = 0.f;
+    for (int c = 0; c < 3; c++) {
+        const float g = dL[c];
+        float rx = 0.f, ry = 0.f, rz = 0.f;
+        dsh[0 * 3 + c] = B_SH_C0 * g;
+        if (deg > 0) {
+            dsh[1 * 3 + c] = -B_SH_C1 * y * g;
+            dsh[2 * 3 + c] = B_SH_C1 * z * g;
+            dsh[3 * 3 + c] = -B_SH_C1 * x * g;
+            rx = -B_SH_C1 * sh[3 * 3 + c];
+            ry = -B_SH_C1 * sh[1 * 3 + c];
+            rz = B_SH_C1 * sh[2 * 3 + c];
+            if (deg > 1) {
+                const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+                dsh[4 * 3 + c] = B_SH_C2[0] * xy * g;
+                dsh[5 * 3 + c] = B_SH_C2[1] * yz * g;
+                dsh[6 * 3 + c] = B_SH_C2[2] * (2.f * zz - xx - yy) * g;
+                dsh[7 * 3 + c] = B_SH_C2[3] * xz * g;
+                dsh[8 * 3 + c] = B_SH_C2[4] * (xx - yy) * g;
+                rx += B_SH_C2[0] * y * sh[4 * 3 + c] + B_SH_C2[2] * 2.f * -x * sh[6 * 3 + c] +
+                      B_SH_C2[3] * z * sh[7 * 3 + c] + B_SH_C2[4] * 2.f * x * sh[8 * 3 + c];
+                ry += B_SH_C2[0] * x * sh[4 * 3 + c] + B_SH_C2[1] * z * sh[5 * 3 + c] +
+                      B_SH_C2[2] * 2.f * -y * sh[6 * 3 + c] + B_SH_C2[4] * 2.f * -y * sh[8 * 3 + c];
+                rz += B_SH_C2[1] * y * sh[5 * 3 + c] + B_SH_C2[2] * 4.f * z * sh[6 * 3 + c] +
+                      B_SH_C2[3] * x * sh[7 * 3 + c];
+                if (deg > 2) {
+                    dsh[9 * 3 + c] = B_SH_C3[0] * y * (3.f * xx - yy) * g;
+                    dsh[10 * 3 + c] = B_SH_C3[1] * xy * z * g;
+                    dsh[11 * 3 + c] = B_SH_C3[2] * y * (4.f * zz - xx - yy) * g;
+                    dsh[12 * 3 + c] = B_SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy) * g;
+                    dsh[13 * 3 + c] = B_SH_C3[4] * x * (4.f * zz - xx - yy) * g;
+                    dsh[14 * 3 + c] = B_SH_C3[5] * z * (xx - yy) * g;
+                    dsh[15 * 3 + c] = B_SH_C3[6] * x * (xx - 3.f * yy) * g;
+                    rx += B_SH_C3[0] * sh[9 * 3 + c] * 6.f * xy + B_SH_C3[1] * sh[10 * 3 + c] * yz +
+                          B_SH_C3[2] * sh[11 * 3 + c] * -2.f * xy + B_SH_C3[3] * sh[12 * 3 + c] * -6.f * xz +
+                          B_SH_C3[4] * sh[13 * 3 + c] * (-3.f * xx + 4.f * zz - yy) +
+                          B_SH_C3[5] * sh[14 * 3 + c] * 2.f * xz + B_SH_C3[6] * sh[15 * 3 + c] * 3.f * (xx - yy);
+                    ry += B_SH_C3[0] * sh[9 * 3 + c] * 3.f * (xx - yy) + B_SH_C3[1] * sh[10 * 3 + c] * xz +
+                          B_SH_C3[2] * sh[11 * 3 + c] * (-3.f * yy + 4.f * zz - xx) +
+                          B_SH_C3[3] * sh[12 * 3 + c] * -6.f * yz + B_SH_C3[4] * sh[13 * 3 + c] * -2.f * xy +
+                          B_SH_C3[5] * sh[14 * 3 + c] * -2.f * yz + B_SH_C3[6] * sh[15 * 3 + c] * -6.f * xy;
+                    rz += B_SH_C3[1] * sh[10 * 3 + c] * xy + B_SH_C3[2] * sh[11 * 3 + c] * 8.f * yz +
+                          B_SH_C3[3] * sh[12 * 3 + c] * 3.f * (2.f * zz - xx - yy) +
+                          B_SH_C3[4] * sh[13 * 3 + c] * 8.f * xz + B_SH_C3[5] * sh[14 * 3 + c] * (xx - yy);
+                }
+            }
+        }
+        for (int k = (deg + 1) * (deg + 1); k < M; k++) dsh[k * 3 + c] = 0.f;
+        ddx += rx * g; ddy += ry * g; ddz += rz * g;
+    }
+    const float dot = x * ddx + y * ddy + z * ddz;  // through dir = d / |d|
+    dmean[0] += (ddx - x * dot) / len;
+    dmean[1] += (ddy - y * dot) / len;
+    dmean[2] += (ddz - z * dot) / len;
+}
+
+__global__ void __launch_bounds__(256) preprocess_backward_kernel(DevSettings s, PreInputs in,
+                                                                  const int32_t* __restrict__ radii, GeomView geo,
+                                                                  const float4* __restrict__ acc, BwdOutputs out)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= in.P) return;
+    const bool vis = radii[g] > 0;
+
+    float dmean[3] = {0.f, 0.f, 0.f}, dm2[2] = {0.f, 0.f}, dcol[3] = {0.f, 0.f, 0.f}, dop = 0.f;
+    float dsc[3] = {0.f, 0.f, 0.f}, drot[4] = {0.f, 0.f, 0.f, 0.f}, dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+
+    if (vis) {
+        const float4 a0 = acc[3 * (size_t)g], a1 = acc[3 * (size_t)g + 1], a2 = acc[3 * (size_t)g + 2];
+        const float gpx = a0.x, gpy = a0.y, gA = a0.z, gB = a0.w, gC = a1.x;
+        dop = a1.y;
+        dcol[0] = a1.z; dcol[1] = a1.w; dcol[2] = a2.x;
+        const float w0[3] = {ldVb(s, 0, 0), ldVb(s, 0, 1), ldVb(s, 0, 2)};
+        const float w1[3] = {ldVb(s, 1, 0), ldVb(s, 1, 1), ldVb(s, 1, 2)};
+        const float p[3] = {in.means3D[3 * g], in.means3D[3 * g + 1], in.means3D[3 * g + 2]};
+
+        if (in.shs && out.dL_dshs) {
+            const uint8_t* cl = geo.clamped + 3 * (size_t)g;
+            const float dL[3] = {cl[0] ? 0.f : dcol[0], cl[1] ? 0.f : dcol[1], cl[2] ? 0.f : dcol[2]};
+            sh_backward(s.sh_degree, s.sh_M, in.shs + (size_t)g * s.sh_M * 3, out.dL_dshs + (size_t)g * s.sh_M * 3, p,
+                        s.campos, dL, dmean);
+        }
+        // pix = (V[:2,:3] p + V[:2,3] - min) * scale - 0.5
+#pragma unroll
+        for (int k = 0; k < 3; k++) dmean[k] += s.scale * (w0[k] * gpx + w1[k] * gpy);
+        dm2[0] = gpx * 0.5f * (float)s.W;  // U3
+        dm2[1] = gpy * 0.5f * (float)s.H;
+
+        // forward recomputation of Sigma and cov2D
+        float cov[6], R[9], sv[3] = {0.f, 0.f, 0.f};
+        if (in.cov3D_precomp) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) cov[k] = in.cov3D_precomp[6 * (size_t)g + k];
+        } else {
+            const float4 q = reinterpret_cast<const float4*>(in.rotations)[g];
+            const float r = q.x, x = q.y, y = q.z, z = q.w;
+            R[0] = 1.f - 2.f * (y * y + z * z); R[1] = 2.f * (x * y - r * z); R[2] = 2.f * (x * z + r * y);
+            R[3] = 2.f * (x * y + r * z); R[4] = 1.f - 2.f * (x * x + z * z); R[5] = 2.f * (y * z - r * x);
+            R[6] = 2.f * (x * z - r * y); R[7] = 2.f * (y * z + r * x); R[8] = 1.f - 2.f * (x * x + y * y);
+#pragma unroll
+            for (int k = 0; k < 3; k++) sv[k] = s.scale_modifier * in.scales[3 * g + k];
+            float M[9];
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) M[3 * i + j] = R[3 * i + j] * sv[j];
+            cov[0] = M[0] * M[0] + M[1] * M[1] + M[2] * M[2];
+            cov[1] = M[0] * M[3] + M[1] * M[4] + M[2] * M[5];
+            cov[2] = M[0] * M[6] + M[1] * M[7] + M[2] * M[8];
+            cov[3] = M[3] * M[3] + M[4] * M[4] + M[5] * M[5];
+            cov[4] = M[3] * M[6] + M[4] * M[7] + M[5] * M[8];
+            cov[5] = M[6] * M[6] + M[7] * M[7] + M[8] * M[8];
+        }
+        const float u0[3] = {cov[0] * w0[0] + cov[1] * w0[1] + cov[2] * w0[2], cov[1] * w0[0] + cov[3] * w0[1] + cov[4] * w0[2],
+                             cov[2] * w0[0] + cov[4] * w0[1] + cov[5] * w0[2]};
+        const float u1[3] = {cov[0] * w1[0] + cov[1] * w1[1] + cov[2] * w1[2], cov[1] * w1[0] + cov[3] * w1[1] + cov[4] * w1[2],
+                             cov[2] * w1[0] + cov[4] * w1[1] + cov[5] * w1[2]};
+        const float s2 = s.scale * s.scale;
+        const float a = s2 * (w0[0] * u0[0] + w0[1] * u0[1] + w0[2] * u0[2]) + LOWPASS;
+        const float b = s2 * (w0[0] * u1[0] + w0[1] * u1[1] + w0[2] * u1[2]);
+        const float c = s2 * (w1[0] * u1[0] + w1[1] * u1[1] + w1[2] * u1[2]) + LOWPASS;
+        const float det = a * c - b * b;
+        const float d2 = 1.f / (det * det);
+        // conic = (c, -b, a)/det  →  cov2D entries (a, b, c)
+        float da = d2 * (-c * c * gA + b * c * gB - b * b * gC);
+        float db = d2 * (2.f * b * c * gA - (det + 2.f * b * b) * gB + 2.f * a * b * gC);
+        float dc = d2 * (-b * b * gA + a * b * gB - a * a * gC);
+        da *= s2; db *= s2; dc *= s2;
+        // G[k][l] = dL/dSigma[k][l] treating the 9 entries as independent
+        float Gm[9];
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+#pragma unroll
+            for (int l = 0; l < 3; l++) Gm[3 * k + l] = da * w0[k] * w0[l] + db * w0[k] * w1[l] + dc * w1[k] * w1[l];
+        if (in.cov3D_precomp) {
+            dcov[0] = Gm[0]; dcov[1] = Gm[1] + Gm[3]; dcov[2] = Gm[2] + Gm[6];
+            dcov[3] = Gm[4]; dcov[4] = Gm[5] + Gm[7]; dcov[5] = Gm[8];
+        } else {
+            // Sigma = M M^T, M = R diag(mod*s):  dL/dM = (G + G^T) M
+            float dM[9];
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    float t = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 3; k++) t += (Gm[3 * i + k] + Gm[3 * k + i]) * (R[3 * k + j] * sv[j]);
+                    dM[3 * i + j] = t;
+                }
+            float gR[9];
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                float t = 0.f;
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    t += dM[3 * i + j] * R[3 * i + j];
+                    gR[3 * i + j] = dM[3 * i + j] * sv[j];
+                }
+                dsc[j] = t * s.scale_modifier;
+            }
+            const float4 q = reinterpret_cast<const float4*>(in.rotations)[g];
+            const float r = q.x, x = q.y, y = q.z, z = q.w;
+            drot[0] = 2.f * (-z * gR[1] + y * gR[2] + z * gR[3] - x * gR[5] - y * gR[6] + x * gR[7]);
+            drot[1] = 2.f * (y * gR[1] + z * gR[2] + y * gR[3] - 2.f * x * gR[4] - r * gR[5] + z * gR[6] + r * gR[7] -
+                             2.f * x * gR[8]);
+            drot[2] = 2.f * (-2.f * y * gR[0] + x * gR[1] + r * gR[2] + x * gR[3] + z * gR[5] - r * gR[6] + z * gR[7] -
+                             2.f * y * gR[8]);
+            drot[3] = 2.f * (-2.f * z * gR[0] - r * gR[1] + x * gR[2] + r * gR[3] - 2.f * z * gR[4] + y * gR[5] +
+                             x * gR[6] + y * gR[7]);
+        }
+    } else if (in.shs && out.dL_dshs) {
+        float* dsh = out.dL_dshs + (size_t)g * s.sh_M * 3;
+        for (int k = 0; k < s.sh_M * 3; k++) dsh[k] = 0.f;
+    }
+
+    if (out.dL_dmeans3D) { out.dL_dmeans3D[3 * g] = dmean[0]; out.dL_dmeans3D[3 * g + 1] = dmean[1]; out.dL_dmeans3D[3 * g + 2] = dmean[2]; }
+    if (out.dL_dmeans2D) { out.dL_dmeans2D[3 * g] = dm2[0]; out.dL_dmeans2D[3 * g + 1] = dm2[1]; out.dL_dmeans2D[3 * g + 2] = 0.f; }
+    if (out.dL_dcolors) { out.dL_dcolors[3 * g] = dcol[0]; out.dL_dcolors[3 * g + 1] = dcol[1]; out.dL_dcolors[3 * g + 2] = dcol[2]; }
+    if (out.dL_dopacities) out.dL_dopacities[g] = dop;
+    if (out.dL_dscales) { out.dL_dscales[3 * g] = dsc[0]; out.dL_dscales[3 * g + 1] = dsc[1]; out.dL_dscales[3 * g + 2] = dsc[2]; }
+    if (out.dL_drotations) reinterpret_cast<float4*>(out.dL_drotations)[g] = make_float4(drot[0], drot[1], drot[2], drot[3]);
+    if (out.dL_dcov3D) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) out.dL_dcov3D[6 * (size_t)g + k] = dcov[k];
+    }
+}
+
+cudaError_t launch_preprocess_backward(const DevSettings& s, const PreInputs& in, const int32_t* radii, GeomView g,
+                                       const float4* acc, BwdOutputs out, cudaStream_t st)
+{
+    if (in.P <= 0) return cudaSuccess;
+    preprocess_backward_kernel<<<(in.P + 255) / 256, 256, 0, st>>>(s, in, radii, g, acc, out);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace gsvc

@@ -1,0 +1,350 @@
+"""Host-side mirror of the reference's rasterizer plugin interface.
+
+Drop-in for `diff_gaussian_rasterization.cuda_ortho_gaussian_rasterizer` as GSVC uses it:
+  - GaussianRasterizationSettings(...)   /root/reference/ortho_gaussian_renderer/renderer.py:63-83,
+                                         preprocess.py:58-79  (13 keyword fields)
+  - GaussianRasterizer(raster_settings)(means3D, means2D, shs, colors_precomp, opacities, scales,
+        rotations, cov3D_precomp) -> (color[3,H,W], radii[P], num_rendered)        renderer.py:85-98
+  - GaussianRasterizer.visible_filter(means3D, scales, rotations, cov3D_precomp) -> radii[P]
+                                                                                    preprocess.py:99-104
+All arithmetic happens in libgsvc_rast.so (hand-written sm_100a CUDA behind the C-ABI of
+include/gsvc_rast.h).  PyTorch only provides device memory, the current stream and autograd
+plumbing.  There is no CPU / eager fallback: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import NamedTuple, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import RasterizerError, Settings
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    x_min: float
+    y_min: float
+    scale: float
+    threshold: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+# per-device instance-capacity hint (last num_rendered seen), so that the binning buffer can be
+# sized without a mid-pipeline host synchronisation
+_capacity_hint: dict = {}
+_pinned_counter: dict = {}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _dev_f32(t: Optional[torch.Tensor], device, what: str) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if t.device != device:
+        raise RasterizerError(f"{what} is on {t.device}, expected {device} (the rasterizer has no CPU path)")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+class _NativeSettings:
+    """Builds the C struct and keeps the tensors it points into alive."""
+
+    def __init__(self, rs: GaussianRasterizationSettings, device: torch.device):
+        bg = rs.bg
+        if not isinstance(bg, torch.Tensor):
+            bg = torch.tensor(bg, dtype=torch.float32)
+        self.bg = bg.to(device=device, dtype=torch.float32).contiguous()
+        vm = rs.viewmatrix
+        if vm.device != device or vm.dtype != torch.float32:
+            vm = vm.to(device=device, dtype=torch.float32)
+        if tuple(vm.shape) != (4, 4):
+            raise RasterizerError(f"viewmatrix must be 4x4, got {tuple(vm.shape)}")
+        self.vm = vm  # strides are honoured natively: renderer.py:77 passes a permuted (non-contiguous) view
+        campos = rs.campos
+        if isinstance(campos, torch.Tensor):
+            campos = campos.detach().to("cpu", torch.float32).reshape(-1).tolist()  # frame.py:41: lives on the CPU
+        s = Settings()
+        s.image_height, s.image_width = int(rs.image_height), int(rs.image_width)
+        s.x_min, s.y_min, s.scale = float(rs.x_min), float(rs.y_min), float(rs.scale)
+        s.threshold, s.scale_modifier = float(rs.threshold), float(rs.scale_modifier)
+        s.bg = self.bg.data_ptr()
+        s.viewmatrix = self.vm.data_ptr()
+        s.vm_stride_r, s.vm_stride_c = int(self.vm.stride(0)), int(self.vm.stride(1))
+        s.sh_degree = int(rs.sh_degree)
+        s.campos[:] = [float(campos[0]), float(campos[1]), float(campos[2])]
+        s.prefiltered, s.debug = int(bool(rs.prefiltered)), int(bool(rs.debug))
+        self.c = s
+
+    @property
+    def ref(self):
+        return C.byref(self.c)
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _bytes(n: int, device) -> torch.Tensor:
+    return torch.empty(int(n), dtype=torch.uint8, device=device)
+
+
+def _pinned(device) -> torch.Tensor:
+    key = (device.index, )
+    t = _pinned_counter.get(key)
+    if t is None:
+        t = torch.zeros(1, dtype=torch.int64).pin_memory()
+        _pinned_counter[key] = t
+    return t
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RasterizerError(f"{what} must be a CUDA tensor: gsvc_b200 has no CPU fallback")
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                raster_settings):
+        L = _lib.lib()
+        _require_cuda(means3D, "means3D")
+        device = means3D.device
+        rs = raster_settings
+        with torch.cuda.device(device):
+            ns = _NativeSettings(rs, device)
+            P = int(means3D.shape[0])
+            means3D_c = _dev_f32(means3D, device, "means3D")
+            sh_c = _dev_f32(sh, device, "shs") if sh.numel() else None
+            col_c = _dev_f32(colors_precomp, device, "colors_precomp") if colors_precomp.numel() else None
+            op_c = _dev_f32(opacities, device, "opacities")
+            sc_c = _dev_f32(scales, device, "scales") if scales.numel() else None
+            rot_c = _dev_f32(rotations, device, "rotations") if rotations.numel() else None
+            cov_c = _dev_f32(cov3Ds_precomp, device, "cov3D_precomp") if cov3Ds_precomp.numel() else None
+            sh_M = int(sh_c.shape[1]) if sh_c is not None else 0
+            H, W = int(rs.image_height), int(rs.image_width)
+
+            geom = _bytes(L.gsvc_rast_geom_bytes(P, sh_M), device)
+            image = _bytes(L.gsvc_rast_image_bytes(W, H), device)
+            color = torch.empty((3, H, W), dtype=torch.float32, device=device)
+            radii = torch.empty((P,), dtype=torch.int32, device=device)
+            stream = _stream_ptr(device)
+            counter = _pinned(device)
+
+            hint = _capacity_hint.get(device.index)
+            cap = 0 if hint is None else int(hint * 1.25) + 4096
+            binning = _bytes(L.gsvc_rast_binning_bytes(cap), device) if cap > 0 else None
+            try:
+                _lib.check(L.gsvc_rast_forward_launch(
+                    ns.ref, P, sh_M, _ptr(means3D_c), _ptr(sh_c), _ptr(col_c), _ptr(op_c), _ptr(sc_c), _ptr(rot_c),
+                    _ptr(cov_c), _ptr(geom), _ptr(image), _ptr(binning), cap, _ptr(color), _ptr(radii),
+                    counter.data_ptr(), stream), "gsvc_rast_forward_launch")
+                # the reference API returns num_rendered as a Python int (renderer.py:90): one sync per call
+                torch.cuda.current_stream(device).synchronize()
+                num_rendered = int(counter[0])
+                if num_rendered > 0xFFFFFFFF:
+                    raise RasterizerError(f"num_rendered {num_rendered} exceeds 32-bit tile ranges")
+                if num_rendered > cap or cap == 0:
+                    # first call on this device, or the hint was too small: size exactly and run the
+                    # scatter / sort / blend stages on the state that is already in place
+                    cap = max(num_rendered, 1)
+                    binning = _bytes(L.gsvc_rast_binning_bytes(cap), device)
+                    _lib.check(L.gsvc_rast_forward_render(ns.ref, P, _ptr(geom), _ptr(image), _ptr(binning), cap,
+                                                          _ptr(color), stream), "gsvc_rast_forward_render")
+                _capacity_hint[device.index] = num_rendered
+            except Exception:
+                if rs.debug:
+                    torch.save((means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                                tuple(rs)), "snapshot_fw.dump")
+                    print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+                raise
+
+        ctx.raster_settings = rs
+        ctx.num_rendered = num_rendered
+        ctx.sh_M = sh_M
+        ctx.capacity = cap
+        ctx.save_for_backward(means3D_c, sh_c, col_c, sc_c, rot_c, cov_c, radii, geom, image, binning)
+        ctx.mark_non_differentiable(radii)
+        return color, radii, num_rendered
+
+    @staticmethod
+    def backward(ctx, grad_out_color, _grad_radii=None, _grad_num=None):
+        L = _lib.lib()
+        rs = ctx.raster_settings
+        means3D, sh, col, sc, rot, cov, radii, geom, image, binning = ctx.saved_tensors
+        device = means3D.device
+        P = int(means3D.shape[0])
+        with torch.cuda.device(device):
+            ns = _NativeSettings(rs, device)
+            g_out = _dev_f32(grad_out_color, device, "grad_out_color")
+            f32 = dict(dtype=torch.float32, device=device)
+            g_means3D = torch.empty((P, 3), **f32)
+            g_means2D = torch.empty((P, 3), **f32)
+            g_opac = torch.empty((P, 1), **f32)
+            g_col = torch.empty((P, 3), **f32) if col is not None else None
+            g_sh = torch.empty((P, ctx.sh_M, 3), **f32) if sh is not None else None
+            g_sc = torch.empty((P, 3), **f32) if sc is not None else None
+            g_rot = torch.empty((P, 4), **f32) if rot is not None else None
+            g_cov = torch.empty((P, 6), **f32) if cov is not None else None
+            scratch = _bytes(L.gsvc_rast_backward_scratch_bytes(P), device)
+            try:
+                _lib.check(L.gsvc_rast_backward(
+                    ns.ref, P, ctx.sh_M, ctx.capacity, _ptr(means3D), _ptr(sh), _ptr(col), _ptr(sc), _ptr(rot),
+                    _ptr(cov), _ptr(radii), _ptr(geom), _ptr(image), _ptr(binning), _ptr(scratch), _ptr(g_out),
+                    _ptr(g_means3D), _ptr(g_means2D), _ptr(g_col), _ptr(g_opac), _ptr(g_sc), _ptr(g_rot),
+                    _ptr(g_cov), _ptr(g_sh), _stream_ptr(device)), "gsvc_rast_backward")
+            except Exception:
+                if rs.debug:
+                    torch.save((means3D, sh, col, sc, rot, cov, radii, grad_out_color, tuple(rs)), "snapshot_bw.dump")
+                    print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
+                raise
+        return g_means3D, g_means2D, g_sh, g_col, g_opac, g_sc, g_rot, g_cov, None
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                        raster_settings):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                     cov3Ds_precomp, raster_settings)
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings: GaussianRasterizationSettings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def visible_filter(self, means3D, scales=None, rotations=None, cov3D_precomp=None):
+        """preprocess.py:99-104 — radii[P] int32 (> 0 where the anchor survives the TSW slab and image culls)."""
+        rs = self.raster_settings
+        if (scales is None or rotations is None) == (cov3D_precomp is None):
+            raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
+        L = _lib.lib()
+        _require_cuda(means3D, "means3D")
+        device = means3D.device
+        with torch.no_grad(), torch.cuda.device(device):
+            ns = _NativeSettings(rs, device)
+            P = int(means3D.shape[0])
+            m = _dev_f32(means3D, device, "means3D")
+            s = _dev_f32(scales, device, "scales")
+            r = _dev_f32(rotations, device, "rotations")
+            c = _dev_f32(cov3D_precomp, device, "cov3D_precomp")
+            radii = torch.empty((P,), dtype=torch.int32, device=device)
+            _lib.check(L.gsvc_rast_visible_filter(ns.ref, P, _ptr(m), _ptr(s), _ptr(r), _ptr(c), _ptr(radii),
+                                                  _stream_ptr(device)), "gsvc_rast_visible_filter")
+        return radii
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        rs = self.raster_settings
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception("Please provide excatly one of either SHs or precomputed colors!")
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
+        empty = torch.Tensor([])
+        shs = empty if shs is None else shs
+        colors_precomp = empty if colors_precomp is None else colors_precomp
+        scales = empty if scales is None else scales
+        rotations = empty if rotations is None else rotations
+        cov3D_precomp = empty if cov3D_precomp is None else cov3D_precomp
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
+                                   cov3D_precomp, rs)
+
+
+class RasterState:
+    """Test hook: re-runs a forward keeping the native state, and exports the stage outputs the
+    bit-exact parity tests compare (sorted keys, point list, tile ranges, per-Gaussian geometry)."""
+
+    def __init__(self, raster_settings, means3D, opacities, shs=None, colors_precomp=None, scales=None,
+                 rotations=None, cov3D_precomp=None, exact_capacity: bool = True):
+        L = _lib.lib()
+        _require_cuda(means3D, "means3D")
+        device = means3D.device
+        self.device, self.rs = device, raster_settings
+        with torch.no_grad(), torch.cuda.device(device):
+            self.ns = _NativeSettings(raster_settings, device)
+            self.P = P = int(means3D.shape[0])
+            t = lambda x, n: _dev_f32(x, device, n)
+            self.inputs = [t(means3D, "means3D"), t(shs, "shs"), t(colors_precomp, "colors_precomp"),
+                           t(opacities, "opacities"), t(scales, "scales"), t(rotations, "rotations"),
+                           t(cov3D_precomp, "cov3D_precomp")]
+            self.sh_M = int(shs.shape[1]) if shs is not None else 0
+            H, W = int(raster_settings.image_height), int(raster_settings.image_width)
+            self.geom = _bytes(L.gsvc_rast_geom_bytes(P, self.sh_M), device)
+            self.image = _bytes(L.gsvc_rast_image_bytes(W, H), device)
+            self.color = torch.empty((3, H, W), dtype=torch.float32, device=device)
+            self.radii = torch.empty((P,), dtype=torch.int32, device=device)
+            alloc_keep = []
+
+            def alloc(_user, which, nbytes):
+                buf = {0: self.geom, 2: self.image}.get(which)
+                if buf is None or buf.numel() < nbytes:
+                    buf = _bytes(nbytes, device)
+                alloc_keep.append((which, buf))
+                return buf.data_ptr()
+
+            cb = _lib.ALLOC_FN(alloc)
+            R = L.gsvc_rast_forward(self.ns.ref, P, self.sh_M, *[_ptr(x) for x in self.inputs], cb, None,
+                                    _ptr(self.color), _ptr(self.radii), _stream_ptr(device))
+            _lib.check(R, "gsvc_rast_forward")
+            self.num_rendered = int(R)
+            for which, buf in alloc_keep:
+                if which == 0:
+                    self.geom = buf
+                elif which == 1:
+                    self.binning = buf
+                else:
+                    self.image = buf
+            torch.cuda.current_stream(device).synchronize()
+
+    def export_keys(self):
+        L = _lib.lib()
+        R = self.num_rendered
+        H, W = int(self.rs.image_height), int(self.rs.image_width)
+        T = ((W + 15) // 16) * ((H + 15) // 16)
+        dev = self.device
+        with torch.cuda.device(dev):
+            keys = torch.zeros(max(R, 1), dtype=torch.int64, device=dev)
+            pl = torch.zeros(max(R, 1), dtype=torch.int32, device=dev)
+            ranges = torch.zeros((T, 2), dtype=torch.int32, device=dev)
+            _lib.check(L.gsvc_rast_export_keys(self.ns.ref, max(R, 1), _ptr(self.image), _ptr(self.binning), _ptr(keys),
+                                               _ptr(pl), _ptr(ranges), _stream_ptr(dev)), "gsvc_rast_export_keys")
+            torch.cuda.current_stream(dev).synchronize()
+        return keys[:R], pl[:R], ranges
+
+    def export_geom(self):
+        L = _lib.lib()
+        P, dev = self.P, self.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            out = dict(depth=torch.zeros(P, **f32), xy=torch.zeros((P, 2), **f32),
+                       conic_opacity=torch.zeros((P, 4), **f32), rgb=torch.zeros((P, 3), **f32),
+                       rect=torch.zeros((P, 4), dtype=torch.int32, device=dev))
+            _lib.check(L.gsvc_rast_export_geom(P, self.sh_M, _ptr(self.geom), _ptr(out["depth"]), _ptr(out["xy"]),
+                                               _ptr(out["conic_opacity"]), _ptr(out["rgb"]), _ptr(out["rect"]),
+                                               _stream_ptr(dev)), "gsvc_rast_export_geom")
+            torch.cuda.current_stream(dev).synchronize()
+        return out
+
+    def export_image(self):
+        L = _lib.lib()
+        H, W = int(self.rs.image_height), int(self.rs.image_width)
+        dev = self.device
+        with torch.cuda.device(dev):
+            fT = torch.zeros((H, W), dtype=torch.float32, device=dev)
+            nc = torch.zeros((H, W), dtype=torch.int32, device=dev)
+            _lib.check(L.gsvc_rast_export_image(self.ns.ref, _ptr(self.image), _ptr(fT), _ptr(nc), _stream_ptr(dev)),
+                       "gsvc_rast_export_image")
+            torch.cuda.current_stream(dev).synchronize()
+        return fT, nc

@@ -1,0 +1,154 @@
+/*
+ * gsvc_rast.h — C-ABI of libgsvc_rast.so, the B200-native (sm_100a) orthographic TSW Gaussian
+ * rasterizer that replaces GSVC's external CUDA extension
+ *   diff_gaussian_rasterization.cuda_ortho_gaussian_rasterizer
+ * (github.com/actcwlf/ortho_diff_gaussian_rasterization, /root/reference/README.md:52).
+ *
+ * The reference binds that extension at exactly two call sites:
+ *   rasterizer(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp)
+ *       /root/reference/ortho_gaussian_renderer/renderer.py:85-98      → gsvc_rast_forward* / gsvc_rast_backward
+ *   rasterizer.visible_filter(means3D, scales, rotations, cov3D_precomp)
+ *       /root/reference/ortho_gaussian_renderer/preprocess.py:99-104   → gsvc_rast_visible_filter
+ * with the settings block built at renderer.py:63-83 / preprocess.py:58-79 → gsvc_rast_settings.
+ *
+ * Conventions: plain pointers and sizes only.  Every array pointer is DEVICE memory on the current
+ * CUDA device unless its name ends in `_host`.  All float arrays are fp32, densely packed,
+ * row-major ([P,3] = 3 consecutive floats per Gaussian).  `stream` is a cudaStream_t passed as
+ * void* (NULL = legacy default stream).  Every function returns 0 (or a non-negative count) on
+ * success and a negative gsvc_rast_status on failure; gsvc_rast_last_error() then returns a
+ * thread-local message.  The library never calls cudaMalloc on these paths: scratch comes from the
+ * caller (sizes from gsvc_rast_*_bytes) so it can live in the host framework's caching allocator.
+ */
+#ifndef GSVC_RAST_H
+#define GSVC_RAST_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define GSVC_RAST_API __attribute__((visibility("default")))
+#else
+#define GSVC_RAST_API
+#endif
+
+#define GSVC_RAST_ABI_VERSION 1
+#define GSVC_RAST_TILE 16 /* tile edge in pixels; tile ids are row-major over ceil(W/16) x ceil(H/16) */
+
+typedef enum gsvc_rast_status {
+    GSVC_RAST_OK = 0,
+    GSVC_RAST_ERR_INVALID = -1,  /* bad argument (null pointer, exclusive-or rules of renderer.py:90-98 violated) */
+    GSVC_RAST_ERR_CUDA = -2,     /* a CUDA runtime call or kernel launch failed */
+    GSVC_RAST_ERR_CAPACITY = -3, /* binning buffer too small for num_rendered (retry with a larger one) */
+    GSVC_RAST_ERR_OVERFLOW = -4  /* num_rendered does not fit 32-bit tile ranges */
+} gsvc_rast_status;
+
+/* The 13 fields of GaussianRasterizationSettings (renderer.py:63-83), in the same order. */
+typedef struct gsvc_rast_settings {
+    int32_t image_height;
+    int32_t image_width;
+    float x_min;
+    float y_min;
+    float scale;
+    float threshold;          /* TSW slab half-thickness: |view z| > threshold is culled */
+    const float *bg;          /* device [3] (pipeline/train.py:328 keeps it on the GPU) */
+    float scale_modifier;
+    const float *viewmatrix;  /* device 4x4; logical V[r][c] at viewmatrix[r*vm_stride_r + c*vm_stride_c] —
+                                 the reference passes a NON-contiguous permuted tensor (renderer.py:77) */
+    int64_t vm_stride_r;
+    int64_t vm_stride_c;
+    int32_t sh_degree;
+    float campos[3];          /* host values: the reference keeps campos on the CPU (frame.py:41) */
+    int32_t prefiltered;
+    int32_t debug;            /* non-zero: synchronise and check for errors after every kernel */
+} gsvc_rast_settings;
+
+GSVC_RAST_API int gsvc_rast_abi_version(void);
+GSVC_RAST_API const char *gsvc_rast_last_error(void);
+
+/* Scratch sizes in bytes.  geom: per-Gaussian state (P Gaussians, sh_M SH coefficients or 0);
+ * image: per-tile / per-pixel state; binning: per-instance state for `capacity` tile instances. */
+GSVC_RAST_API size_t gsvc_rast_geom_bytes(int32_t P, int32_t sh_M);
+GSVC_RAST_API size_t gsvc_rast_image_bytes(int32_t image_width, int32_t image_height);
+GSVC_RAST_API size_t gsvc_rast_binning_bytes(int64_t capacity);
+GSVC_RAST_API size_t gsvc_rast_backward_scratch_bytes(int32_t P); /* per-Gaussian gradient accumulators of the blend backward */
+
+/*
+ * visible_filter (preprocess.py:99-104): radii[P] int32, 0 = culled (slab / degenerate / off-image).
+ * Exactly one of (scales, rotations) or cov3D_precomp ([P,6] xx,xy,xz,yy,yz,zz) must be non-NULL.
+ */
+GSVC_RAST_API int gsvc_rast_visible_filter(const gsvc_rast_settings *st, int32_t P, const float *means3D, const float *scales,
+                             const float *rotations, const float *cov3D_precomp, int32_t *radii, void *stream);
+
+/*
+ * Forward, launch form (no host synchronisation): preprocess → tile counting → tile scan →
+ * instance scatter → per-tile depth sort → front-to-back blend, all enqueued on `stream`.
+ * Exactly one of shs ([P,sh_M,3]) / colors_precomp ([P,3]); exactly one of (scales,rotations) /
+ * cov3D_precomp.  `binning` holds `capacity` instances; num_rendered is written asynchronously to
+ * *num_rendered_host (pinned host memory).  After synchronising, the caller MUST check
+ * *num_rendered_host <= capacity; if not, out_color is invalid and gsvc_rast_forward_render must be
+ * re-run with a larger binning buffer (geom/image state stays valid).
+ * Outputs: out_color [3,H,W], radii [P].
+ */
+GSVC_RAST_API int gsvc_rast_forward_launch(const gsvc_rast_settings *st, int32_t P, int32_t sh_M, const float *means3D,
+                             const float *shs, const float *colors_precomp, const float *opacities,
+                             const float *scales, const float *rotations, const float *cov3D_precomp,
+                             void *geom, void *image, void *binning, int64_t capacity, float *out_color,
+                             int32_t *radii, int64_t *num_rendered_host, void *stream);
+
+/* Re-run the instance scatter / sort / blend stages on existing geom+image state. */
+GSVC_RAST_API int gsvc_rast_forward_render(const gsvc_rast_settings *st, int32_t P, const void *geom, void *image, void *binning,
+                             int64_t capacity, float *out_color, void *stream);
+
+/*
+ * Forward, allocator-callback form (the shape of the upstream binding: three opaque buffers
+ * resized through a callback).  `alloc(user, which, bytes)` must return device memory of at least
+ * `bytes` (which: 0 geom, 1 binning, 2 image).  Synchronises `stream` once to size the binning
+ * buffer exactly.  Returns num_rendered (>= 0) or a negative status.
+ */
+typedef void *(*gsvc_rast_alloc_fn)(void *user, int32_t which, size_t bytes);
+GSVC_RAST_API int64_t gsvc_rast_forward(const gsvc_rast_settings *st, int32_t P, int32_t sh_M, const float *means3D,
+                          const float *shs, const float *colors_precomp, const float *opacities,
+                          const float *scales, const float *rotations, const float *cov3D_precomp,
+                          gsvc_rast_alloc_fn alloc, void *user, float *out_color, int32_t *radii, void *stream);
+
+/*
+ * Backward of the forward above.  dL_dout [3,H,W]; geom/image/binning are the buffers the forward
+ * filled; `capacity` the instance capacity the binning buffer was laid out with (the value passed to
+ * gsvc_rast_forward_launch / _render; max(num_rendered, 1) after gsvc_rast_forward).  Gradient outputs (any may be NULL when the matching input was
+ * not given): dL_dmeans3D [P,3], dL_dmeans2D [P,3] (columns 0,1 = dL/dpixel * (0.5 W, 0.5 H), column 2 = 0),
+ * dL_dcolors [P,3], dL_dopacities [P], dL_dscales [P,3], dL_drotations [P,4], dL_dcov3D [P,6],
+ * dL_dshs [P,sh_M,3].  All outputs are fully overwritten (zeros for culled Gaussians).
+ * `scratch`: gsvc_rast_backward_scratch_bytes(P) bytes of device memory (contents undefined on return).
+ */
+GSVC_RAST_API int gsvc_rast_backward(const gsvc_rast_settings *st, int32_t P, int32_t sh_M, int64_t capacity,
+                       const float *means3D, const float *shs, const float *colors_precomp, const float *scales,
+                       const float *rotations, const float *cov3D_precomp, const int32_t *radii, const void *geom,
+                       const void *image, const void *binning, void *scratch, const float *dL_dout, float *dL_dmeans3D,
+                       float *dL_dmeans2D, float *dL_dcolors, float *dL_dopacities, float *dL_dscales,
+                       float *dL_drotations, float *dL_dcov3D, float *dL_dshs, void *stream);
+
+/*
+ * Stage exports for bit-exact parity tests (not used on the hot path).
+ * keys: sorted_keys [R] = (tile << 32) | depth_key, point_list [R], ranges [T,2] (untouched tiles 0,0).
+ * geom: depth [P], xy [P,2], conic_opacity [P,4], rgb [P,3], rect [P,4] int32 (minx,miny,maxx,maxy tiles).
+ * image: final_T [H,W], n_contrib [H,W].  Any output pointer may be NULL.
+ */
+GSVC_RAST_API int gsvc_rast_export_keys(const gsvc_rast_settings *st, int64_t capacity, const void *image, const void *binning,
+                          uint64_t *sorted_keys, uint32_t *point_list, uint32_t *ranges, void *stream);
+GSVC_RAST_API int gsvc_rast_export_geom(int32_t P, int32_t sh_M, const void *geom, float *depth, float *xy, float *conic_opacity,
+                          float *rgb, int32_t *rect, void *stream);
+GSVC_RAST_API int gsvc_rast_export_image(const gsvc_rast_settings *st, const void *image, float *final_T, uint32_t *n_contrib,
+                           void *stream);
+
+/* Number of kernel launches issued by this library in the calling thread since the last reset
+ * (bench.py reports it as gpu_launches). */
+GSVC_RAST_API int64_t gsvc_rast_launch_count(int32_t reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSVC_RAST_H */
