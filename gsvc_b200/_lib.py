@@ -52,7 +52,12 @@ SIGNATURES = {
     "gsvc_rast_export_geom": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsvc_rast_export_image": (C.c_int, [_SP, _vp, _vp, _vp, _vp]),
     "gsvc_rast_launch_count": (_i64, [_i32]),
+    "gsvc_rast_stage_timing": (C.c_int, [_i32]),
+    "gsvc_rast_stage_times": (C.c_int, [C.POINTER(C.c_float)]),
 }
+
+STAGES = ("preprocess", "tile_scan", "scatter", "sort_tiles", "render_forward", "render_backward",
+          "preprocess_backward", "visible_filter")
 
 _lib = None
 
@@ -87,3 +92,14 @@ def check(rc: int, what: str):
         msg = lib().gsvc_rast_last_error().decode("utf-8", "replace")
         raise RasterizerError(f"{what} failed (status {rc}): {msg}")
     return rc
+
+
+def stage_timing(enable: bool):
+    check(lib().gsvc_rast_stage_timing(1 if enable else 0), "gsvc_rast_stage_timing")
+
+
+def stage_times() -> dict:
+    """Milliseconds per stage for the most recent call (stages that did not run are omitted)."""
+    buf = (C.c_float * len(STAGES))()
+    check(lib().gsvc_rast_stage_times(buf), "gsvc_rast_stage_times")
+    return {name: float(buf[i]) for i, name in enumerate(STAGES) if buf[i] >= 0}

@@ -1,6 +1,7 @@
 // extern "C" boundary of libgsvc_rast.so (see include/gsvc_rast.h for the contract and the
 // reference call sites each entry point replaces).  No torch types, no allocation: raw device
 // pointers, sizes and a cudaStream_t.
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -10,9 +11,24 @@
 namespace gsvc {
 
 static thread_local char g_err[512] = "";
-static thread_local long long g_launches = 0;
+// process-wide (the backward runs on PyTorch's autograd thread, not on the caller's)
+static std::atomic<long long> g_launches{0};
 
-void count_launch(int n) { g_launches += n; }
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- optional per-stage device timing (CUDA events on the launching stream) ----------------------
+enum Stage { ST_PREPROCESS = 0, ST_TILE_SCAN, ST_SCATTER, ST_SORT, ST_RENDER_FWD, ST_RENDER_BWD, ST_PREPROCESS_BWD,
+             ST_VISIBLE_FILTER, ST_COUNT };
+static std::atomic<bool> g_timing{false};
+static cudaEvent_t g_ev[ST_COUNT][2];
+static bool g_ev_made = false;
+static std::atomic<bool> g_ev_set[ST_COUNT];
+
+struct StageScope {
+    int id; cudaStream_t s;
+    StageScope(int id_, cudaStream_t s_) : id(id_), s(s_) { if (g_timing) cudaEventRecord(g_ev[id][0], s); }
+    ~StageScope() { if (g_timing) { cudaEventRecord(g_ev[id][1], s); g_ev_set[id] = true; } }
+};
 
 static int fail(int code, const char* fmt, ...)
 {
@@ -78,9 +94,9 @@ static int render_stages(const DevSettings& d, int P, GeomView g, ImageView im, 
                          float* out_color, cudaStream_t stream, bool dbg)
 {
     BinView b = bin_view(binning, cap);
-    CK(launch_scatter(d, P, g, im, b, cap, stream), "scatter");
-    CK(launch_sort_tiles(d, im, b, cap, stream), "sort_tiles");
-    CK(launch_render_forward(d, g, im, b, cap, out_color, stream), "render_forward");
+    { StageScope t(ST_SCATTER, stream); CK(launch_scatter(d, P, g, im, b, cap, stream), "scatter"); }
+    { StageScope t(ST_SORT, stream); CK(launch_sort_tiles(d, im, b, cap, stream), "sort_tiles"); }
+    { StageScope t(ST_RENDER_FWD, stream); CK(launch_render_forward(d, g, im, b, cap, out_color, stream), "render_forward"); }
     return 0;
 }
 
@@ -98,9 +114,36 @@ size_t gsvc_rast_binning_bytes(int64_t cap) { return bin_bytes(cap < 1 ? 1 : cap
 size_t gsvc_rast_backward_scratch_bytes(int32_t P) { return bwd_scratch_bytes(P < 1 ? 1 : P); }
 int64_t gsvc_rast_launch_count(int32_t reset)
 {
-    const long long v = g_launches;
-    if (reset) g_launches = 0;
-    return v;
+    return reset ? g_launches.exchange(0) : g_launches.load();
+}
+
+int gsvc_rast_stage_timing(int32_t enable)
+{
+    if (enable && !g_ev_made) {
+        for (int i = 0; i < ST_COUNT; i++)
+            for (int j = 0; j < 2; j++)
+                if (cudaEventCreate(&g_ev[i][j]) != cudaSuccess) return fail(GSVC_RAST_ERR_CUDA, "cudaEventCreate failed");
+        g_ev_made = true;
+    }
+    g_timing = enable != 0;
+    for (int i = 0; i < ST_COUNT; i++) g_ev_set[i] = false;
+    return 0;
+}
+
+int gsvc_rast_stage_times(float* ms_host)
+{
+    if (!ms_host) return fail(GSVC_RAST_ERR_INVALID, "ms_host is NULL");
+    for (int i = 0; i < ST_COUNT; i++) {
+        ms_host[i] = -1.f;
+        if (!g_ev_made || !g_ev_set[i]) continue;
+        if (cudaEventSynchronize(g_ev[i][1]) != cudaSuccess) return fail(GSVC_RAST_ERR_CUDA, "cudaEventSynchronize failed");
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, g_ev[i][0], g_ev[i][1]) != cudaSuccess)
+            return fail(GSVC_RAST_ERR_CUDA, "cudaEventElapsedTime failed");
+        ms_host[i] = ms;
+        g_ev_set[i] = false;
+    }
+    return ST_COUNT;
 }
 
 int gsvc_rast_visible_filter(const gsvc_rast_settings* st, int32_t P, const float* means3D, const float* scales,
@@ -115,7 +158,7 @@ int gsvc_rast_visible_filter(const gsvc_rast_settings* st, int32_t P, const floa
     if (P > 0 && !radii) return fail(GSVC_RAST_ERR_INVALID, "radii is NULL");
     const bool dbg = st->debug != 0;
     PreInputs in{P, means3D, nullptr, nullptr, nullptr, scales, rotations, cov3D_precomp};
-    CK(launch_visible_filter(d, in, radii, stream), "visible_filter");
+    { StageScope t(ST_VISIBLE_FILTER, stream); CK(launch_visible_filter(d, in, radii, stream), "visible_filter"); }
     return 0;
 }
 
@@ -139,8 +182,8 @@ int gsvc_rast_forward_launch(const gsvc_rast_settings* st, int32_t P, int32_t sh
     GeomView g = geom_view(geom, P < 1 ? 1 : P, d.sh_M);
     ImageView im = image_view(image, d.W, d.H);
     PreInputs in{P, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp};
-    CK(launch_preprocess(d, in, radii, g, im, stream), "preprocess");
-    CK(launch_tile_scan(d, im, stream), "tile_scan");
+    { StageScope t(ST_PREPROCESS, stream); CK(launch_preprocess(d, in, radii, g, im, stream), "preprocess"); }
+    { StageScope t(ST_TILE_SCAN, stream); CK(launch_tile_scan(d, im, stream), "tile_scan"); }
     if (num_rendered_host)
         CK(cudaMemcpyAsync(num_rendered_host, &im.hdr->num_rendered, sizeof(int64_t), cudaMemcpyDeviceToHost, stream),
            "num_rendered readback");
@@ -222,9 +265,9 @@ int gsvc_rast_backward(const gsvc_rast_settings* st, int32_t P, int32_t sh_M, in
     BinView b = bin_view(const_cast<void*>(binning), capacity);
     float4* acc = static_cast<float4*>(scratch);
     PreInputs in{P, means3D, shs, colors_precomp, nullptr, scales, rotations, cov3D_precomp};
-    CK(launch_render_backward(d, P, g, im, b, dL_dout, acc, stream), "render_backward");
+    { StageScope t(ST_RENDER_BWD, stream); CK(launch_render_backward(d, P, g, im, b, dL_dout, acc, stream), "render_backward"); }
     BwdOutputs out{dL_dmeans3D, dL_dmeans2D, dL_dcolors, dL_dopacities, dL_dscales, dL_drotations, dL_dcov3D, dL_dshs};
-    CK(launch_preprocess_backward(d, in, radii, g, acc, out, stream), "preprocess_backward");
+    { StageScope t(ST_PREPROCESS_BWD, stream); CK(launch_preprocess_backward(d, in, radii, g, acc, out, stream), "preprocess_backward"); }
     return 0;
 }
 

@@ -17,80 +17,123 @@
 namespace gsvc {
 
 // ---- exclusive scan over tiles: offsets, ranges, num_rendered; resets the scatter cursors ----------
+// One CTA: thread t owns a contiguous run of tiles, sums it (all loads in flight at once), the 1024
+// partial sums are scanned with shuffles, then the run is re-read (L1/L2 hits) and written out.
 constexpr int SCAN_THREADS = 1024;
 
-__global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(int T, ImageView im)
+__global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(int T, int items, ImageView im)
 {
     __shared__ unsigned long long warp_sums[SCAN_THREADS / 32];
-    __shared__ unsigned long long carry_s;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) carry_s = 0ull;
+    const int lo = min(T, tid * items), hi = min(T, lo + items);
+    unsigned long long sum = 0ull;
+    for (int t = lo; t < hi; t++) sum += im.tile_count[t];
+    unsigned long long v = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long o = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += o;
+    }
+    if (lane == 31) warp_sums[wid] = v;
     __syncthreads();
-    // Coalesced chunks of SCAN_THREADS tiles; the running carry makes it a full scan for any T.
-    for (int base = 0; base < T; base += SCAN_THREADS) {
-        const int t = base + tid;
-        const unsigned int c = t < T ? im.tile_count[t] : 0u;
-        unsigned long long v = c;
+    if (wid == 0) {
+        unsigned long long w = warp_sums[lane];
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const unsigned long long n = __shfl_up_sync(0xffffffffu, v, d);
-            if (lane >= d) v += n;
+            const unsigned long long o = __shfl_up_sync(0xffffffffu, w, d);
+            if (lane >= d) w += o;
         }
-        if (lane == 31) warp_sums[wid] = v;
-        __syncthreads();
-        if (wid == 0) {
-            unsigned long long w = warp_sums[lane];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const unsigned long long n = __shfl_up_sync(0xffffffffu, w, d);
-                if (lane >= d) w += n;
-            }
-            warp_sums[lane] = w;  // inclusive over warps
-        }
-        __syncthreads();
-        const unsigned long long carry = carry_s;
-        const unsigned long long incl = carry + (wid ? warp_sums[wid - 1] : 0ull) + v;
-        if (t < T) {
-            const unsigned long long excl = incl - c;
-            im.tile_offset[t] = (unsigned int)excl;
-            im.tile_cursor[t] = 0u;
-            im.ranges[t] = c ? make_uint2((unsigned int)excl, (unsigned int)incl) : make_uint2(0u, 0u);
-        }
-        __syncthreads();
-        if (tid == SCAN_THREADS - 1) carry_s = incl;
-        __syncthreads();
+        warp_sums[lane] = w;  // inclusive over warps
     }
-    if (tid == 0) {
-        im.hdr->num_rendered = carry_s;
+    __syncthreads();
+    unsigned long long run = (wid ? warp_sums[wid - 1] : 0ull) + v - sum;  // exclusive prefix of this thread's run
+    for (int t = lo; t < hi; t++) {
+        const unsigned int c = im.tile_count[t];
+        im.tile_offset[t] = (unsigned int)run;
+        im.tile_cursor[t] = 0u;
+        im.ranges[t] = c ? make_uint2((unsigned int)run, (unsigned int)(run + c)) : make_uint2(0u, 0u);
+        run += c;
+    }
+    if (tid == SCAN_THREADS - 1) {
+        im.hdr->num_rendered = warp_sums[SCAN_THREADS / 32 - 1];
         im.hdr->overflow = 0u;
     }
 }
 
 cudaError_t launch_tile_scan(const DevSettings& s, ImageView im, cudaStream_t st)
 {
-    tile_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(s.gx * s.gy, im);
+    const int T = s.gx * s.gy;
+    const int items = (T + SCAN_THREADS - 1) / SCAN_THREADS;
+    tile_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(T, items, im);
     count_launch();
     return cudaGetLastError();
 }
 
 // ---- scatter: one instance (depth_key << 32 | id) per (Gaussian, tile in rect) into its tile bucket ----
+// Slot = tile_offset + atomicAdd(cursor): the atomic's round trip (~700 cycles) is the cost, so
+//   * small rectangles (<= SCATTER_SMALL tiles, the common case) are handled by their own lane with
+//     all atomics issued before the first store (independent round trips overlap);
+//   * large rectangles (up to hundreds of tiles for a 30 px sigma) are spread over the 32 lanes of
+//     the warp, so no lane serialises a long chain.
+constexpr int SCATTER_SMALL = 8;
+
+__device__ __forceinline__ void scatter_one(int t, unsigned long long item, ImageView& im, BinView& bin,
+                                            unsigned long long cap)
+{
+    const unsigned long long slot = (unsigned long long)im.tile_offset[t] + atomicAdd(im.tile_cursor + t, 1u);
+    if (slot < cap)
+        bin.inst[slot] = item;
+    else
+        im.hdr->overflow = 1u;
+}
+
 __global__ void __launch_bounds__(256) scatter_kernel(int P, int gx, GeomView geo, ImageView im, BinView bin,
                                                       unsigned long long cap)
 {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= P) return;
-    const ushort4 r = geo.rect[g];
-    if (r.z <= r.x || r.w <= r.y) return;
-    const unsigned long long item = ((unsigned long long)ordered_u32(geo.feat2[g].y) << 32) | (unsigned int)g;
-    for (int ty = r.y; ty < r.w; ty++)
-        for (int tx = r.x; tx < r.z; tx++) {
-            const int t = ty * gx + tx;
-            const unsigned long long slot = (unsigned long long)im.tile_offset[t] + atomicAdd(im.tile_cursor + t, 1u);
-            if (slot < cap)
-                bin.inst[slot] = item;
-            else
-                im.hdr->overflow = 1u;
+    const int lane = threadIdx.x & 31;
+    ushort4 r = make_ushort4(0, 0, 0, 0);
+    if (g < P) r = geo.rect[g];
+    const int w = (int)r.z - (int)r.x, h = (int)r.w - (int)r.y;
+    const int area = (w > 0 && h > 0) ? w * h : 0;
+    unsigned long long item = 0ull;
+    if (area > 0) item = ((unsigned long long)ordered_u32(geo.feat2[g].y) << 32) | (unsigned int)g;
+
+    if (area > 0 && area <= SCATTER_SMALL) {
+        unsigned int slot[SCATTER_SMALL];
+        int tl[SCATTER_SMALL];
+#pragma unroll
+        for (int i = 0; i < SCATTER_SMALL; i++) {
+            tl[i] = -1;
+            if (i < area) {
+                const int ty = r.y + i / w, tx = r.x + i - (i / w) * w;
+                tl[i] = ty * gx + tx;
+                slot[i] = atomicAdd(im.tile_cursor + tl[i], 1u);
+            }
         }
+#pragma unroll
+        for (int i = 0; i < SCATTER_SMALL; i++) {
+            if (tl[i] >= 0) {
+                const unsigned long long sl = (unsigned long long)im.tile_offset[tl[i]] + slot[i];
+                if (sl < cap)
+                    bin.inst[sl] = item;
+                else
+                    im.hdr->overflow = 1u;
+            }
+        }
+    }
+    unsigned int big = __ballot_sync(0xffffffffu, area > SCATTER_SMALL);
+    while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const int bx = __shfl_sync(0xffffffffu, (int)r.x, src), by = __shfl_sync(0xffffffffu, (int)r.y, src);
+        const int bw = __shfl_sync(0xffffffffu, w, src), ba = __shfl_sync(0xffffffffu, area, src);
+        const unsigned long long bitem = __shfl_sync(0xffffffffu, item, src);
+        for (int i = lane; i < ba; i += 32) {
+            const int row = i / bw;
+            scatter_one((by + row) * gx + bx + (i - row * bw), bitem, im, bin, cap);
+        }
+    }
 }
 
 cudaError_t launch_scatter(const DevSettings& s, int P, GeomView g, ImageView im, BinView b, long long cap,
@@ -105,65 +148,97 @@ cudaError_t launch_scatter(const DevSettings& s, int P, GeomView g, ImageView im
 // ---- per-tile sort of the 64-bit composites -----------------------------------------------------
 // Normalised bitonic network: every compare-exchange moves the minimum to the lower index, so an
 // arbitrary length n is handled by treating indices >= n as +inf (pairs that touch them are no-ops).
-constexpr int SORT_THREADS = 128;
-constexpr int SORT_SMEM_ITEMS = 4096;  // 32 KB; longer buckets are sorted in place in global memory
+// Typical buckets hold ~100 instances: one WARP sorts one bucket in shared memory with __syncwarp
+// between stages (no block barriers, 8 buckets per CTA).  Buckets above SORT_WARP_ITEMS are sorted
+// by the whole CTA afterwards (shared memory up to SORT_SMEM_ITEMS, in place in global beyond).
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int SORT_WARP_ITEMS = 512;
+constexpr int SORT_SMEM_ITEMS = SORT_WARPS * SORT_WARP_ITEMS;  // 4096 items = 32 KB
 
-template <typename Ptr>
+template <bool BLOCK, typename Ptr>
 __device__ __forceinline__ void bitonic_sort(Ptr a, int n, int tid, int nthreads)
 {
-    int npad = 1;
-    while (npad < n) npad <<= 1;
-    const int half = npad >> 1;
-    for (int k = 2; k <= npad; k <<= 1) {
-        const int hk = k >> 1;
+    int lg = 0;
+    while ((1 << lg) < n) lg++;
+    const int half = (1 << lg) >> 1;
+    for (int p = 1; p <= lg; p++) {          // merge size k = 2^p
+        const int k = 1 << p, hk = k >> 1;
         for (int i = tid; i < half; i += nthreads) {
-            const int blk = i / hk, pos = i - blk * hk;
+            const int blk = i >> (p - 1), pos = i & (hk - 1);
             const int lo = blk * k + pos, hi = blk * k + k - 1 - pos;
             if (hi < n) {
                 const unsigned long long x = a[lo], y = a[hi];
                 if (x > y) { a[lo] = y; a[hi] = x; }
             }
         }
-        __syncthreads();
-        for (int j = k >> 2; j >= 1; j >>= 1) {
+        if (BLOCK) __syncthreads(); else __syncwarp();
+        for (int q = p - 2; q >= 0; q--) {   // half-cleaners, distance j = 2^q
+            const int j = 1 << q;
             for (int i = tid; i < half; i += nthreads) {
-                const int lo = 2 * j * (i / j) + (i % j), hi = lo + j;
+                const int lo = ((i >> q) << (q + 1)) + (i & (j - 1)), hi = lo + j;
                 if (hi < n) {
                     const unsigned long long x = a[lo], y = a[hi];
                     if (x > y) { a[lo] = y; a[hi] = x; }
                 }
             }
-            __syncthreads();
+            if (BLOCK) __syncthreads(); else __syncwarp();
         }
     }
 }
 
-__global__ void __launch_bounds__(SORT_THREADS) sort_tiles_kernel(ImageView im, BinView bin, unsigned long long cap)
+__global__ void __launch_bounds__(SORT_THREADS) sort_tiles_kernel(int T, ImageView im, BinView bin,
+                                                                  unsigned long long cap)
 {
     __shared__ unsigned long long s_items[SORT_SMEM_ITEMS];
-    const int t = blockIdx.x;
-    const uint2 rg = im.ranges[t];
-    const int n = (int)(rg.y - rg.x);
-    if (n <= 0 || (unsigned long long)rg.y > cap) return;
-    unsigned long long* src = bin.inst + rg.x;
-    const int tid = threadIdx.x;
-    if (n <= SORT_SMEM_ITEMS) {
-        for (int i = tid; i < n; i += SORT_THREADS) s_items[i] = src[i];
-        __syncthreads();
-        bitonic_sort(s_items, n, tid, SORT_THREADS);
-        for (int i = tid; i < n; i += SORT_THREADS) {
-            const unsigned long long v = s_items[i];
+    __shared__ int s_big[SORT_WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int t = blockIdx.x * SORT_WARPS + warp;
+    uint2 rg = make_uint2(0u, 0u);
+    int n = 0;
+    if (t < T) {
+        rg = im.ranges[t];
+        n = (unsigned long long)rg.y > cap ? 0 : (int)(rg.y - rg.x);
+    }
+    const bool big = n > SORT_WARP_ITEMS;
+    if (lane == 0) s_big[warp] = big ? t : -1;
+    if (!big && n > 0) {
+        unsigned long long* mine = s_items + warp * SORT_WARP_ITEMS;
+        const unsigned long long* src = bin.inst + rg.x;
+        for (int i = lane; i < n; i += 32) mine[i] = src[i];
+        __syncwarp();
+        bitonic_sort<false>(mine, n, lane, 32);
+        for (int i = lane; i < n; i += 32) {
+            const unsigned long long v = mine[i];
             bin.point_list[rg.x + i] = (unsigned int)v;
             bin.depth_keys[rg.x + i] = (unsigned int)(v >> 32);
         }
-    } else {
-        __syncthreads();
-        bitonic_sort(src, n, tid, SORT_THREADS);  // global-memory fallback (block-wide barriers order the accesses)
-        for (int i = tid; i < n; i += SORT_THREADS) {
-            const unsigned long long v = src[i];
-            bin.point_list[rg.x + i] = (unsigned int)v;
-            bin.depth_keys[rg.x + i] = (unsigned int)(v >> 32);
+    }
+    __syncthreads();
+    for (int w = 0; w < SORT_WARPS; w++) {
+        const int tb = s_big[w];
+        if (tb < 0) continue;  // block-uniform
+        const uint2 rb = im.ranges[tb];
+        const int nb = (int)(rb.y - rb.x);
+        unsigned long long* src = bin.inst + rb.x;
+        if (nb <= SORT_SMEM_ITEMS) {
+            for (int i = tid; i < nb; i += SORT_THREADS) s_items[i] = src[i];
+            __syncthreads();
+            bitonic_sort<true>(s_items, nb, tid, SORT_THREADS);
+            for (int i = tid; i < nb; i += SORT_THREADS) {
+                const unsigned long long v = s_items[i];
+                bin.point_list[rb.x + i] = (unsigned int)v;
+                bin.depth_keys[rb.x + i] = (unsigned int)(v >> 32);
+            }
+        } else {
+            bitonic_sort<true>(src, nb, tid, SORT_THREADS);  // in place in global memory; block barriers order it
+            for (int i = tid; i < nb; i += SORT_THREADS) {
+                const unsigned long long v = src[i];
+                bin.point_list[rb.x + i] = (unsigned int)v;
+                bin.depth_keys[rb.x + i] = (unsigned int)(v >> 32);
+            }
         }
+        __syncthreads();
     }
 }
 
@@ -171,7 +246,7 @@ cudaError_t launch_sort_tiles(const DevSettings& s, ImageView im, BinView b, lon
 {
     const int T = s.gx * s.gy;
     if (T <= 0) return cudaSuccess;
-    sort_tiles_kernel<<<T, SORT_THREADS, 0, st>>>(im, b, (unsigned long long)cap);
+    sort_tiles_kernel<<<(T + SORT_WARPS - 1) / SORT_WARPS, SORT_THREADS, 0, st>>>(T, im, b, (unsigned long long)cap);
     count_launch();
     return cudaGetLastError();
 }

@@ -144,7 +144,20 @@ GSVC_RAST_API int gsvc_rast_export_geom(int32_t P, int32_t sh_M, const void *geo
 GSVC_RAST_API int gsvc_rast_export_image(const gsvc_rast_settings *st, const void *image, float *final_T, uint32_t *n_contrib,
                            void *stream);
 
-/* Number of kernel launches issued by this library in the calling thread since the last reset
+/*
+ * Optional per-stage device timing (tracing aid; used by bench.py for the roofline numbers).
+ * gsvc_rast_stage_timing(1) makes every later call (any thread) bracket each stage with CUDA
+ * events on the launching stream; gsvc_rast_stage_times() waits for them and writes the last
+ * duration of each stage in milliseconds (-1 if the stage did not run since the previous query):
+ *   [0] preprocess  [1] tile_scan  [2] scatter  [3] sort_tiles  [4] render_forward
+ *   [5] render_backward  [6] preprocess_backward  [7] visible_filter
+ * Returns the number of stages (8).
+ */
+#define GSVC_RAST_NUM_STAGES 8
+GSVC_RAST_API int gsvc_rast_stage_timing(int32_t enable);
+GSVC_RAST_API int gsvc_rast_stage_times(float *ms_host);
+
+/* Number of kernel launches issued by this library (all threads) since the last reset
  * (bench.py reports it as gpu_launches). */
 GSVC_RAST_API int64_t gsvc_rast_launch_count(int32_t reset);
 

@@ -217,6 +217,8 @@ def _blend_tiles(st, tiles, ranges, point_list, pix, conic, opac, rgb, bg, dtype
 def forward(st, means3D, opacities, scales=None, rotations=None, cov3D_precomp=None, colors_precomp=None,
             shs=None, dtype=torch.float32, requires_grad=False, elem_budget=6_000_000, tile_subset=None):
     """Full forward. Returns dict(color [3,H,W] torch, radii, num_rendered, keys, point_list, ranges, leaves)."""
+    import time as _time
+    _t0 = _time.perf_counter()
     leaves = {}
 
     def leaf(name, x):
@@ -242,6 +244,7 @@ def forward(st, means3D, opacities, scales=None, rotations=None, cov3D_precomp=N
     pix = pre["pix"] + pixgrad_holder
     leaves["_pix_holder"] = pixgrad_holder
     b = bin_and_sort(st, pre)
+    t_pre = _time.perf_counter() - _t0
     W, H = int(st.image_width), int(st.image_height)
     gx, gy = (W + TILE - 1) // TILE, (H + TILE - 1) // TILE
     bg = _t(np.asarray(st.bg, dtype=np.float64), dtype)
@@ -274,7 +277,7 @@ def forward(st, means3D, opacities, scales=None, rotations=None, cov3D_precomp=N
     color = color[:, :H, :W]
     return dict(color=color, radii=pre["radii"].numpy(), num_rendered=b["R"], keys=b["keys"],
                 point_list=b["point_list"], ranges=ranges, final_T=final_T[:H, :W], n_contrib=n_contrib[:H, :W],
-                leaves=leaves, pre=pre, bin=b, settings=st)
+                leaves=leaves, pre=pre, bin=b, settings=st, t_pre=t_pre)
 
 
 def backward(fwd, dL_dout):
