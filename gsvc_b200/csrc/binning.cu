@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(int P, int gx, GeomView ge
     const int w = (int)r.z - (int)r.x, h = (int)r.w - (int)r.y;
     const int area = (w > 0 && h > 0) ? w * h : 0;
     unsigned long long item = 0ull;
-    if (area > 0) item = ((unsigned long long)ordered_u32(geo.feat2[g].y) << 32) | (unsigned int)g;
+    if (area > 0) item = ((unsigned long long)ordered_u32(geo.feat2[g].w) << 32) | (unsigned int)g;
 
     if (area > 0 && area <= SCATTER_SMALL) {
         unsigned int slot[SCATTER_SMALL];
@@ -285,13 +285,10 @@ __global__ void export_geom_kernel(int P, GeomView geo, float* depth, float* xy,
     const bool vis = r.z > r.x && r.w > r.y;
     float4 f0 = make_float4(0, 0, 0, 0), f1 = f0, f2 = f0;
     if (vis) { f0 = geo.feat0[g]; f1 = geo.feat1[g]; f2 = geo.feat2[g]; }
-    if (depth) depth[g] = f2.y;
+    if (depth) depth[g] = f2.w;
     if (xy) { xy[2 * g] = f0.x; xy[2 * g + 1] = f0.y; }
-    if (conic_opacity) {
-        conic_opacity[4 * g] = f0.z; conic_opacity[4 * g + 1] = f0.w;
-        conic_opacity[4 * g + 2] = f1.x; conic_opacity[4 * g + 3] = f1.y;
-    }
-    if (rgb) { rgb[3 * g] = f1.z; rgb[3 * g + 1] = f1.w; rgb[3 * g + 2] = f2.x; }
+    if (conic_opacity) reinterpret_cast<float4*>(conic_opacity)[g] = f1;
+    if (rgb) { rgb[3 * g] = f2.x; rgb[3 * g + 1] = f2.y; rgb[3 * g + 2] = f2.z; }
     if (rect) { rect[4 * g] = r.x; rect[4 * g + 1] = r.y; rect[4 * g + 2] = r.z; rect[4 * g + 3] = r.w; }
 }
 

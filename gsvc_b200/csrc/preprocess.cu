@@ -182,9 +182,9 @@ __global__ void __launch_bounds__(256) preprocess_kernel(DevSettings s, PreInput
         hx = sqrtf(t2 * a) * 1.0001f + 1e-3f;
         hy = sqrtf(t2 * c) * 1.0001f + 1e-3f;
     }
-    geo.feat0[g] = make_float4(px, py, cA, cB);
-    geo.feat1[g] = make_float4(cC, op, rgb[0], rgb[1]);
-    geo.feat2[g] = make_float4(rgb[2], vz, hx, hy);
+    geo.feat0[g] = make_float4(px, py, hx, hy);
+    geo.feat1[g] = make_float4(cA, cB, cC, op);
+    geo.feat2[g] = make_float4(rgb[0], rgb[1], rgb[2], vz);
     geo.rect[g] = make_ushort4((unsigned short)rminx, (unsigned short)rminy, (unsigned short)rmaxx,
                                (unsigned short)rmaxy);
     for (int ty = rminy; ty < rmaxy; ty++)

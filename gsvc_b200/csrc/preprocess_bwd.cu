@@ -113,20 +113,24 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(DevSettings s,
         dm2[0] = gpx * 0.5f * (float)s.W;  // U3
         dm2[1] = gpy * 0.5f * (float)s.H;
 
-        // forward recomputation of Sigma and cov2D
-        float cov[6], R[9], sv[3] = {0.f, 0.f, 0.f};
+        // Forward recomputation of Sigma and cov2D, then the conic -> cov2D -> Sigma -> (scale, quaternion)
+        // chain.  The chain divides by det^2 and sums terms of opposite sign, so it is evaluated in
+        // fp64 (a few hundred flops per visible Gaussian in an HBM-bound kernel: free on B200) — in
+        // fp32 the cancellation alone costs ~3e-5 relative on rotation gradients.
+        double cov[6], R[9], sv[3] = {0., 0., 0.};
+        const double W0[3] = {w0[0], w0[1], w0[2]}, W1[3] = {w1[0], w1[1], w1[2]};
         if (in.cov3D_precomp) {
 #pragma unroll
             for (int k = 0; k < 6; k++) cov[k] = in.cov3D_precomp[6 * (size_t)g + k];
         } else {
             const float4 q = reinterpret_cast<const float4*>(in.rotations)[g];
-            const float r = q.x, x = q.y, y = q.z, z = q.w;
-            R[0] = 1.f - 2.f * (y * y + z * z); R[1] = 2.f * (x * y - r * z); R[2] = 2.f * (x * z + r * y);
-            R[3] = 2.f * (x * y + r * z); R[4] = 1.f - 2.f * (x * x + z * z); R[5] = 2.f * (y * z - r * x);
-            R[6] = 2.f * (x * z - r * y); R[7] = 2.f * (y * z + r * x); R[8] = 1.f - 2.f * (x * x + y * y);
+            const double r = q.x, x = q.y, y = q.z, z = q.w;
+            R[0] = 1. - 2. * (y * y + z * z); R[1] = 2. * (x * y - r * z); R[2] = 2. * (x * z + r * y);
+            R[3] = 2. * (x * y + r * z); R[4] = 1. - 2. * (x * x + z * z); R[5] = 2. * (y * z - r * x);
+            R[6] = 2. * (x * z - r * y); R[7] = 2. * (y * z + r * x); R[8] = 1. - 2. * (x * x + y * y);
 #pragma unroll
-            for (int k = 0; k < 3; k++) sv[k] = s.scale_modifier * in.scales[3 * g + k];
-            float M[9];
+            for (int k = 0; k < 3; k++) sv[k] = (double)s.scale_modifier * (double)in.scales[3 * g + k];
+            double M[9];
 #pragma unroll
             for (int i = 0; i < 3; i++)
 #pragma unroll
@@ -138,62 +142,63 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(DevSettings s,
             cov[4] = M[3] * M[6] + M[4] * M[7] + M[5] * M[8];
             cov[5] = M[6] * M[6] + M[7] * M[7] + M[8] * M[8];
         }
-        const float u0[3] = {cov[0] * w0[0] + cov[1] * w0[1] + cov[2] * w0[2], cov[1] * w0[0] + cov[3] * w0[1] + cov[4] * w0[2],
-                             cov[2] * w0[0] + cov[4] * w0[1] + cov[5] * w0[2]};
-        const float u1[3] = {cov[0] * w1[0] + cov[1] * w1[1] + cov[2] * w1[2], cov[1] * w1[0] + cov[3] * w1[1] + cov[4] * w1[2],
-                             cov[2] * w1[0] + cov[4] * w1[1] + cov[5] * w1[2]};
-        const float s2 = s.scale * s.scale;
-        const float a = s2 * (w0[0] * u0[0] + w0[1] * u0[1] + w0[2] * u0[2]) + LOWPASS;
-        const float b = s2 * (w0[0] * u1[0] + w0[1] * u1[1] + w0[2] * u1[2]);
-        const float c = s2 * (w1[0] * u1[0] + w1[1] * u1[1] + w1[2] * u1[2]) + LOWPASS;
-        const float det = a * c - b * b;
-        const float d2 = 1.f / (det * det);
-        // conic = (c, -b, a)/det  →  cov2D entries (a, b, c)
-        float da = d2 * (-c * c * gA + b * c * gB - b * b * gC);
-        float db = d2 * (2.f * b * c * gA - (det + 2.f * b * b) * gB + 2.f * a * b * gC);
-        float dc = d2 * (-b * b * gA + a * b * gB - a * a * gC);
+        const double u0[3] = {cov[0] * W0[0] + cov[1] * W0[1] + cov[2] * W0[2], cov[1] * W0[0] + cov[3] * W0[1] + cov[4] * W0[2],
+                              cov[2] * W0[0] + cov[4] * W0[1] + cov[5] * W0[2]};
+        const double u1[3] = {cov[0] * W1[0] + cov[1] * W1[1] + cov[2] * W1[2], cov[1] * W1[0] + cov[3] * W1[1] + cov[4] * W1[2],
+                              cov[2] * W1[0] + cov[4] * W1[1] + cov[5] * W1[2]};
+        const double s2 = (double)s.scale * (double)s.scale;
+        const double a = s2 * (W0[0] * u0[0] + W0[1] * u0[1] + W0[2] * u0[2]) + (double)LOWPASS;
+        const double b = s2 * (W0[0] * u1[0] + W0[1] * u1[1] + W0[2] * u1[2]);
+        const double c = s2 * (W1[0] * u1[0] + W1[1] * u1[1] + W1[2] * u1[2]) + (double)LOWPASS;
+        const double det = a * c - b * b;
+        const double d2 = 1. / (det * det);
+        const double GA = gA, GB = gB, GC = gC;
+        // conic = (c, -b, a)/det  ->  cov2D entries (a, b, c)
+        double da = d2 * (-c * c * GA + b * c * GB - b * b * GC);
+        double db = d2 * (2. * b * c * GA - (det + 2. * b * b) * GB + 2. * a * b * GC);
+        double dc = d2 * (-b * b * GA + a * b * GB - a * a * GC);
         da *= s2; db *= s2; dc *= s2;
         // G[k][l] = dL/dSigma[k][l] treating the 9 entries as independent
-        float Gm[9];
+        double Gm[9];
 #pragma unroll
         for (int k = 0; k < 3; k++)
 #pragma unroll
-            for (int l = 0; l < 3; l++) Gm[3 * k + l] = da * w0[k] * w0[l] + db * w0[k] * w1[l] + dc * w1[k] * w1[l];
+            for (int l = 0; l < 3; l++) Gm[3 * k + l] = da * W0[k] * W0[l] + db * W0[k] * W1[l] + dc * W1[k] * W1[l];
         if (in.cov3D_precomp) {
-            dcov[0] = Gm[0]; dcov[1] = Gm[1] + Gm[3]; dcov[2] = Gm[2] + Gm[6];
-            dcov[3] = Gm[4]; dcov[4] = Gm[5] + Gm[7]; dcov[5] = Gm[8];
+            dcov[0] = (float)Gm[0]; dcov[1] = (float)(Gm[1] + Gm[3]); dcov[2] = (float)(Gm[2] + Gm[6]);
+            dcov[3] = (float)Gm[4]; dcov[4] = (float)(Gm[5] + Gm[7]); dcov[5] = (float)Gm[8];
         } else {
             // Sigma = M M^T, M = R diag(mod*s):  dL/dM = (G + G^T) M
-            float dM[9];
+            double dM[9];
 #pragma unroll
             for (int i = 0; i < 3; i++)
 #pragma unroll
                 for (int j = 0; j < 3; j++) {
-                    float t = 0.f;
+                    double t = 0.;
 #pragma unroll
                     for (int k = 0; k < 3; k++) t += (Gm[3 * i + k] + Gm[3 * k + i]) * (R[3 * k + j] * sv[j]);
                     dM[3 * i + j] = t;
                 }
-            float gR[9];
+            double gR[9];
 #pragma unroll
             for (int j = 0; j < 3; j++) {
-                float t = 0.f;
+                double t = 0.;
 #pragma unroll
                 for (int i = 0; i < 3; i++) {
                     t += dM[3 * i + j] * R[3 * i + j];
                     gR[3 * i + j] = dM[3 * i + j] * sv[j];
                 }
-                dsc[j] = t * s.scale_modifier;
+                dsc[j] = (float)(t * (double)s.scale_modifier);
             }
             const float4 q = reinterpret_cast<const float4*>(in.rotations)[g];
-            const float r = q.x, x = q.y, y = q.z, z = q.w;
-            drot[0] = 2.f * (-z * gR[1] + y * gR[2] + z * gR[3] - x * gR[5] - y * gR[6] + x * gR[7]);
-            drot[1] = 2.f * (y * gR[1] + z * gR[2] + y * gR[3] - 2.f * x * gR[4] - r * gR[5] + z * gR[6] + r * gR[7] -
-                             2.f * x * gR[8]);
-            drot[2] = 2.f * (-2.f * y * gR[0] + x * gR[1] + r * gR[2] + x * gR[3] + z * gR[5] - r * gR[6] + z * gR[7] -
-                             2.f * y * gR[8]);
-            drot[3] = 2.f * (-2.f * z * gR[0] - r * gR[1] + x * gR[2] + r * gR[3] - 2.f * z * gR[4] + y * gR[5] +
-                             x * gR[6] + y * gR[7]);
+            const double r = q.x, x = q.y, y = q.z, z = q.w;
+            drot[0] = (float)(2. * (-z * gR[1] + y * gR[2] + z * gR[3] - x * gR[5] - y * gR[6] + x * gR[7]));
+            drot[1] = (float)(2. * (y * gR[1] + z * gR[2] + y * gR[3] - 2. * x * gR[4] - r * gR[5] + z * gR[6] + r * gR[7] -
+                                    2. * x * gR[8]));
+            drot[2] = (float)(2. * (-2. * y * gR[0] + x * gR[1] + r * gR[2] + x * gR[3] + z * gR[5] - r * gR[6] + z * gR[7] -
+                                    2. * y * gR[8]));
+            drot[3] = (float)(2. * (-2. * z * gR[0] - r * gR[1] + x * gR[2] + r * gR[3] - 2. * z * gR[4] + y * gR[5] +
+                                    x * gR[6] + y * gR[7]));
         }
     } else if (in.shs && out.dL_dshs) {
         float* dsh = out.dL_dshs + (size_t)g * s.sh_M * 3;

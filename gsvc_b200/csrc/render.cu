@@ -5,12 +5,15 @@
 // One CTA per 16x16 tile; its 8 warps each own an 8x4-pixel block (one pixel per lane).  Gaussians
 // of the tile's depth-sorted list are gathered with float4 loads into shared memory in batches of
 // 256.  Both kernels are instruction-issue bound (ncu: >85 % issue-active, <2 % DRAM), so the design
-// goal is to execute fewer pixel-Gaussian evaluations, not to move fewer bytes:
+// goal is to execute fewer and cheaper pixel-Gaussian evaluations, not to move fewer bytes:
 //   * exact sub-tile culling — per chunk of 32 staged Gaussians every lane tests ONE Gaussian's
 //     alpha >= 1/255 bounding box (half extents precomputed by the preprocess kernel, inflated for
 //     rounding) against the warp's 8x4 block; a ballot gives the warp its private work list.  Only
 //     pairs the reference would `continue` past (alpha < 1/255, no state change) are skipped, so
 //     results are unchanged;
+//   * the conic is pre-scaled by -log2(e)/2 while staging, so a pair costs 5 FP32 ops + one
+//     ex2.approx (MUFU) up to the alpha test; staged records are 48 B interleaved so one address
+//     serves all three LDS.128;
 //   * warp-ballot early termination once all 32 pixels of a block are saturated (T < 1e-4 stop rule);
 //   * backward: the 9 per-Gaussian gradient terms are reduced across the warp with a
 //     transpose-butterfly (14 shuffles instead of 45) and only then added to global memory, 8 lanes
@@ -22,9 +25,24 @@ namespace gsvc {
 constexpr int BLEND_THREADS = TILE_PIX;  // 256
 constexpr int BATCH = 256;
 constexpr unsigned FULL = 0xffffffffu;
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+
+__device__ __forceinline__ float ex2_approx(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 struct BlockGeom {
-    int px, py;          // this lane's pixel
+    int px, py;                    // this lane's pixel
     float xmin, xmax, ymin, ymax;  // pixel-centre bounds of the warp's 8x4 block
 };
 
@@ -41,12 +59,29 @@ __device__ __forceinline__ BlockGeom block_geom(int tile, int gx, int tid)
     return b;
 }
 
-// Does the alpha >= 1/255 bounding box of the staged Gaussian touch the block?  (hx = hy = 0 with a
-// centre outside the block means "can never contribute".)
-__device__ __forceinline__ bool block_hit(const BlockGeom& b, const float4 f0, const float4 f2)
+// Staged record k = s_feat[3k .. 3k+2]:
+//   [0] = (pix.x, pix.y, hx, hy)   [1] = (A', B', C', opacity) with A' = -A log2e/2, B' = -B log2e, C' = -C log2e/2
+//   [2] = (r, g, b, -)
+// so that  alpha = opacity * 2^(A' dx^2 + B' dx dy + C' dy^2).
+__device__ __forceinline__ void stage(float4* s_feat, int slot, const GeomView& geo, unsigned int id)
 {
-    return (f0.x + f2.z >= b.xmin) && (f0.x - f2.z <= b.xmax) && (f0.y + f2.w >= b.ymin) && (f0.y - f2.w <= b.ymax) &&
-           (f2.z > 0.f);
+    const float4 f0 = __ldg(geo.feat0 + id);
+    float4 f1 = __ldg(geo.feat1 + id);
+    const float4 f2 = __ldg(geo.feat2 + id);
+    f1.x *= -0.5f * LOG2E;
+    f1.y *= -LOG2E;
+    f1.z *= -0.5f * LOG2E;
+    s_feat[3 * slot] = f0;
+    s_feat[3 * slot + 1] = f1;
+    s_feat[3 * slot + 2] = f2;
+}
+
+// Does the alpha >= 1/255 bounding box of the staged Gaussian touch the block?  (hx = 0 marks
+// "can never reach 1/255".)
+__device__ __forceinline__ bool block_hit(const BlockGeom& b, const float4 f0)
+{
+    return (f0.x + f0.z >= b.xmin) && (f0.x - f0.z <= b.xmax) && (f0.y + f0.w >= b.ymin) && (f0.y - f0.w <= b.ymax) &&
+           (f0.z > 0.f);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -56,9 +91,7 @@ __global__ void __launch_bounds__(BLEND_THREADS)
 render_forward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, unsigned long long cap,
                       float* __restrict__ out_color)
 {
-    __shared__ float4 s_f0[BATCH];
-    __shared__ float4 s_f1[BATCH];
-    __shared__ float4 s_f2[BATCH];
+    __shared__ float4 s_feat[3 * BATCH];
 
     const int tile = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -75,44 +108,44 @@ render_forward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, un
     bool done = !inside;
 
     for (int base = 0; base < n; base += BATCH) {
-        // block-wide vote doubles as the barrier that protects the staging buffers
+        // block-wide vote doubles as the barrier that protects the staging buffer
         if (__syncthreads_count(done) == BLEND_THREADS) break;
-        const int idx = base + tid;
-        if (idx < n) {
-            const unsigned int id = bin.point_list[rg.x + idx];
-            s_f0[tid] = __ldg(geo.feat0 + id);
-            s_f1[tid] = __ldg(geo.feat1 + id);
-            s_f2[tid] = __ldg(geo.feat2 + id);
-        }
+        if (base + tid < n) stage(s_feat, tid, geo, bin.point_list[rg.x + base + tid]);
         __syncthreads();
         const int cnt = min(BATCH, n - base);
         for (int c = 0; c < cnt; c += 32) {
             // warp-ballot early termination: all 32 pixels of the block saturated
             if (__ballot_sync(FULL, !done) == 0u) break;
-            const int j = c + lane;
             bool hit = false;
-            if (j < cnt) hit = block_hit(bg, s_f0[j], s_f2[j]);
+            if (c + lane < cnt) hit = block_hit(bg, s_feat[3 * (c + lane)]);
             unsigned int m = __ballot_sync(FULL, hit);
+            const float4* chunk = s_feat + 3 * c;
+            const unsigned int pos1 = (unsigned int)(base + c + 1);
             while (m) {
-                const int k = c + __ffs(m) - 1;
+                const int k = __ffs(m) - 1;
                 m &= m - 1;
-                const float4 f0 = s_f0[k];
-                const float4 f1 = s_f1[k];
-                const float cb = s_f2[k].x;
-                if (done) continue;
+                const float4* e = chunk + 3 * k;
+                const float4 f0 = e[0];
+                const float4 f1 = e[1];
                 const float dx = f0.x - pxf, dy = f0.y - pyf;
-                const float power = -0.5f * (f0.z * dx * dx + f1.x * dy * dy) - f0.w * dx * dy;
-                if (power > 0.f) continue;
-                const float alpha = fminf(ALPHA_MAX, f1.y * __expf(power));
-                if (alpha < ALPHA_MIN) continue;
-                const float test_T = T * (1.f - alpha);
-                if (test_T < T_STOP) { done = true; continue; }
-                const float w = alpha * T;
-                C0 += f1.z * w;
-                C1 += f1.w * w;
-                C2 += cb * w;
-                T = test_T;
-                last = (unsigned int)(base + k + 1);
+                const float u = fmaf(f1.x, dx, f1.y * dy);            // A' dx + B' dy
+                const float p2 = fmaf(u, dx, (f1.z * dy) * dy);       // log2 of the falloff
+                const float alpha = fminf(ALPHA_MAX, f1.w * ex2_approx(p2));
+                // the reference `continue`s on power > 0 and on alpha < 1/255
+                if (!done && !(p2 > 0.f) && !(alpha < ALPHA_MIN)) {
+                    const float test_T = T * (1.f - alpha);
+                    if (test_T < T_STOP) {
+                        done = true;
+                    } else {
+                        const float4 f2 = e[2];
+                        const float w = alpha * T;
+                        C0 = fmaf(f2.x, w, C0);
+                        C1 = fmaf(f2.y, w, C1);
+                        C2 = fmaf(f2.z, w, C2);
+                        T = test_T;
+                        last = pos1 + (unsigned int)k;
+                    }
+                }
             }
         }
     }
@@ -141,7 +174,7 @@ cudaError_t launch_render_forward(const DevSettings& s, GeomView g, ImageView im
 // ------------------------------------------------------------------------------------------------
 // Sum 8 values across the warp with 9 shuffles: after three exchange-and-halve steps every lane
 // holds one partial, after two more butterfly steps lane L holds the full sum of value index
-// 4*bit4(L) + 2*bit3(L) + bit2(L) in v[0].
+// (L >> 2) in v[0].
 __device__ __forceinline__ float warp_reduce8(float v[8], int lane)
 {
     bool hi = lane & 16;
@@ -180,9 +213,7 @@ __global__ void __launch_bounds__(BLEND_THREADS)
 render_backward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, const float* __restrict__ dL_dout,
                        float* __restrict__ acc /* [P][12] */)
 {
-    __shared__ float4 s_f0[BATCH];
-    __shared__ float4 s_f1[BATCH];
-    __shared__ float4 s_f2[BATCH];
+    __shared__ float4 s_feat[3 * BATCH];
     __shared__ unsigned int s_id[BATCH];
     __shared__ unsigned int s_max[BLEND_THREADS / 32];
 
@@ -201,7 +232,7 @@ render_backward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, c
     const unsigned int last = inside ? im.n_contrib[pix] : 0u;
     float g0 = 0.f, g1 = 0.f, g2 = 0.f;
     if (inside) { g0 = dL_dout[pix]; g1 = dL_dout[N + pix]; g2 = dL_dout[2 * N + pix]; }
-    const float bg_dot = __ldg(s.bg) * g0 + __ldg(s.bg + 1) * g1 + __ldg(s.bg + 2) * g2;
+    const float bgT = -T_final * (__ldg(s.bg) * g0 + __ldg(s.bg + 1) * g1 + __ldg(s.bg + 2) * g2);
 
     // nothing behind the deepest contributor of the tile matters: start the replay there
     const unsigned int wmax = __reduce_max_sync(FULL, last);
@@ -223,52 +254,55 @@ render_backward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, c
         if (kpos >= 0) {
             const unsigned int id = bin.point_list[rg.x + kpos];
             s_id[tid] = id;
-            s_f0[tid] = __ldg(geo.feat0 + id);
-            s_f1[tid] = __ldg(geo.feat1 + id);
-            s_f2[tid] = __ldg(geo.feat2 + id);
+            stage(s_feat, tid, geo, id);
         }
         __syncthreads();
         const int cnt = min(BATCH, m_len - base);
         for (int c = 0; c < cnt; c += 32) {
-            const int j = c + lane;
-            bool hit = false;
             // staged slot j holds list position m_len-1-(base+j); only positions below the warp's deepest
             // contributor can matter
-            if (j < cnt && (unsigned int)(m_len - 1 - (base + j)) < wmax) hit = block_hit(bg, s_f0[j], s_f2[j]);
+            const int pos0 = m_len - 1 - (base + c);  // list position of chunk slot 0
+            bool hit = false;
+            if (c + lane < cnt && (unsigned int)(pos0 - lane) < wmax) hit = block_hit(bg, s_feat[3 * (c + lane)]);
             unsigned int m = __ballot_sync(FULL, hit);
+            const float4* chunk = s_feat + 3 * c;
             while (m) {
-                const int k = c + __ffs(m) - 1;
+                const int k = __ffs(m) - 1;
                 m &= m - 1;
-                const unsigned int pos = (unsigned int)(m_len - 1 - (base + k));  // 0-based list position
-                const float4 f0 = s_f0[k];
-                const float4 f1 = s_f1[k];
-                const float cb = s_f2[k].x;
+                const float4* e = chunk + 3 * k;
+                const float4 f0 = e[0];
+                const float4 f1 = e[1];
                 const float dx = f0.x - pxf, dy = f0.y - pyf;
-                const float power = -0.5f * (f0.z * dx * dx + f1.x * dy * dy) - f0.w * dx * dy;
-                const float Gs = __expf(power);
-                const float alpha = fminf(ALPHA_MAX, f1.y * Gs);
-                const bool use = (pos < last) && !(power > 0.f) && !(alpha < ALPHA_MIN);
+                const float u = fmaf(f1.x, dx, f1.y * dy);
+                const float p2 = fmaf(u, dx, (f1.z * dy) * dy);
+                const float Gs = ex2_approx(p2);
+                const float alpha = fminf(ALPHA_MAX, f1.w * Gs);
+                const bool use = ((unsigned int)(pos0 - k) < last) && !(p2 > 0.f) && !(alpha < ALPHA_MIN);
                 if (!__any_sync(FULL, use)) continue;
 
                 // v = (d_px, d_py, d_A, d_B, d_C, d_op, d_r, d_g), d_b separately
                 float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 float d_b = 0.f;
                 if (use) {
-                    T = T / (1.f - alpha);
+                    const float4 f2 = e[2];
+                    const float ra = rcp_approx(1.f - alpha);
+                    T *= ra;
                     const float dchan = alpha * T;
-                    a0 = last_alpha * lc0 + (1.f - last_alpha) * a0;
-                    a1 = last_alpha * lc1 + (1.f - last_alpha) * a1;
-                    a2 = last_alpha * lc2 + (1.f - last_alpha) * a2;
-                    lc0 = f1.z; lc1 = f1.w; lc2 = cb;
-                    float dL_dalpha = (f1.z - a0) * g0 + (f1.w - a1) * g1 + (cb - a2) * g2;
-                    v[6] = dchan * g0; v[7] = dchan * g1; d_b = dchan * g2;
-                    dL_dalpha *= T;
+                    const float om = 1.f - last_alpha;
+                    a0 = fmaf(last_alpha, lc0, om * a0);
+                    a1 = fmaf(last_alpha, lc1, om * a1);
+                    a2 = fmaf(last_alpha, lc2, om * a2);
+                    lc0 = f2.x; lc1 = f2.y; lc2 = f2.z;
                     last_alpha = alpha;
-                    dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
-                    const float dL_dG = f1.y * dL_dalpha;  // U4: straight-through the 0.99 cap
+                    float dL_dalpha = (f2.x - a0) * g0 + (f2.y - a1) * g1 + (f2.z - a2) * g2;
+                    v[6] = dchan * g0; v[7] = dchan * g1; d_b = dchan * g2;
+                    dL_dalpha = fmaf(dL_dalpha, T, bgT * ra);
+                    const float dL_dG = f1.w * dL_dalpha;  // U4: straight-through the 0.99 cap
                     const float gdx = Gs * dx, gdy = Gs * dy;
-                    v[0] = dL_dG * (-gdx * f0.z - gdy * f0.w);
-                    v[1] = dL_dG * (-gdy * f1.x - gdx * f0.w);
+                    // -gdx*A - gdy*B with A = -2 A'/log2e, B = -B'/log2e
+                    const float q = dL_dG * LN2;
+                    v[0] = q * fmaf(2.f * gdx, f1.x, gdy * f1.y);
+                    v[1] = q * fmaf(2.f * gdy, f1.z, gdx * f1.y);
                     v[2] = -0.5f * gdx * dx * dL_dG;
                     v[3] = -gdx * dy * dL_dG;
                     v[4] = -0.5f * gdy * dy * dL_dG;
@@ -276,7 +310,7 @@ render_backward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, c
                 }
                 const float sum8 = warp_reduce8(v, lane);
                 d_b = warp_sum(d_b);
-                float* a = acc + (size_t)s_id[k] * 12;
+                float* a = acc + (size_t)s_id[c + k] * 12;
                 if ((lane & 3) == 0) atomicAdd(a + (lane >> 2), sum8);
                 if (lane == 0) atomicAdd(a + 8, d_b);
             }
