@@ -58,55 +58,59 @@ def algorithmic_bytes(P, V, R, N, T):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region, sampled in-process through NVML
+    (the same counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints; polling
+    nvidia-smi itself stalls the driver for milliseconds at a time and would perturb the timing)."""
 
-    def __init__(self, index):
-        self.index, self.samples, self.proc = index, [], None
+    def __init__(self, index, period=0.02):
+        self.index, self.period, self.samples, self.stop_flag = index, period, [], False
+        self.ok = False
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    def _reasons(self):
+        nv = self.nv
+        try:
+            return nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            return nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.samples.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM), self._reasons()))
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+        if self.ok:
+            self.thread = threading.Thread(target=self._run, daemon=True)
             self.thread.start()
-            # nvidia-smi's start-up stalls the driver for milliseconds: let it settle before anything is timed
-            t0 = time.time()
-            while not self.samples and time.time() - t0 < 10.0:
-                time.sleep(0.05)
-            self.samples.clear()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) >= 6:
-                self.samples.append(parts)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for p in self.samples:
-            try:
-                sm.append(float(p[0]))
-                mx = float(p[1])
-            except ValueError:
-                continue
-            for n, v in zip(names, p[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "")]}
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4,
+                 "hw_power_brake_slowdown": 0x80}
+        sm = [c for c, _ in self.samples]
+        bits = 0
+        for _, r in self.samples:
+            bits |= int(r)
+        reasons = sorted(n for n, m in names.items() if bits & m)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_sm, "reasons": reasons,
+                "samples": len(sm), "source": "nvml"}
 
 
 def build_scene(n_frames: int, device):
@@ -238,26 +242,26 @@ def run_product_arm(args, rank, local_rank, world):
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize(device)
 
-    def timed(fn, steps, collect_stages=False):
-        """K steps, each bracketed by CUDA events on the launching stream, L2 flushed before each."""
+    def timed(fn, steps):
+        """EXACTLY `steps` steps between two barrier+synchronize brackets.  Each step is bracketed by its own
+        CUDA events on the launching stream and the 256 MiB L2 flush runs between steps, outside the events;
+        the host never synchronises inside the region, so it runs ahead of the device exactly as a training
+        loop does.  Returns the max over ranks of the summed per-step device time."""
         sync_all()
-        total_ms, stage_ms = 0.0, {}
+        evs = []
         for _ in range(steps):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             out = fn()
             e1.record()
-            torch.cuda.synchronize(device)
-            total_ms += e0.elapsed_time(e1)
-            if collect_stages:
-                for k, v in _lib.stage_times().items():
-                    stage_ms.setdefault(k, []).append(v)
+            evs.append((e0, e1))
         sync_all()
+        total_ms = sum(a.elapsed_time(b) for a, b in evs)
         t = torch.tensor([total_ms], dtype=torch.float64, device=device)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), stage_ms, out
+        return float(t.item()), out
 
     # ---- warm-up (also sets the instance-capacity hint so no step re-sizes its buffers)
     for _ in range(max(args.warmup, 3)):
@@ -271,30 +275,71 @@ def run_product_arm(args, rank, local_rank, world):
     clocks.start()
     _lib.stage_timing(True)
     L.gsvc_rast_launch_count(1)
-    total_ms, stage_ms, _ = timed(train_step, args.steps, collect_stages=True)
+    total_ms, _ = timed(train_step, args.steps)
     launches = int(L.gsvc_rast_launch_count(1))
-    fwd_ms, fwd_stage_ms, _ = timed(forward_only, args.steps, collect_stages=True)
+    stage_avg = _lib.stage_times()          # mean per stage over the timed steps (last 256)
+    fwd_ms, _ = timed(forward_only, args.steps)
+    fwd_stage_avg = _lib.stage_times()
     _lib.stage_timing(False)
 
-    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region
+    # ---- end to end through the public API with HOST buffers: every step copies its inputs from pinned host
+    # memory and reads its results (image + packed gradients) back to pinned host memory, inside the timed
+    # region.  Copies run on their own streams and are double-buffered, as a host integration would do.
     host_in = {k: v.detach().cpu().pin_memory() for k, v in g.items()}
-    host_img = torch.empty((3, H, W), dtype=torch.float32).pin_memory()
-    host_grads = torch.empty((P, 14), dtype=torch.float32).pin_memory()
+    host_img = [torch.empty((3, H, W), dtype=torch.float32).pin_memory() for _ in range(2)]
+    host_grads = [torch.empty((P, 14), dtype=torch.float32).pin_memory() for _ in range(2)]
+    dev_in = [{k: torch.empty_like(v, device=device) for k, v in host_in.items()} for _ in range(2)]
+    dev_grads = [torch.empty((P, 14), dtype=torch.float32, device=device) for _ in range(2)]
     h2d = sum(v.numel() * 4 for v in host_in.values())
-    d2h = host_img.numel() * 4 + host_grads.numel() * 4
+    d2h = host_img[0].numel() * 4 + host_grads[0].numel() * 4
+    s_h2d, s_d2h = torch.cuda.Stream(device), torch.cuda.Stream(device)
+    main = torch.cuda.current_stream(device)
+    compute_done = [None, None]
+    d2h_done = [None, None]
 
-    def e2e_step():
-        p = {k: v.to(device, non_blocking=True).requires_grad_(True) for k, v in host_in.items()}
+    def e2e_step(i):
+        b = i & 1
+        with torch.cuda.stream(s_h2d):
+            if compute_done[b] is not None:
+                s_h2d.wait_event(compute_done[b])        # the device input set is free again
+            for k, v in host_in.items():
+                dev_in[b][k].copy_(v, non_blocking=True)
+            in_ready = s_h2d.record_event()
+        main.wait_event(in_ready)
+        if d2h_done[b] is not None:
+            main.wait_event(d2h_done[b])                 # the device gradient buffer has been read out
+        p = {k: v.requires_grad_(True) for k, v in dev_in[b].items()}
         color, radii, n, grads = train_step(p)
         if world == 1:
-            pack_grads({k: gr for (k, _), gr in zip(GRAD_LAYOUT, grads)}, out=grad_buf)
-        host_img.copy_(color.detach(), non_blocking=True)
-        host_grads.copy_(grad_buf, non_blocking=True)
+            pack_grads({k: gr for (k, _), gr in zip(GRAD_LAYOUT, grads)}, out=dev_grads[b])
+        else:
+            dev_grads[b].copy_(grad_buf)
+        for v in dev_in[b].values():
+            v.requires_grad_(False)
+        compute_done[b] = main.record_event()
+        color = color.detach()
+        color.record_stream(s_d2h)
+        with torch.cuda.stream(s_d2h):
+            s_d2h.wait_event(compute_done[b])
+            host_img[b].copy_(color, non_blocking=True)
+            host_grads[b].copy_(dev_grads[b], non_blocking=True)
+            d2h_done[b] = s_d2h.record_event()
         return n
 
-    for _ in range(3):
-        e2e_step()
-    e2e_ms, _, _ = timed(e2e_step, args.steps)
+    for i in range(4):
+        e2e_step(i)
+    sync_all()
+    e_start = torch.cuda.Event(enable_timing=True)
+    e_end = torch.cuda.Event(enable_timing=True)
+    e_start.record(s_h2d)
+    for i in range(args.steps):
+        e2e_step(i)
+    e_end.record(s_d2h)
+    sync_all()
+    t = torch.tensor([e_start.elapsed_time(e_end)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
     clk = clocks.stop()
 
     if rank == 0:
@@ -302,7 +347,6 @@ def run_product_arm(args, rank, local_rank, world):
         value = world * 1000.0 / ms_per_step
         peak, peak_src = load_peaks()
         alg = algorithmic_bytes(P, V, num_rendered, N, T)
-        stage_avg = {k: sum(v) / len(v) for k, v in stage_ms.items()}
         dom = max(stage_avg, key=stage_avg.get)
         achieved = alg[dom] / (stage_avg[dom] * 1e-3) / 1e9
         pairs = 256.0 * num_rendered
@@ -311,13 +355,13 @@ def run_product_arm(args, rank, local_rank, world):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "P": P, "V": V, "R": num_rendered, "N": N, "T": T,
-                       "frames": f"frame {f0}+rank of F=600, front view", "l2": "256 MiB flush between timed steps",
+                       "frames": f"frame {f0}+rank of F=600, front view", "l2": "256 MiB flush between timed steps (outside the per-step events)",
                        "parallelism": f"frame-sharded x{world}" + (", NCCL fp32 sum all-reduce of [P,14] grads per step" if world > 1 else "")},
             "fwd_frames_per_s": world * 1000.0 * args.steps / fwd_ms,
             "fwd_ms_per_view": fwd_ms / args.steps,
             "stage_ms": {k: round(v, 5) for k, v in stage_avg.items()},
-            "fwd_stage_ms": {k: round(sum(v) / len(v), 5) for k, v in fwd_stage_ms.items()},
-            "pairs_per_s_fwd": pairs / (sum(fwd_stage_ms["render_forward"]) / len(fwd_stage_ms["render_forward"]) * 1e-3),
+            "fwd_stage_ms": {k: round(v, 5) for k, v in fwd_stage_avg.items()},
+            "pairs_per_s_fwd": pairs / (fwd_stage_avg["render_forward"] * 1e-3),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes": alg[dom],

@@ -20,14 +20,21 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 enum Stage { ST_PREPROCESS = 0, ST_TILE_SCAN, ST_SCATTER, ST_SORT, ST_RENDER_FWD, ST_RENDER_BWD, ST_PREPROCESS_BWD,
              ST_VISIBLE_FILTER, ST_COUNT };
 static std::atomic<bool> g_timing{false};
-static cudaEvent_t g_ev[ST_COUNT][2];
+constexpr int EV_RING = 256;                       // per-stage samples kept between two queries
+static cudaEvent_t g_ev[ST_COUNT][EV_RING][2];
 static bool g_ev_made = false;
-static std::atomic<bool> g_ev_set[ST_COUNT];
+static std::atomic<unsigned int> g_ev_n[ST_COUNT];  // samples recorded since the last query
 
 struct StageScope {
-    int id; cudaStream_t s;
-    StageScope(int id_, cudaStream_t s_) : id(id_), s(s_) { if (g_timing) cudaEventRecord(g_ev[id][0], s); }
-    ~StageScope() { if (g_timing) { cudaEventRecord(g_ev[id][1], s); g_ev_set[id] = true; } }
+    int id; cudaStream_t s; unsigned int slot;
+    StageScope(int id_, cudaStream_t s_) : id(id_), s(s_), slot(0)
+    {
+        if (g_timing) { slot = g_ev_n[id].load() % EV_RING; cudaEventRecord(g_ev[id][slot][0], s); }
+    }
+    ~StageScope()
+    {
+        if (g_timing) { cudaEventRecord(g_ev[id][slot][1], s); g_ev_n[id].fetch_add(1); }
+    }
 };
 
 static int fail(int code, const char* fmt, ...)
@@ -121,12 +128,14 @@ int gsvc_rast_stage_timing(int32_t enable)
 {
     if (enable && !g_ev_made) {
         for (int i = 0; i < ST_COUNT; i++)
-            for (int j = 0; j < 2; j++)
-                if (cudaEventCreate(&g_ev[i][j]) != cudaSuccess) return fail(GSVC_RAST_ERR_CUDA, "cudaEventCreate failed");
+            for (int k = 0; k < EV_RING; k++)
+                for (int j = 0; j < 2; j++)
+                    if (cudaEventCreate(&g_ev[i][k][j]) != cudaSuccess)
+                        return fail(GSVC_RAST_ERR_CUDA, "cudaEventCreate failed");
         g_ev_made = true;
     }
     g_timing = enable != 0;
-    for (int i = 0; i < ST_COUNT; i++) g_ev_set[i] = false;
+    for (int i = 0; i < ST_COUNT; i++) g_ev_n[i] = 0;
     return 0;
 }
 
@@ -135,13 +144,19 @@ int gsvc_rast_stage_times(float* ms_host)
     if (!ms_host) return fail(GSVC_RAST_ERR_INVALID, "ms_host is NULL");
     for (int i = 0; i < ST_COUNT; i++) {
         ms_host[i] = -1.f;
-        if (!g_ev_made || !g_ev_set[i]) continue;
-        if (cudaEventSynchronize(g_ev[i][1]) != cudaSuccess) return fail(GSVC_RAST_ERR_CUDA, "cudaEventSynchronize failed");
-        float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, g_ev[i][0], g_ev[i][1]) != cudaSuccess)
-            return fail(GSVC_RAST_ERR_CUDA, "cudaEventElapsedTime failed");
-        ms_host[i] = ms;
-        g_ev_set[i] = false;
+        const unsigned int n = g_ev_made ? g_ev_n[i].exchange(0) : 0;
+        if (n == 0) continue;
+        const unsigned int cnt = n < (unsigned)EV_RING ? n : (unsigned)EV_RING;
+        double sum = 0.0;
+        for (unsigned int k = 0; k < cnt; k++) {
+            if (cudaEventSynchronize(g_ev[i][k][1]) != cudaSuccess)
+                return fail(GSVC_RAST_ERR_CUDA, "cudaEventSynchronize failed");
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, g_ev[i][k][0], g_ev[i][k][1]) != cudaSuccess)
+                return fail(GSVC_RAST_ERR_CUDA, "cudaEventElapsedTime failed");
+            sum += ms;
+        }
+        ms_host[i] = (float)(sum / cnt);
     }
     return ST_COUNT;
 }
@@ -166,7 +181,7 @@ int gsvc_rast_forward_launch(const gsvc_rast_settings* st, int32_t P, int32_t sh
                              const float* shs, const float* colors_precomp, const float* opacities,
                              const float* scales, const float* rotations, const float* cov3D_precomp, void* geom,
                              void* image, void* binning, int64_t capacity, float* out_color, int32_t* radii,
-                             int64_t* num_rendered_host, void* stream_)
+                             uint64_t* count_slot_host, uint32_t ticket, void* stream_)
 {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DevSettings d;
@@ -183,15 +198,37 @@ int gsvc_rast_forward_launch(const gsvc_rast_settings* st, int32_t P, int32_t sh
     ImageView im = image_view(image, d.W, d.H);
     PreInputs in{P, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp};
     { StageScope t(ST_PREPROCESS, stream); CK(launch_preprocess(d, in, radii, g, im, stream), "preprocess"); }
-    { StageScope t(ST_TILE_SCAN, stream); CK(launch_tile_scan(d, im, stream), "tile_scan"); }
-    if (num_rendered_host)
-        CK(cudaMemcpyAsync(num_rendered_host, &im.hdr->num_rendered, sizeof(int64_t), cudaMemcpyDeviceToHost, stream),
-           "num_rendered readback");
+    {
+        StageScope t(ST_TILE_SCAN, stream);
+        CK(launch_tile_scan(d, im, reinterpret_cast<unsigned long long*>(count_slot_host), ticket & 0xFFFFFFu, stream),
+           "tile_scan");
+    }
     if (capacity > 0) {
         rc = render_stages(d, P, g, im, binning, capacity, out_color, stream, dbg);
         if (rc) return rc;
     }
     return 0;
+}
+
+int64_t gsvc_rast_wait_count(const uint64_t* count_slot_host, uint32_t ticket, void* stream_)
+{
+    if (!count_slot_host) return fail(GSVC_RAST_ERR_INVALID, "count_slot_host is NULL");
+    const volatile uint64_t* slot = count_slot_host;
+    const uint64_t want = (uint64_t)(ticket & 0xFFFFFFu);
+    // The scan runs a few tens of microseconds after launch: spin briefly, then fall back to a stream
+    // synchronise (which also surfaces asynchronous launch errors).
+    for (long long spin = 0; spin < 20000000ll; spin++) {
+        const uint64_t v = *slot;
+        if ((v >> 40) == want) return (int64_t)(v & ((1ull << 40) - 1));
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(stream_));
+    if (e != cudaSuccess) return fail(GSVC_RAST_ERR_CUDA, "wait_count: %s", cudaGetErrorString(e));
+    const uint64_t v = *slot;
+    if ((v >> 40) == want) return (int64_t)(v & ((1ull << 40) - 1));
+    return fail(GSVC_RAST_ERR_CUDA, "wait_count: the tile scan never published ticket %u", (unsigned)want);
 }
 
 int gsvc_rast_forward_render(const gsvc_rast_settings* st, int32_t P, const void* geom, void* image, void* binning,
@@ -225,7 +262,7 @@ int64_t gsvc_rast_forward(const gsvc_rast_settings* st, int32_t P, int32_t sh_M,
     if (!geom || !image) return fail(GSVC_RAST_ERR_INVALID, "alloc callback returned NULL");
     // phase A: preprocess + tile scan; the exact instance count sizes the binning buffer
     int rc = gsvc_rast_forward_launch(st, P, sh_M, means3D, shs, colors_precomp, opacities, scales, rotations,
-                                      cov3D_precomp, geom, image, nullptr, 0, out_color, radii, nullptr, stream_);
+                                      cov3D_precomp, geom, image, nullptr, 0, out_color, radii, nullptr, 0, stream_);
     if (rc) return rc;
     ImageView im = image_view(image, st->image_width, st->image_height);
     unsigned long long R = 0;

@@ -17,18 +17,24 @@
 namespace gsvc {
 
 // ---- exclusive scan over tiles: offsets, ranges, num_rendered; resets the scatter cursors ----------
-// One CTA: thread t owns a contiguous run of tiles, sums it (all loads in flight at once), the 1024
-// partial sums are scanned with shuffles, then the run is re-read (L1/L2 hits) and written out.
+// Multi-CTA single-pass scan: CTA b scans its 1024 tiles (one tile per thread, coalesced), publishes
+// its aggregate (flag bit 63) and adds up the aggregates of all predecessors (decoupled look-back on
+// aggregates only: nothing depends on a predecessor's look-back, so there is no serial chain).
+// The partials array sits right behind tile_count and is zeroed by the same memset.  The last CTA
+// also writes num_rendered, tagged with the caller's ticket, straight into mapped pinned host memory
+// so the host learns R as soon as the scan ends — long before the blend kernel finishes.
 constexpr int SCAN_THREADS = 1024;
+constexpr unsigned long long SCAN_FLAG = 1ull << 63;
 
-__global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(int T, int items, ImageView im)
+__global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(int T, ImageView im, unsigned long long* host_slot,
+                                                                 unsigned int ticket)
 {
     __shared__ unsigned long long warp_sums[SCAN_THREADS / 32];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int lo = min(T, tid * items), hi = min(T, lo + items);
-    unsigned long long sum = 0ull;
-    for (int t = lo; t < hi; t++) sum += im.tile_count[t];
-    unsigned long long v = sum;
+    __shared__ unsigned long long s_prefix;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, b = blockIdx.x;
+    const int t = b * SCAN_THREADS + tid;
+    const unsigned int c = t < T ? im.tile_count[t] : 0u;
+    unsigned long long v = c;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const unsigned long long o = __shfl_up_sync(0xffffffffu, v, d);
@@ -44,27 +50,46 @@ __global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(int T, int item
             if (lane >= d) w += o;
         }
         warp_sums[lane] = w;  // inclusive over warps
+        const unsigned long long total = __shfl_sync(0xffffffffu, w, 31);
+        volatile unsigned long long* partials = im.scan_partials;
+        if (lane == 0) partials[b] = SCAN_FLAG | total;
+        unsigned long long prefix = 0ull;
+        for (int base = b - 1; base >= 0; base -= 32) {
+            const int idx = base - lane;
+            unsigned long long a = 0ull;
+            if (idx >= 0) {
+                do { a = partials[idx]; } while (!(a & SCAN_FLAG));
+                a &= ~SCAN_FLAG;
+            }
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+            prefix += a;
+        }
+        if (lane == 0) {
+            s_prefix = prefix;
+            if (b == (int)gridDim.x - 1) {
+                const unsigned long long R = prefix + total;
+                im.hdr->num_rendered = R;
+                im.hdr->overflow = 0u;
+                if (host_slot) *host_slot = ((unsigned long long)ticket << 40) | (R < (1ull << 40) ? R : (1ull << 40) - 1);
+            }
+        }
     }
     __syncthreads();
-    unsigned long long run = (wid ? warp_sums[wid - 1] : 0ull) + v - sum;  // exclusive prefix of this thread's run
-    for (int t = lo; t < hi; t++) {
-        const unsigned int c = im.tile_count[t];
-        im.tile_offset[t] = (unsigned int)run;
+    if (t < T) {
+        const unsigned long long incl = s_prefix + (wid ? warp_sums[wid - 1] : 0ull) + v;
+        const unsigned long long excl = incl - c;
+        im.tile_offset[t] = (unsigned int)excl;
         im.tile_cursor[t] = 0u;
-        im.ranges[t] = c ? make_uint2((unsigned int)run, (unsigned int)(run + c)) : make_uint2(0u, 0u);
-        run += c;
-    }
-    if (tid == SCAN_THREADS - 1) {
-        im.hdr->num_rendered = warp_sums[SCAN_THREADS / 32 - 1];
-        im.hdr->overflow = 0u;
+        im.ranges[t] = c ? make_uint2((unsigned int)excl, (unsigned int)incl) : make_uint2(0u, 0u);
     }
 }
 
-cudaError_t launch_tile_scan(const DevSettings& s, ImageView im, cudaStream_t st)
+cudaError_t launch_tile_scan(const DevSettings& s, ImageView im, unsigned long long* host_slot, unsigned int ticket,
+                             cudaStream_t st)
 {
     const int T = s.gx * s.gy;
-    const int items = (T + SCAN_THREADS - 1) / SCAN_THREADS;
-    tile_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(T, items, im);
+    tile_scan_kernel<<<(T + SCAN_THREADS - 1) / SCAN_THREADS, SCAN_THREADS, 0, st>>>(T, im, host_slot, ticket);
     count_launch();
     return cudaGetLastError();
 }

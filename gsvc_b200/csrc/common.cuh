@@ -50,6 +50,7 @@ struct ImageHeader {
 struct ImageView {
     ImageHeader* hdr;
     unsigned int* tile_count;   // [T] instances per tile (atomics in preprocess)
+    unsigned long long* scan_partials;  // [ceil(T/1024)] per-CTA aggregates of the tile scan (zeroed with tile_count)
     unsigned int* tile_offset;  // [T] exclusive scan of tile_count
     unsigned int* tile_cursor;  // [T] scatter cursors
     uint2* ranges;              // [T] (start,end) — (0,0) for untouched tiles, as identifyTileRanges leaves them
@@ -100,6 +101,7 @@ inline ImageView image_view(void* buf, int W, int H)
     ImageView v;
     v.hdr = carve<ImageHeader>(p, 1);
     v.tile_count = carve<unsigned int>(p, T);
+    v.scan_partials = carve<unsigned long long>(p, T / 1024 + 1);
     v.tile_offset = carve<unsigned int>(p, T);
     v.tile_cursor = carve<unsigned int>(p, T);
     v.ranges = carve<uint2>(p, T);
@@ -112,8 +114,8 @@ inline size_t image_bytes(int W, int H)
     char* p = nullptr;
     size_t T = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
     size_t N = (size_t)W * H;
-    carve<ImageHeader>(p, 1); carve<unsigned int>(p, T); carve<unsigned int>(p, T); carve<unsigned int>(p, T);
-    carve<uint2>(p, T); carve<float>(p, N); carve<unsigned int>(p, N);
+    carve<ImageHeader>(p, 1); carve<unsigned int>(p, T); carve<unsigned long long>(p, T / 1024 + 1);
+    carve<unsigned int>(p, T); carve<unsigned int>(p, T); carve<uint2>(p, T); carve<float>(p, N); carve<unsigned int>(p, N);
     return (size_t)p + 256;
 }
 inline BinView bin_view(void* buf, long long cap)
@@ -162,7 +164,8 @@ struct PreInputs {
 cudaError_t launch_visible_filter(const DevSettings& s, const PreInputs& in, int32_t* radii, cudaStream_t st);
 cudaError_t launch_preprocess(const DevSettings& s, const PreInputs& in, int32_t* radii, GeomView g, ImageView im,
                               cudaStream_t st);
-cudaError_t launch_tile_scan(const DevSettings& s, ImageView im, cudaStream_t st);
+cudaError_t launch_tile_scan(const DevSettings& s, ImageView im, unsigned long long* host_slot, unsigned int ticket,
+                             cudaStream_t st);
 cudaError_t launch_scatter(const DevSettings& s, int P, GeomView g, ImageView im, BinView b, long long cap,
                            cudaStream_t st);
 cudaError_t launch_sort_tiles(const DevSettings& s, ImageView im, BinView b, long long cap, cudaStream_t st);

@@ -203,8 +203,10 @@ cudaError_t launch_visible_filter(const DevSettings& s, const PreInputs& in, int
 cudaError_t launch_preprocess(const DevSettings& s, const PreInputs& in, int32_t* radii, GeomView g, ImageView im,
                               cudaStream_t st)
 {
+    // one memset clears the per-tile counters and the scan's per-CTA partials that sit right behind them
     const size_t T = (size_t)s.gx * s.gy;
-    cudaError_t e = cudaMemsetAsync(im.tile_count, 0, T * sizeof(unsigned int), st);
+    const size_t nbytes = reinterpret_cast<char*>(im.scan_partials + (T / 1024 + 1)) - reinterpret_cast<char*>(im.tile_count);
+    cudaError_t e = cudaMemsetAsync(im.tile_count, 0, nbytes, st);
     if (e != cudaSuccess) return e;
     if (in.P <= 0) return cudaSuccess;
     preprocess_kernel<false><<<(in.P + 255) / 256, 256, 0, st>>>(s, in, radii, g, im.tile_count);

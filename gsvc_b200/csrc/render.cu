@@ -60,14 +60,20 @@ __device__ __forceinline__ BlockGeom block_geom(int tile, int gx, int tid)
 }
 
 // Staged record k = s_feat[3k .. 3k+2]:
-//   [0] = (pix.x, pix.y, hx, hy)   [1] = (A', B', C', opacity) with A' = -A log2e/2, B' = -B log2e, C' = -C log2e/2
-//   [2] = (r, g, b, -)
-// so that  alpha = opacity * 2^(A' dx^2 + B' dx dy + C' dy^2).
+//   [0] = (pix.x, pix.y, B/A, B/C)
+//   [1] = (A', B', C', opacity) with A' = -A log2e/2, B' = -B log2e, C' = -C log2e/2, so that
+//         alpha = opacity * 2^q(d),  q(d) = A' dx^2 + B' dx dy + C' dy^2  (q <= 0, concave)
+//   [2] = (r, g, b, thr) with thr = -log2(255 opacity) - margin: alpha >= 1/255  <=>  q >= thr (+margin)
+constexpr float CULL_MARGIN = 1e-3f;  // in log2 units (7e-4 relative in alpha) >> fp32 rounding of q
+
 __device__ __forceinline__ void stage(float4* s_feat, int slot, const GeomView& geo, unsigned int id)
 {
-    const float4 f0 = __ldg(geo.feat0 + id);
+    float4 f0 = __ldg(geo.feat0 + id);
     float4 f1 = __ldg(geo.feat1 + id);
-    const float4 f2 = __ldg(geo.feat2 + id);
+    float4 f2 = __ldg(geo.feat2 + id);
+    f0.z = __fdividef(f1.y, f1.x);
+    f0.w = __fdividef(f1.y, f1.z);
+    f2.w = -__log2f(255.0f * f1.w) - CULL_MARGIN;
     f1.x *= -0.5f * LOG2E;
     f1.y *= -LOG2E;
     f1.z *= -0.5f * LOG2E;
@@ -76,12 +82,24 @@ __device__ __forceinline__ void stage(float4* s_feat, int slot, const GeomView& 
     s_feat[3 * slot + 2] = f2;
 }
 
-// Does the alpha >= 1/255 bounding box of the staged Gaussian touch the block?  (hx = 0 marks
-// "can never reach 1/255".)
-__device__ __forceinline__ bool block_hit(const BlockGeom& b, const float4 f0)
+// Exact sub-tile culling: can the staged Gaussian reach alpha >= 1/255 anywhere in the block
+// [xmin,xmax] x [ymin,ymax]?  q is concave with its maximum (0) at the centre, so its maximum over
+// the rectangle is attained at the centre if that lies inside, else on an edge facing the centre:
+// on the vertical line x = clamp(cx) the maximiser is y = cy - (B/C)(x - cx), on the horizontal
+// line y = clamp(cy) it is x = cx - (B/A)(y - cy), each clamped to the edge.  Both candidates are
+// points of the rectangle, so max(q1, q2) never over-estimates, and it equals the true maximum.
+__device__ __forceinline__ bool block_hit(const BlockGeom& b, const float4* e)
 {
-    return (f0.x + f0.z >= b.xmin) && (f0.x - f0.z <= b.xmax) && (f0.y + f0.w >= b.ymin) && (f0.y - f0.w <= b.ymax) &&
-           (f0.z > 0.f);
+    const float4 f0 = e[0];
+    const float4 f1 = e[1];
+    const float thr = e[2].w;
+    const float ex = fminf(fmaxf(f0.x, b.xmin), b.xmax), ey = fminf(fmaxf(f0.y, b.ymin), b.ymax);
+    const float dxe = ex - f0.x, dye = ey - f0.y;
+    const float dy1 = fminf(fmaxf(fmaf(-f0.w, dxe, f0.y), b.ymin), b.ymax) - f0.y;
+    const float dx2 = fminf(fmaxf(fmaf(-f0.z, dye, f0.x), b.xmin), b.xmax) - f0.x;
+    const float q1 = fmaf(fmaf(f1.x, dxe, f1.y * dy1), dxe, (f1.z * dy1) * dy1);
+    const float q2 = fmaf(fmaf(f1.x, dx2, f1.y * dye), dx2, (f1.z * dye) * dye);
+    return fmaxf(q1, q2) >= thr;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -117,7 +135,7 @@ render_forward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, un
             // warp-ballot early termination: all 32 pixels of the block saturated
             if (__ballot_sync(FULL, !done) == 0u) break;
             bool hit = false;
-            if (c + lane < cnt) hit = block_hit(bg, s_feat[3 * (c + lane)]);
+            if (c + lane < cnt) hit = block_hit(bg, s_feat + 3 * (c + lane));
             unsigned int m = __ballot_sync(FULL, hit);
             const float4* chunk = s_feat + 3 * c;
             const unsigned int pos1 = (unsigned int)(base + c + 1);
@@ -263,7 +281,7 @@ render_backward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, c
             // contributor can matter
             const int pos0 = m_len - 1 - (base + c);  // list position of chunk slot 0
             bool hit = false;
-            if (c + lane < cnt && (unsigned int)(pos0 - lane) < wmax) hit = block_hit(bg, s_feat[3 * (c + lane)]);
+            if (c + lane < cnt && (unsigned int)(pos0 - lane) < wmax) hit = block_hit(bg, s_feat + 3 * (c + lane));
             unsigned int m = __ballot_sync(FULL, hit);
             const float4* chunk = s_feat + 3 * c;
             while (m) {

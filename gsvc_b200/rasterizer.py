@@ -14,6 +14,7 @@ plumbing.  There is no CPU / eager fallback: CPU tensors raise.
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from typing import NamedTuple, Optional
 
 import torch
@@ -39,10 +40,11 @@ class GaussianRasterizationSettings(NamedTuple):
     debug: bool
 
 
-# per-device instance-capacity hint (last num_rendered seen), so that the binning buffer can be
-# sized without a mid-pipeline host synchronisation
+# instance-capacity hint per (device, P, H, W): the last num_rendered seen, so that the binning buffer
+# can be sized before the instance count of THIS call is known (no mid-pipeline host synchronisation)
 _capacity_hint: dict = {}
-_pinned_counter: dict = {}
+_count_slots = threading.local()
+_F32 = torch.float32
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -54,43 +56,42 @@ def _dev_f32(t: Optional[torch.Tensor], device, what: str) -> Optional[torch.Ten
         return None
     if t.device != device:
         raise RasterizerError(f"{what} is on {t.device}, expected {device} (the rasterizer has no CPU path)")
-    if t.dtype != torch.float32:
+    if t.dtype != _F32:
         t = t.float()
-    return t.contiguous()
+    return t if t.is_contiguous() else t.contiguous()
 
 
 class _NativeSettings:
     """Builds the C struct and keeps the tensors it points into alive."""
+    __slots__ = ("bg", "vm", "c", "ref")
 
     def __init__(self, rs: GaussianRasterizationSettings, device: torch.device):
         bg = rs.bg
         if not isinstance(bg, torch.Tensor):
-            bg = torch.tensor(bg, dtype=torch.float32)
-        self.bg = bg.to(device=device, dtype=torch.float32).contiguous()
+            bg = torch.tensor(bg, dtype=_F32)
+        if bg.device != device or bg.dtype != _F32 or not bg.is_contiguous():
+            bg = bg.to(device=device, dtype=_F32).contiguous()
         vm = rs.viewmatrix
-        if vm.device != device or vm.dtype != torch.float32:
-            vm = vm.to(device=device, dtype=torch.float32)
-        if tuple(vm.shape) != (4, 4):
+        if vm.device != device or vm.dtype != _F32:
+            vm = vm.to(device=device, dtype=_F32)
+        if vm.dim() != 2 or vm.shape[0] != 4 or vm.shape[1] != 4:
             raise RasterizerError(f"viewmatrix must be 4x4, got {tuple(vm.shape)}")
-        self.vm = vm  # strides are honoured natively: renderer.py:77 passes a permuted (non-contiguous) view
+        self.bg, self.vm = bg, vm  # strides honoured natively: renderer.py:77 passes a permuted (non-contiguous) view
         campos = rs.campos
         if isinstance(campos, torch.Tensor):
-            campos = campos.detach().to("cpu", torch.float32).reshape(-1).tolist()  # frame.py:41: lives on the CPU
+            campos = campos.detach().reshape(-1).tolist()  # frame.py:41: lives on the CPU
         s = Settings()
         s.image_height, s.image_width = int(rs.image_height), int(rs.image_width)
         s.x_min, s.y_min, s.scale = float(rs.x_min), float(rs.y_min), float(rs.scale)
         s.threshold, s.scale_modifier = float(rs.threshold), float(rs.scale_modifier)
-        s.bg = self.bg.data_ptr()
-        s.viewmatrix = self.vm.data_ptr()
-        s.vm_stride_r, s.vm_stride_c = int(self.vm.stride(0)), int(self.vm.stride(1))
+        s.bg = bg.data_ptr()
+        s.viewmatrix = vm.data_ptr()
+        s.vm_stride_r, s.vm_stride_c = vm.stride(0), vm.stride(1)
         s.sh_degree = int(rs.sh_degree)
-        s.campos[:] = [float(campos[0]), float(campos[1]), float(campos[2])]
+        s.campos[0], s.campos[1], s.campos[2] = campos[0], campos[1], campos[2]
         s.prefiltered, s.debug = int(bool(rs.prefiltered)), int(bool(rs.debug))
         self.c = s
-
-    @property
-    def ref(self):
-        return C.byref(self.c)
+        self.ref = C.byref(s)
 
 
 def _stream_ptr(device) -> int:
@@ -101,18 +102,24 @@ def _bytes(n: int, device) -> torch.Tensor:
     return torch.empty(int(n), dtype=torch.uint8, device=device)
 
 
-def _pinned(device) -> torch.Tensor:
-    key = (device.index, )
-    t = _pinned_counter.get(key)
-    if t is None:
-        t = torch.zeros(1, dtype=torch.int64).pin_memory()
-        _pinned_counter[key] = t
-    return t
+def _count_slot():
+    """One pinned, device-addressable 64-bit word per host thread + a ticket counter (see gsvc_rast.h)."""
+    st = _count_slots
+    if not hasattr(st, "slot"):
+        st.slot = torch.zeros(1, dtype=torch.int64).pin_memory()
+        st.ptr = st.slot.data_ptr()
+        st.ticket = 0
+    st.ticket = (st.ticket % 0xFFFFFE) + 1
+    return st.ptr, st.ticket
 
 
 def _require_cuda(t: torch.Tensor, what: str):
     if not t.is_cuda:
         raise RasterizerError(f"{what} must be a CUDA tensor: gsvc_b200 has no CPU fallback")
+
+
+def _align(n: int) -> int:
+    return (n + 255) & ~255
 
 
 class _RasterizeGaussians(torch.autograd.Function):
@@ -125,7 +132,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         rs = raster_settings
         with torch.cuda.device(device):
             ns = _NativeSettings(rs, device)
-            P = int(means3D.shape[0])
+            P = means3D.shape[0]
             means3D_c = _dev_f32(means3D, device, "means3D")
             sh_c = _dev_f32(sh, device, "shs") if sh.numel() else None
             col_c = _dev_f32(colors_precomp, device, "colors_precomp") if colors_precomp.numel() else None
@@ -133,37 +140,45 @@ class _RasterizeGaussians(torch.autograd.Function):
             sc_c = _dev_f32(scales, device, "scales") if scales.numel() else None
             rot_c = _dev_f32(rotations, device, "rotations") if rotations.numel() else None
             cov_c = _dev_f32(cov3Ds_precomp, device, "cov3D_precomp") if cov3Ds_precomp.numel() else None
-            sh_M = int(sh_c.shape[1]) if sh_c is not None else 0
+            sh_M = sh_c.shape[1] if sh_c is not None else 0
             H, W = int(rs.image_height), int(rs.image_width)
 
-            geom = _bytes(L.gsvc_rast_geom_bytes(P, sh_M), device)
-            image = _bytes(L.gsvc_rast_image_bytes(W, H), device)
-            color = torch.empty((3, H, W), dtype=torch.float32, device=device)
+            hint_key = (device.index, P, H, W)
+            hint = _capacity_hint.get(hint_key)
+            cap = 0 if hint is None else int(hint * 1.25) + 4096
+            # one allocation for all native state: [geom | image | binning]
+            n_geom = _align(L.gsvc_rast_geom_bytes(P, sh_M))
+            n_img = _align(L.gsvc_rast_image_bytes(W, H))
+            n_bin = L.gsvc_rast_binning_bytes(cap) if cap > 0 else 0
+            state = _bytes(n_geom + n_img + n_bin, device)
+            base = state.data_ptr()
+            geom_p, image_p = base, base + n_geom
+            binning = None
+            bin_p = base + n_geom + n_img if cap > 0 else None
+            color = torch.empty((3, H, W), dtype=_F32, device=device)
             radii = torch.empty((P,), dtype=torch.int32, device=device)
             stream = _stream_ptr(device)
-            counter = _pinned(device)
-
-            hint = _capacity_hint.get(device.index)
-            cap = 0 if hint is None else int(hint * 1.25) + 4096
-            binning = _bytes(L.gsvc_rast_binning_bytes(cap), device) if cap > 0 else None
+            slot, ticket = _count_slot()
             try:
                 _lib.check(L.gsvc_rast_forward_launch(
                     ns.ref, P, sh_M, _ptr(means3D_c), _ptr(sh_c), _ptr(col_c), _ptr(op_c), _ptr(sc_c), _ptr(rot_c),
-                    _ptr(cov_c), _ptr(geom), _ptr(image), _ptr(binning), cap, _ptr(color), _ptr(radii),
-                    counter.data_ptr(), stream), "gsvc_rast_forward_launch")
-                # the reference API returns num_rendered as a Python int (renderer.py:90): one sync per call
-                torch.cuda.current_stream(device).synchronize()
-                num_rendered = int(counter[0])
+                    _ptr(cov_c), geom_p, image_p, bin_p, cap, color.data_ptr(), radii.data_ptr(), slot, ticket,
+                    stream), "gsvc_rast_forward_launch")
+                # The reference API returns num_rendered as a Python int (renderer.py:90).  The scan kernel
+                # publishes it into pinned memory as soon as it is known, so this wait ends while the
+                # scatter / sort / blend kernels are still running: no stream synchronisation.
+                num_rendered = _lib.check(L.gsvc_rast_wait_count(slot, ticket, stream), "gsvc_rast_wait_count")
                 if num_rendered > 0xFFFFFFFF:
                     raise RasterizerError(f"num_rendered {num_rendered} exceeds 32-bit tile ranges")
                 if num_rendered > cap or cap == 0:
-                    # first call on this device, or the hint was too small: size exactly and run the
-                    # scatter / sort / blend stages on the state that is already in place
+                    # first call for this shape, or the hint was too small: size exactly and run the
+                    # scatter / sort / blend stages on the state that is already in place (stream-ordered)
                     cap = max(num_rendered, 1)
                     binning = _bytes(L.gsvc_rast_binning_bytes(cap), device)
-                    _lib.check(L.gsvc_rast_forward_render(ns.ref, P, _ptr(geom), _ptr(image), _ptr(binning), cap,
-                                                          _ptr(color), stream), "gsvc_rast_forward_render")
-                _capacity_hint[device.index] = num_rendered
+                    bin_p = binning.data_ptr()
+                    _lib.check(L.gsvc_rast_forward_render(ns.ref, P, geom_p, image_p, bin_p, cap, color.data_ptr(),
+                                                          stream), "gsvc_rast_forward_render")
+                _capacity_hint[hint_key] = num_rendered
             except Exception:
                 if rs.debug:
                     torch.save((means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
@@ -175,7 +190,8 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.num_rendered = num_rendered
         ctx.sh_M = sh_M
         ctx.capacity = cap
-        ctx.save_for_backward(means3D_c, sh_c, col_c, sc_c, rot_c, cov_c, radii, geom, image, binning)
+        ctx.offsets = (n_geom, n_img)
+        ctx.save_for_backward(means3D_c, sh_c, col_c, sc_c, rot_c, cov_c, radii, state, binning)
         ctx.mark_non_differentiable(radii)
         return color, radii, num_rendered
 
@@ -183,26 +199,31 @@ class _RasterizeGaussians(torch.autograd.Function):
     def backward(ctx, grad_out_color, _grad_radii=None, _grad_num=None):
         L = _lib.lib()
         rs = ctx.raster_settings
-        means3D, sh, col, sc, rot, cov, radii, geom, image, binning = ctx.saved_tensors
+        means3D, sh, col, sc, rot, cov, radii, state, binning = ctx.saved_tensors
         device = means3D.device
-        P = int(means3D.shape[0])
+        P = means3D.shape[0]
+        n_geom, n_img = ctx.offsets
+        base = state.data_ptr()
+        bin_p = binning.data_ptr() if binning is not None else base + n_geom + n_img
         with torch.cuda.device(device):
             ns = _NativeSettings(rs, device)
             g_out = _dev_f32(grad_out_color, device, "grad_out_color")
-            f32 = dict(dtype=torch.float32, device=device)
-            g_means3D = torch.empty((P, 3), **f32)
-            g_means2D = torch.empty((P, 3), **f32)
-            g_opac = torch.empty((P, 1), **f32)
-            g_col = torch.empty((P, 3), **f32) if col is not None else None
-            g_sh = torch.empty((P, ctx.sh_M, 3), **f32) if sh is not None else None
-            g_sc = torch.empty((P, 3), **f32) if sc is not None else None
-            g_rot = torch.empty((P, 4), **f32) if rot is not None else None
-            g_cov = torch.empty((P, 6), **f32) if cov is not None else None
-            scratch = _bytes(L.gsvc_rast_backward_scratch_bytes(P), device)
+            # one allocation for every gradient (contiguous slices) and the accumulator scratch
+            widths = (3, 3, 1, 3 if col is not None else 0, ctx.sh_M * 3 if sh is not None else 0,
+                      3 if sc is not None else 0, 4 if rot is not None else 0, 6 if cov is not None else 0)
+            n_scratch = L.gsvc_rast_backward_scratch_bytes(P) // 4
+            flat = torch.empty((sum(widths) * P + n_scratch + 64 + 4 * len(widths),), dtype=_F32, device=device)
+            outs, off = [], 0
+            for w in widths:
+                outs.append(flat[off:off + w * P] if w else None)
+                off = (off + w * P + 3) & ~3  # every slice starts 16-byte aligned (float4 stores)
+            off = (off + 63) & ~63  # 256-byte aligned scratch
+            scratch_p = flat.data_ptr() + 4 * off
+            g_means3D, g_means2D, g_opac, g_col, g_sh, g_sc, g_rot, g_cov = outs
             try:
                 _lib.check(L.gsvc_rast_backward(
                     ns.ref, P, ctx.sh_M, ctx.capacity, _ptr(means3D), _ptr(sh), _ptr(col), _ptr(sc), _ptr(rot),
-                    _ptr(cov), _ptr(radii), _ptr(geom), _ptr(image), _ptr(binning), _ptr(scratch), _ptr(g_out),
+                    _ptr(cov), _ptr(radii), base, base + n_geom, bin_p, scratch_p, _ptr(g_out),
                     _ptr(g_means3D), _ptr(g_means2D), _ptr(g_col), _ptr(g_opac), _ptr(g_sc), _ptr(g_rot),
                     _ptr(g_cov), _ptr(g_sh), _stream_ptr(device)), "gsvc_rast_backward")
             except Exception:
@@ -210,7 +231,9 @@ class _RasterizeGaussians(torch.autograd.Function):
                     torch.save((means3D, sh, col, sc, rot, cov, radii, grad_out_color, tuple(rs)), "snapshot_bw.dump")
                     print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
                 raise
-        return g_means3D, g_means2D, g_sh, g_col, g_opac, g_sc, g_rot, g_cov, None
+        v = lambda t, *shape: None if t is None else t.view(*shape)
+        return (v(g_means3D, P, 3), v(g_means2D, P, 3), v(g_sh, P, ctx.sh_M, 3), v(g_col, P, 3), v(g_opac, P, 1),
+                v(g_sc, P, 3), v(g_rot, P, 4), v(g_cov, P, 6), None)
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,

@@ -87,17 +87,25 @@ GSVC_RAST_API int gsvc_rast_visible_filter(const gsvc_rast_settings *st, int32_t
  * Forward, launch form (no host synchronisation): preprocess → tile counting → tile scan →
  * instance scatter → per-tile depth sort → front-to-back blend, all enqueued on `stream`.
  * Exactly one of shs ([P,sh_M,3]) / colors_precomp ([P,3]); exactly one of (scales,rotations) /
- * cov3D_precomp.  `binning` holds `capacity` instances; num_rendered is written asynchronously to
- * *num_rendered_host (pinned host memory).  After synchronising, the caller MUST check
- * *num_rendered_host <= capacity; if not, out_color is invalid and gsvc_rast_forward_render must be
- * re-run with a larger binning buffer (geom/image state stays valid).
+ * cov3D_precomp.  `binning` holds `capacity` instances (capacity 0 / binning NULL: only the
+ * preprocess and scan stages run).
+ * num_rendered: `count_slot_host` (may be NULL) is ONE 64-bit word of pinned host memory that the
+ * device can address (cudaHostAlloc / torch pin_memory under UVA).  The scan kernel stores
+ * (ticket & 0xFFFFFF) << 40 | num_rendered into it the moment the scan ends — well before the blend
+ * finishes — so gsvc_rast_wait_count() returns early and the caller can go on enqueueing work.
+ * The caller MUST check num_rendered <= capacity; if not, out_color is invalid and
+ * gsvc_rast_forward_render must be re-run with a larger binning buffer (geom/image stay valid).
  * Outputs: out_color [3,H,W], radii [P].
  */
 GSVC_RAST_API int gsvc_rast_forward_launch(const gsvc_rast_settings *st, int32_t P, int32_t sh_M, const float *means3D,
                              const float *shs, const float *colors_precomp, const float *opacities,
                              const float *scales, const float *rotations, const float *cov3D_precomp,
                              void *geom, void *image, void *binning, int64_t capacity, float *out_color,
-                             int32_t *radii, int64_t *num_rendered_host, void *stream);
+                             int32_t *radii, uint64_t *count_slot_host, uint32_t ticket, void *stream);
+
+/* Wait (spin on the pinned word, no stream synchronisation) until the launch with this ticket has
+ * published num_rendered; returns it, or a negative status. */
+GSVC_RAST_API int64_t gsvc_rast_wait_count(const uint64_t *count_slot_host, uint32_t ticket, void *stream);
 
 /* Re-run the instance scatter / sort / blend stages on existing geom+image state. */
 GSVC_RAST_API int gsvc_rast_forward_render(const gsvc_rast_settings *st, int32_t P, const void *geom, void *image, void *binning,
@@ -147,8 +155,9 @@ GSVC_RAST_API int gsvc_rast_export_image(const gsvc_rast_settings *st, const voi
 /*
  * Optional per-stage device timing (tracing aid; used by bench.py for the roofline numbers).
  * gsvc_rast_stage_timing(1) makes every later call (any thread) bracket each stage with CUDA
- * events on the launching stream; gsvc_rast_stage_times() waits for them and writes the last
- * duration of each stage in milliseconds (-1 if the stage did not run since the previous query):
+ * events on the launching stream (no host synchronisation); gsvc_rast_stage_times() waits for them
+ * and writes the MEAN duration of each stage in milliseconds over the calls made since the previous
+ * query (the last 256 at most; -1 if the stage did not run):
  *   [0] preprocess  [1] tile_scan  [2] scatter  [3] sort_tiles  [4] render_forward
  *   [5] render_backward  [6] preprocess_backward  [7] visible_filter
  * Returns the number of stages (8).
