@@ -1,0 +1,86 @@
+"""C-ABI checks that need no GPU: the library loads, exports every symbol include/gsvc_rast.h declares,
+the ctypes binding covers exactly that set, size helpers behave, and argument errors are reported through
+the status code / last_error channel before any CUDA work is attempted."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+from gsvc_b200 import _lib, build as native_build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "gsvc_rast.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    native_build.build()          # nvcc cross-compiles for sm_100a without a GPU
+    return _lib.lib()
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    return sorted(set(re.findall(r"GSVC_RAST_API\s+[\w\s\*]+?\b(gsvc_rast_\w+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported_and_bound(lib):
+    names = declared_symbols()
+    assert len(names) >= 15
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r"\bT (gsvc_rast_\w+)", out))
+    assert set(names) == exported, (set(names) ^ exported)
+    assert set(names) == set(_lib.SIGNATURES), (set(names) ^ set(_lib.SIGNATURES))
+    for n in names:
+        assert getattr(lib, n) is not None
+
+
+def test_no_torch_or_python_dependency_in_the_abi():
+    out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    assert "torch" not in out and "python" not in out
+    src = open(HEADER).read()
+    assert "at::" not in src and "#include <torch" not in src and "Tensor" not in src
+
+
+def test_abi_version_and_sizes(lib):
+    assert lib.gsvc_rast_abi_version() == _lib.ABI_VERSION == 1
+    g1, g2 = lib.gsvc_rast_geom_bytes(1000, 0), lib.gsvc_rast_geom_bytes(2000, 0)
+    assert 56 * 1000 <= g1 < g2 <= 2 * g1 + 4096
+    assert lib.gsvc_rast_geom_bytes(1000, 16) > g1                       # SH clamp flags
+    im = lib.gsvc_rast_image_bytes(1920, 1080)
+    assert im >= 8 * 1920 * 1080 + 20 * 8160
+    assert lib.gsvc_rast_binning_bytes(10 ** 6) >= 16 * 10 ** 6
+    assert lib.gsvc_rast_backward_scratch_bytes(1000) >= 48 * 1000
+    assert lib.gsvc_rast_binning_bytes(0) > 0 and lib.gsvc_rast_geom_bytes(0, 0) > 0
+
+
+def test_argument_errors_do_not_need_a_gpu(lib):
+    assert lib.gsvc_rast_visible_filter(None, 10, None, None, None, None, None, None) == _lib.ERR_INVALID
+    assert b"settings" in lib.gsvc_rast_last_error()
+    s = _lib.Settings()
+    s.image_height, s.image_width = 64, 64
+    assert lib.gsvc_rast_visible_filter(C.byref(s), 10, None, None, None, None, None, None) == _lib.ERR_INVALID
+    assert b"viewmatrix" in lib.gsvc_rast_last_error()
+    s.viewmatrix = 0x1000   # never dereferenced: argument validation fails first
+    s.image_width = 0
+    assert lib.gsvc_rast_visible_filter(C.byref(s), 10, 0x1000, None, None, None, 0x1000, None) == _lib.ERR_INVALID
+    s.image_width = 64
+    # neither (scales, rotations) nor cov3D_precomp
+    assert lib.gsvc_rast_visible_filter(C.byref(s), 10, 0x1000, None, None, None, 0x1000, None) == _lib.ERR_INVALID
+    assert b"exactly one" in lib.gsvc_rast_last_error()
+    # both colour sources / none
+    rc = lib.gsvc_rast_forward_launch(C.byref(s), 10, 0, 0x1000, None, None, 0x1000, 0x1000, 0x1000, None,
+                                      0x1000, 0x1000, None, 0, 0x1000, 0x1000, None, 0, None)
+    assert rc == _lib.ERR_INVALID and b"SHs or precomputed colors" in lib.gsvc_rast_last_error()
+    assert lib.gsvc_rast_wait_count(None, 1, None) == _lib.ERR_INVALID
+    with pytest.raises(_lib.RasterizerError):
+        _lib.check(_lib.ERR_INVALID, "x")
+    assert lib.gsvc_rast_launch_count(1) >= 0 and lib.gsvc_rast_launch_count(0) == 0
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libgsvc_rast.so"))
+    with pytest.raises(_lib.RasterizerError, match="no CPU or PyTorch fallback"):
+        _lib.lib()

@@ -1,0 +1,169 @@
+"""Host-side logic without a GPU: frame-cube geometry / view matrices against the reference's formulas,
+the reference-shaped plugin surface, and the frame-sharded gradient all-reduce (gloo, world_size 2)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from gsvc_b200 import sharding
+from gsvc_b200.frames import CONFIGS, CubeGeometry, make_view_matrix, synthetic_gaussians
+from gsvc_b200.rasterizer import GaussianRasterizationSettings, GaussianRasterizer, RasterizerError
+
+
+def look_at(eye, center, up):
+    """Textbook right-handed lookAt (what glm.lookAt computes, frame.py:35-38), as the mathematical matrix."""
+    eye, center, up = (np.asarray(v, np.float64) for v in (eye, center, up))
+    f = center - eye
+    f /= np.linalg.norm(f)
+    s = np.cross(f, up)
+    s /= np.linalg.norm(s)
+    u = np.cross(s, f)
+    M = np.eye(4)
+    M[0, :3], M[1, :3], M[2, :3] = s, u, -f
+    M[0, 3], M[1, 3], M[2, 3] = -s @ eye, -u @ eye, f @ eye
+    return M
+
+
+@pytest.mark.parametrize("z", [-0.3125, 0.0, 0.123])
+def test_view_matrices_match_lookat(z):
+    vm, vms, cam = make_view_matrix(z=z)
+    V = look_at((0, 0, z), (0, 0, z - 0.1), (0, 1, 0))       # frame.py:21-24
+    Vs = look_at((0, 0, z), (0, 0, z + 0.1), (0, 1, 0))
+    # the reference stores np.array(glm.mat4) = column-major = transpose; renderer.py:77 permutes it back
+    np.testing.assert_allclose(vm.permute(1, 0).numpy(), V, atol=1e-7)
+    np.testing.assert_allclose(vms.permute(1, 0).numpy(), Vs, atol=1e-7)
+    np.testing.assert_allclose(cam.numpy(), [0, 0, z])
+    p = np.array([0.3, -0.2, z + 0.01, 1.0])
+    np.testing.assert_allclose((V @ p)[:3], [0.3, -0.2, 0.01], atol=1e-7)       # front: (x, y, z - z_f)
+    np.testing.assert_allclose((Vs @ p)[:3], [-0.3, -0.2, -0.01], atol=1e-7)    # back: x-mirror, depth reversed
+
+
+def test_cube_geometry_matches_reference_formulas():
+    g = CubeGeometry(1920, 1080, 600)                 # frame.py:98-101, SURVEY.md §8
+    assert g.scale == 960 and g.x_min == -1.0 and g.y_min == -0.5625
+    assert g.z_of(0) == -0.3125 and abs(g.z_of(301) - g.z_of(300) - 1 / 960) < 1e-12
+    fr = g.frame(300)
+    assert (fr.image_width, fr.image_height, fr.plane) == (1920, 1080, "xy")
+    assert CONFIGS[2] == dict(P=200_000, W=1920, H=1080, F=600)
+
+
+def test_generator_is_seeded_and_in_range():
+    g = CubeGeometry(256, 256, 256)
+    a = synthetic_gaussians(5000, g, 128, seed=1)
+    b = synthetic_gaussians(5000, g, 128, seed=1)
+    c = synthetic_gaussians(5000, g, 128, seed=2)
+    for k in a:
+        assert torch.equal(a[k], b[k]) and not torch.equal(a[k], c[k])
+    assert a["means3D"].shape == (5000, 3) and a["opacities"].shape == (5000, 1)
+    assert torch.allclose(a["rotations"].norm(dim=-1), torch.ones(5000), atol=1e-5)
+    s_px = a["scales"] * g.scale
+    assert s_px.min() >= 0.3 - 1e-6 and s_px.max() <= 30 + 1e-4
+    assert (a["opacities"] >= 0.05).all() and (a["opacities"] <= 1).all()
+    assert (a["means3D"][:, 2] - g.z_of(128)).abs().max() <= 1.5 * 0.05 + 1e-6
+
+
+def test_plugin_surface_matches_reference_call_sites():
+    names = ("image_height", "image_width", "x_min", "y_min", "scale", "threshold", "bg", "scale_modifier",
+             "viewmatrix", "sh_degree", "campos", "prefiltered", "debug")       # renderer.py:63-83
+    assert GaussianRasterizationSettings._fields == names
+    from diff_gaussian_rasterization.cuda_ortho_gaussian_rasterizer import (      # renderer.py:6
+        GaussianRasterizationSettings as S2, GaussianRasterizer as R2)
+    assert S2 is GaussianRasterizationSettings and R2 is GaussianRasterizer
+    fr = CubeGeometry(64, 48, 64).frame(32)
+    rs = GaussianRasterizationSettings(image_height=48, image_width=64, x_min=fr.x_min, y_min=fr.y_min, scale=fr.scale,
+                                       threshold=0.05, bg=torch.zeros(3), scale_modifier=1.0,
+                                       viewmatrix=fr.view_matrix.permute(1, 0), sh_degree=0, campos=fr.cam_pos,
+                                       prefiltered=False, debug=False)
+    rast = GaussianRasterizer(raster_settings=rs)
+    assert isinstance(rast, torch.nn.Module) and rast.raster_settings is rs
+    g = synthetic_gaussians(10, CubeGeometry(64, 48, 64), 32, seed=1)
+    with pytest.raises(Exception, match="SHs or precomputed colors"):
+        rast(means3D=g["means3D"], means2D=g["means3D"], shs=None, colors_precomp=None, opacities=g["opacities"],
+             scales=g["scales"], rotations=g["rotations"], cov3D_precomp=None)
+    with pytest.raises(Exception, match="scale/rotation pair or precomputed 3D covariance"):
+        rast(means3D=g["means3D"], means2D=g["means3D"], shs=None, colors_precomp=g["colors_precomp"],
+             opacities=g["opacities"], scales=g["scales"], rotations=g["rotations"],
+             cov3D_precomp=torch.zeros(10, 6))
+    with pytest.raises(Exception):
+        rast.visible_filter(means3D=g["means3D"], scales=None, rotations=None, cov3D_precomp=None)
+    # CPU tensors: the product has no CPU path and must say so instead of silently computing somewhere else
+    with pytest.raises(RasterizerError, match="no CPU fallback"):
+        rast(means3D=g["means3D"], means2D=g["means3D"], shs=None, colors_precomp=g["colors_precomp"],
+             opacities=g["opacities"], scales=g["scales"], rotations=g["rotations"], cov3D_precomp=None)
+    with pytest.raises(RasterizerError, match="no CPU fallback"):
+        rast.visible_filter(means3D=g["means3D"], scales=g["scales"], rotations=g["rotations"], cov3D_precomp=None)
+
+
+def test_product_never_imports_the_oracle():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for d in ("gsvc_b200", "diff_gaussian_rasterization"):
+        for dirpath, _, files in os.walk(os.path.join(root, d)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h")):
+                    src = open(os.path.join(dirpath, f)).read()
+                    assert "from oracle" not in src and "import oracle" not in src and "splat_oracle" not in src, f
+
+
+def test_frame_assignment_and_packing():
+    frames = list(range(300, 308))
+    for world in (1, 2, 4, 8):
+        parts = [sharding.frames_for_rank(frames, r, world) for r in range(world)]
+        assert sorted(sum(parts, [])) == frames and all(len(p) == 8 // world for p in parts)
+    P = 7
+    grads = {k: torch.randn(P, w) for k, w in sharding.GRAD_LAYOUT}
+    buf = sharding.pack_grads(grads)
+    assert buf.shape == (P, 14) and sharding.GRAD_WIDTH == 14
+    back = sharding.unpack_grads(buf)
+    for k, _ in sharding.GRAD_LAYOUT:
+        assert torch.equal(back[k], grads[k])
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _oracle_view_grads(scene_cfg, frame_id, back):
+    """CPU stand-in for one rasterizer fwd+bwd (tests may use the oracle; the product path never does)."""
+    from oracle import c_oracle
+    from tests.scenes import make_scene, np_inputs
+    scene = make_scene(frame=frame_id, back=back, **scene_cfg)
+    gi = np_inputs(scene["gaussians"])
+    fo = c_oracle.forward(scene["oracle_settings"], gi["means3D"], gi["opacities"], gi["scales"], gi["rotations"],
+                          colors_precomp=gi["colors_precomp"])
+    H, W = scene_cfg["H"], scene_cfg["W"]
+    dL = torch.randn(3, H, W, generator=torch.Generator().manual_seed(1000 + 2 * frame_id + int(back))).numpy()
+    go = c_oracle.backward(fo, dL)
+    return {k: torch.as_tensor(go[k], dtype=torch.float32).reshape(-1, w) for k, w in sharding.GRAD_LAYOUT}
+
+
+SCENE = dict(P=400, W=48, H=32, F=64, seed=3, window=4)
+FRAMES = [30, 31, 32, 33]
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # every rank holds the same Gaussians (same seed; the window generator does not depend on the frame id)
+    total = sharding.render_window_grads(FRAMES, lambda f, b: _oracle_view_grads(SCENE, f, b), rank=rank, world=world)
+    torch.save(total, os.path.join(out_dir, f"rank{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_frame_sharded_allreduce_equals_single_rank(tmp_path):
+    """BASELINE config 3 in miniature: 2 ranks render disjoint frame subsets, one sum all-reduce of the
+    [P,14] buffer; every rank must end with the single-rank result (up to fp32 summation order)."""
+    single = sharding.render_window_grads(FRAMES, lambda f, b: _oracle_view_grads(SCENE, f, b), rank=0, world=1)
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = torch.load(tmp_path / "rank0.pt"), torch.load(tmp_path / "rank1.pt")
+    assert torch.equal(r0, r1)
+    assert single.abs().max() > 0
+    assert (r0 - single).abs().max() <= 1e-6 * single.abs().max() + 1e-12
