@@ -257,7 +257,12 @@ def run_product_arm(args, rank, local_rank, world):
             e1.record()
             evs.append((e0, e1))
         sync_all()
-        total_ms = sum(a.elapsed_time(b) for a, b in evs)
+        per_step = [a.elapsed_time(b) for a, b in evs]
+        total_ms = sum(per_step)
+        if os.environ.get("GSVC_BENCH_DEBUG"):
+            ps = sorted(per_step)
+            sys.stderr.write(f"[bench debug] {fn.__name__}: mean {total_ms / steps:.4f} median {ps[len(ps) // 2]:.4f} "
+                             f"p10 {ps[len(ps) // 10]:.4f} p90 {ps[9 * len(ps) // 10]:.4f} max {ps[-1]:.4f} ms\n")
         t = torch.tensor([total_ms], dtype=torch.float64, device=device)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -135,7 +135,8 @@ inline size_t bin_bytes(long long cap)
 }
 
 // Per-Gaussian gradient accumulators written by the blend backward (3 float4 per Gaussian):
-//  acc0 = (dL/dpix.x, dL/dpix.y, dL/dA, dL/dB)  acc1 = (dL/dC, dL/dopacity, dL/dr, dL/dg)  acc2 = (dL/db,0,0,0)
+//  acc0 = (S w dx, S w dy, S w dx^2, S w dx dy)  acc1 = (S w dy^2, dL/dopacity, dL/dr, dL/dg)  acc2 = (dL/db,0,0,0)
+//  with w = Gs * dL/dGs summed over the Gaussian's pixels; preprocess_backward turns the moments into dL/dpix, dL/dconic
 inline size_t bwd_scratch_bytes(int P) { return align_up((size_t)P * 48, 256) + 256; }
 
 // U2: order-preserving float -> uint32 (ascending key == ascending view depth, negatives included)

@@ -93,8 +93,12 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(DevSettings s,
     float dsc[3] = {0.f, 0.f, 0.f}, drot[4] = {0.f, 0.f, 0.f, 0.f}, dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 
     if (vis) {
+        // blend-backward accumulators: raw moments of w = Gs dL/dGs (see render.cu)
+        //   a0 = (S w dx, S w dy, S w dx^2, S w dx dy)  a1 = (S w dy^2, dL/dopacity, dL/dr, dL/dg)  a2.x = dL/db
         const float4 a0 = acc[3 * (size_t)g], a1 = acc[3 * (size_t)g + 1], a2 = acc[3 * (size_t)g + 2];
-        const float gpx = a0.x, gpy = a0.y, gA = a0.z, gB = a0.w, gC = a1.x;
+        const float4 con = geo.feat1[g];  // conic (A, B, C), opacity
+        const float gpx = -(con.x * a0.x + con.y * a0.y), gpy = -(con.z * a0.y + con.y * a0.x);
+        const float gA = -0.5f * a0.z, gB = -a0.w, gC = -0.5f * a1.x;
         dop = a1.y;
         dcol[0] = a1.z; dcol[1] = a1.w; dcol[2] = a2.x;
         const float w0[3] = {ldVb(s, 0, 0), ldVb(s, 0, 1), ldVb(s, 0, 2)};

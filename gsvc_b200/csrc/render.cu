@@ -26,7 +26,6 @@ constexpr int BLEND_THREADS = TILE_PIX;  // 256
 constexpr int BATCH = 256;
 constexpr unsigned FULL = 0xffffffffu;
 constexpr float LOG2E = 1.4426950408889634f;
-constexpr float LN2 = 0.6931471805599453f;
 
 __device__ __forceinline__ float ex2_approx(float x)
 {
@@ -261,6 +260,10 @@ render_backward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, c
     for (int w = 0; w < BLEND_THREADS / 32; w++) bmax = max(bmax, s_max[w]);
     const int m_len = (int)bmax;  // list entries [0, m_len) are replayed, back to front
 
+    // lanes 0,4,..,28 own the 8 reduced sums (index lane/4), lane 1 the ninth: one atomic instruction
+    const bool red_lane = (lane & 3) == 0 || lane == 1;
+    const int red_off = lane == 1 ? 8 : (lane >> 2);
+
     float T = T_final;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;      // colour composited behind the current Gaussian
     float lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;   // previous (deeper) contributor's colour and alpha
@@ -298,39 +301,38 @@ render_backward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, c
                 const bool use = ((unsigned int)(pos0 - k) < last) && !(p2 > 0.f) && !(alpha < ALPHA_MIN);
                 if (!__any_sync(FULL, use)) continue;
 
-                // v = (d_px, d_py, d_A, d_B, d_C, d_op, d_r, d_g), d_b separately
-                float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                float d_b = 0.f;
-                if (use) {
-                    const float4 f2 = e[2];
-                    const float ra = rcp_approx(1.f - alpha);
-                    T *= ra;
-                    const float dchan = alpha * T;
-                    const float om = 1.f - last_alpha;
-                    a0 = fmaf(last_alpha, lc0, om * a0);
-                    a1 = fmaf(last_alpha, lc1, om * a1);
-                    a2 = fmaf(last_alpha, lc2, om * a2);
-                    lc0 = f2.x; lc1 = f2.y; lc2 = f2.z;
-                    last_alpha = alpha;
-                    float dL_dalpha = (f2.x - a0) * g0 + (f2.y - a1) * g1 + (f2.z - a2) * g2;
-                    v[6] = dchan * g0; v[7] = dchan * g1; d_b = dchan * g2;
-                    dL_dalpha = fmaf(dL_dalpha, T, bgT * ra);
-                    const float dL_dG = f1.w * dL_dalpha;  // U4: straight-through the 0.99 cap
-                    const float gdx = Gs * dx, gdy = Gs * dy;
-                    // -gdx*A - gdy*B with A = -2 A'/log2e, B = -B'/log2e
-                    const float q = dL_dG * LN2;
-                    v[0] = q * fmaf(2.f * gdx, f1.x, gdy * f1.y);
-                    v[1] = q * fmaf(2.f * gdy, f1.z, gdx * f1.y);
-                    v[2] = -0.5f * gdx * dx * dL_dG;
-                    v[3] = -gdx * dy * dL_dG;
-                    v[4] = -0.5f * gdy * dy * dL_dG;
-                    v[5] = Gs * dL_dalpha;
-                }
+                // Branch-free: a pair that does not contribute is blended with alpha = 0, which leaves T, the
+                // behind-colour recursion and every sum unchanged (bit-identically), so no lane diverges.
+                // Per-pair sums are raw moments of w = Gs * dL/dGs; the per-Gaussian kernel turns them into
+                // dL/dpix and dL/dconic (it knows A,B,C), which keeps 9 FP32 ops out of this loop:
+                //   v = (S w dx, S w dy, S w dx^2, S w dx dy, S w dy^2, S Gs dL/dalpha, dL/dr, dL/dg), d_b = dL/db
+                const float4 f2 = e[2];
+                const float ae = use ? alpha : 0.f;
+                const float ra = rcp_approx(1.f - ae);
+                T *= ra;
+                const float om = 1.f - last_alpha;
+                a0 = fmaf(last_alpha, lc0, om * a0);
+                a1 = fmaf(last_alpha, lc1, om * a1);
+                a2 = fmaf(last_alpha, lc2, om * a2);
+                lc0 = f2.x; lc1 = f2.y; lc2 = f2.z;
+                last_alpha = ae;
+                float dla = (f2.x - a0) * g0 + (f2.y - a1) * g1 + (f2.z - a2) * g2;
+                dla = fmaf(dla, T, bgT * ra);
+                dla = use ? dla : 0.f;                       // U4: straight-through the 0.99 cap otherwise
+                const float dchan = ae * T;
+                float v[8];
+                v[5] = Gs * dla;
+                const float w = f1.w * v[5];
+                v[0] = w * dx;
+                v[1] = w * dy;
+                v[2] = v[0] * dx;
+                v[3] = v[0] * dy;
+                v[4] = v[1] * dy;
+                v[6] = dchan * g0;
+                v[7] = dchan * g1;
                 const float sum8 = warp_reduce8(v, lane);
-                d_b = warp_sum(d_b);
-                float* a = acc + (size_t)s_id[c + k] * 12;
-                if ((lane & 3) == 0) atomicAdd(a + (lane >> 2), sum8);
-                if (lane == 0) atomicAdd(a + 8, d_b);
+                const float d_b = warp_sum(dchan * g2);
+                if (red_lane) atomicAdd(acc + (size_t)s_id[c + k] * 12 + red_off, lane == 1 ? d_b : sum8);
             }
         }
     }
