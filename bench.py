@@ -200,7 +200,7 @@ def run_product_arm(args, rank, local_rank, world):
     import torch.distributed as dist
     from gsvc_b200 import _lib
     from gsvc_b200.rasterizer import GaussianRasterizer
-    from gsvc_b200.sharding import GRAD_LAYOUT, allreduce_grads, pack_grads
+    from gsvc_b200.sharding import GRAD_LAYOUT, pack_grads, packed_backward
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py product arm needs a CUDA device (no CPU fallback exists)")
@@ -218,7 +218,11 @@ def run_product_arm(args, rank, local_rank, world):
     N, T = W * H, ((W + 15) // 16) * ((H + 15) // 16)
     params = {k: v.clone().requires_grad_(True) for k, v in g.items()}
     dL = torch.randn((3, H, W), generator=torch.Generator().manual_seed(100 + rank)).to(device)
-    grad_buf = torch.empty((P, 14), dtype=torch.float32, device=device)
+    # frame-sharded steps: the backward writes straight into one of two [P,14] buffers (no pack pass) and the
+    # NCCL sum all-reduce of that buffer runs asynchronously, overlapping the next step's forward
+    grad_bufs = [torch.empty((P, 14), dtype=torch.float32, device=device) for _ in range(2)]
+    pending = [None, None]
+    step_no = [0]
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=device)  # 256 MiB > 126 MB L2
 
     def forward_only(p=params):
@@ -231,11 +235,17 @@ def run_product_arm(args, rank, local_rank, world):
         color, radii, n = rast(means3D=p["means3D"], means2D=means2D, shs=None, colors_precomp=p["colors_precomp"],
                                opacities=p["opacities"], scales=p["scales"], rotations=p["rotations"],
                                cov3D_precomp=None)
-        grads = torch.autograd.grad(color, [p[k] for k, _ in GRAD_LAYOUT], grad_outputs=dL)
         if world > 1:
-            pack_grads({k: gr for (k, _), gr in zip(GRAD_LAYOUT, grads)}, out=grad_buf)
-            allreduce_grads(grad_buf)
-        return color, radii, n, grads
+            b = step_no[0] & 1
+            step_no[0] += 1
+            if pending[b] is not None:
+                pending[b].wait()              # stream-level wait: the buffer's previous all-reduce has finished
+            with packed_backward(grad_bufs[b]):
+                grads = torch.autograd.grad(color, [p[k] for k, _ in GRAD_LAYOUT], grad_outputs=dL)
+            pending[b] = dist.all_reduce(grad_bufs[b], op=dist.ReduceOp.SUM, async_op=True)
+            return color, radii, n, grads, b
+        grads = torch.autograd.grad(color, [p[k] for k, _ in GRAD_LAYOUT], grad_outputs=dL)
+        return color, radii, n, grads, None
 
     def sync_all():
         if world > 1:
@@ -275,6 +285,9 @@ def run_product_arm(args, rank, local_rank, world):
     torch.cuda.synchronize(device)
     num_rendered = out[2]
     V = int((out[1] > 0).sum().item())
+    for w in pending:
+        if w is not None:
+            w.wait()
 
     clocks = ClockSampler(local_rank)
     clocks.start()
@@ -314,11 +327,12 @@ def run_product_arm(args, rank, local_rank, world):
         if d2h_done[b] is not None:
             main.wait_event(d2h_done[b])                 # the device gradient buffer has been read out
         p = {k: v.requires_grad_(True) for k, v in dev_in[b].items()}
-        color, radii, n, grads = train_step(p)
+        color, radii, n, grads, gb = train_step(p)
         if world == 1:
             pack_grads({k: gr for (k, _), gr in zip(GRAD_LAYOUT, grads)}, out=dev_grads[b])
         else:
-            dev_grads[b].copy_(grad_buf)
+            pending[gb].wait()
+            dev_grads[b].copy_(grad_bufs[gb])
         for v in dev_in[b].values():
             v.requires_grad_(False)
         compute_done[b] = main.record_event()

@@ -48,7 +48,7 @@ SIGNATURES = {
     "gsvc_rast_forward_render": (C.c_int, [_SP, _i32, _vp, _vp, _vp, _i64, _vp, _vp]),
     "gsvc_rast_forward": (_i64, [_SP, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ALLOC_FN, _vp, _vp, _vp, _vp]),
     "gsvc_rast_backward": (C.c_int, [_SP, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                     _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+                                     _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsvc_rast_export_keys": (C.c_int, [_SP, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsvc_rast_export_geom": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsvc_rast_export_image": (C.c_int, [_SP, _vp, _vp, _vp, _vp]),

@@ -283,7 +283,8 @@ int gsvc_rast_backward(const gsvc_rast_settings* st, int32_t P, int32_t sh_M, in
                        const float* rotations, const float* cov3D_precomp, const int32_t* radii, const void* geom,
                        const void* image, const void* binning, void* scratch, const float* dL_dout,
                        float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacities,
-                       float* dL_dscales, float* dL_drotations, float* dL_dcov3D, float* dL_dshs, void* stream_)
+                       float* dL_dscales, float* dL_drotations, float* dL_dcov3D, float* dL_dshs, float* dL_packed,
+                       void* stream_)
 {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DevSettings d;
@@ -303,7 +304,10 @@ int gsvc_rast_backward(const gsvc_rast_settings* st, int32_t P, int32_t sh_M, in
     float4* acc = static_cast<float4*>(scratch);
     PreInputs in{P, means3D, shs, colors_precomp, nullptr, scales, rotations, cov3D_precomp};
     { StageScope t(ST_RENDER_BWD, stream); CK(launch_render_backward(d, P, g, im, b, dL_dout, acc, stream), "render_backward"); }
-    BwdOutputs out{dL_dmeans3D, dL_dmeans2D, dL_dcolors, dL_dopacities, dL_dscales, dL_drotations, dL_dcov3D, dL_dshs};
+    if (dL_packed && (shs || cov3D_precomp))
+        return fail(GSVC_RAST_ERR_INVALID, "dL_packed needs colors_precomp and the scale/rotation pair");
+    BwdOutputs out{dL_dmeans3D, dL_dmeans2D, dL_dcolors, dL_dopacities, dL_dscales, dL_drotations, dL_dcov3D, dL_dshs,
+                   dL_packed};
     { StageScope t(ST_PREPROCESS_BWD, stream); CK(launch_preprocess_backward(d, in, radii, g, acc, out, stream), "preprocess_backward"); }
     return 0;
 }

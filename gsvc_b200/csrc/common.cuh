@@ -177,6 +177,7 @@ cudaError_t launch_render_backward(const DevSettings& s, int P, GeomView g, Imag
 struct BwdOutputs {
     float* dL_dmeans3D; float* dL_dmeans2D; float* dL_dcolors; float* dL_dopacities;
     float* dL_dscales; float* dL_drotations; float* dL_dcov3D; float* dL_dshs;
+    float* packed;  // optional [P,14] (means3D, colours, opacity, scales, rotation) replacing the five dense arrays
 };
 cudaError_t launch_preprocess_backward(const DevSettings& s, const PreInputs& in, const int32_t* radii, GeomView g,
                                        const float4* acc, BwdOutputs out, cudaStream_t st);

@@ -209,6 +209,17 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(DevSettings s,
         for (int k = 0; k < s.sh_M * 3; k++) dsh[k] = 0.f;
     }
 
+    if (out.packed) {
+        // [P,14] row = (means3D 3, colours 3, opacity 1, scales 3, rotation 4): the layout the frame-sharded
+        // all-reduce sums (sharding.GRAD_LAYOUT), written here so that no pack kernel is needed
+        float2* row = reinterpret_cast<float2*>(out.packed + 14 * (size_t)g);
+        row[0] = make_float2(dmean[0], dmean[1]); row[1] = make_float2(dmean[2], dcol[0]);
+        row[2] = make_float2(dcol[1], dcol[2]);   row[3] = make_float2(dop, dsc[0]);
+        row[4] = make_float2(dsc[1], dsc[2]);     row[5] = make_float2(drot[0], drot[1]);
+        row[6] = make_float2(drot[2], drot[3]);
+        if (out.dL_dmeans2D) { out.dL_dmeans2D[3 * g] = dm2[0]; out.dL_dmeans2D[3 * g + 1] = dm2[1]; out.dL_dmeans2D[3 * g + 2] = 0.f; }
+        return;
+    }
     if (out.dL_dmeans3D) { out.dL_dmeans3D[3 * g] = dmean[0]; out.dL_dmeans3D[3 * g + 1] = dmean[1]; out.dL_dmeans3D[3 * g + 2] = dmean[2]; }
     if (out.dL_dmeans2D) { out.dL_dmeans2D[3 * g] = dm2[0]; out.dL_dmeans2D[3 * g + 1] = dm2[1]; out.dL_dmeans2D[3 * g + 2] = 0.f; }
     if (out.dL_dcolors) { out.dL_dcolors[3 * g] = dcol[0]; out.dL_dcolors[3 * g + 1] = dcol[1]; out.dL_dcolors[3 * g + 2] = dcol[2]; }

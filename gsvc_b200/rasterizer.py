@@ -44,6 +44,13 @@ class GaussianRasterizationSettings(NamedTuple):
 # can be sized before the instance count of THIS call is known (no mid-pipeline host synchronisation)
 _capacity_hint: dict = {}
 _count_slots = threading.local()
+
+
+class _PackedTarget:
+    buf = None  # process-wide on purpose: autograd runs backward on its own thread
+
+
+_packed_target = _PackedTarget()
 _F32 = torch.float32
 
 
@@ -208,6 +215,13 @@ class _RasterizeGaussians(torch.autograd.Function):
         with torch.cuda.device(device):
             ns = _NativeSettings(rs, device)
             g_out = _dev_f32(grad_out_color, device, "grad_out_color")
+            # frame-sharded training: write (means3D, colours, opacity, scales, rotation) gradients straight into
+            # the caller's [P,14] all-reduce buffer (gsvc_b200.sharding.packed_backward) and return views of it
+            packed = _packed_target.buf
+            if packed is not None and (col is None or sc is None or packed.shape != (P, 14) or
+                                       packed.device != device or packed.dtype != _F32 or
+                                       not packed.is_contiguous()):
+                packed = None
             # one allocation for every gradient (contiguous slices) and the accumulator scratch
             widths = (3, 3, 1, 3 if col is not None else 0, ctx.sh_M * 3 if sh is not None else 0,
                       3 if sc is not None else 0, 4 if rot is not None else 0, 6 if cov is not None else 0)
@@ -225,13 +239,16 @@ class _RasterizeGaussians(torch.autograd.Function):
                     ns.ref, P, ctx.sh_M, ctx.capacity, _ptr(means3D), _ptr(sh), _ptr(col), _ptr(sc), _ptr(rot),
                     _ptr(cov), _ptr(radii), base, base + n_geom, bin_p, scratch_p, _ptr(g_out),
                     _ptr(g_means3D), _ptr(g_means2D), _ptr(g_col), _ptr(g_opac), _ptr(g_sc), _ptr(g_rot),
-                    _ptr(g_cov), _ptr(g_sh), _stream_ptr(device)), "gsvc_rast_backward")
+                    _ptr(g_cov), _ptr(g_sh), _ptr(packed), _stream_ptr(device)), "gsvc_rast_backward")
             except Exception:
                 if rs.debug:
                     torch.save((means3D, sh, col, sc, rot, cov, radii, grad_out_color, tuple(rs)), "snapshot_bw.dump")
                     print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
                 raise
         v = lambda t, *shape: None if t is None else t.view(*shape)
+        if packed is not None:
+            return (packed[:, 0:3], v(g_means2D, P, 3), None, packed[:, 3:6], packed[:, 6:7], packed[:, 7:10],
+                    packed[:, 10:14], None, None)
         return (v(g_means3D, P, 3), v(g_means2D, P, 3), v(g_sh, P, ctx.sh_M, 3), v(g_col, P, 3), v(g_opac, P, 1),
                 v(g_sc, P, 3), v(g_rot, P, 4), v(g_cov, P, 6), None)
 

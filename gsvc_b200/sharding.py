@@ -9,6 +9,7 @@ There is no other exchange on this path (forward-only decode needs none at all).
 """
 from __future__ import annotations
 
+import contextlib
 from typing import Callable, Dict, List, Sequence
 
 import torch
@@ -33,6 +34,19 @@ def pack_grads(grads: Dict[str, torch.Tensor], out: torch.Tensor = None) -> torc
         out[:, c:c + w] = grads[name].reshape(P, w)
         c += w
     return out
+
+
+@contextlib.contextmanager
+def packed_backward(buf: torch.Tensor):
+    """While active, the rasterizer backward writes the GRAD_LAYOUT gradients directly into `buf` ([P,14] fp32,
+    contiguous, on the rasterizer's device) and returns views of it, so the all-reduce needs no pack pass."""
+    from . import rasterizer
+    prev = rasterizer._packed_target.buf
+    rasterizer._packed_target.buf = buf
+    try:
+        yield buf
+    finally:
+        rasterizer._packed_target.buf = prev
 
 
 def unpack_grads(buf: torch.Tensor) -> Dict[str, torch.Tensor]:

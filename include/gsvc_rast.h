@@ -130,6 +130,9 @@ GSVC_RAST_API int64_t gsvc_rast_forward(const gsvc_rast_settings *st, int32_t P,
  * not given): dL_dmeans3D [P,3], dL_dmeans2D [P,3] (columns 0,1 = dL/dpixel * (0.5 W, 0.5 H), column 2 = 0),
  * dL_dcolors [P,3], dL_dopacities [P], dL_dscales [P,3], dL_drotations [P,4], dL_dcov3D [P,6],
  * dL_dshs [P,sh_M,3].  All outputs are fully overwritten (zeros for culled Gaussians).
+ * `dL_packed` (optional, colors_precomp + scale/rotation inputs only): [P,14] rows of
+ * (means3D 3, colours 3, opacity 1, scales 3, rotation 4) written INSTEAD of those five dense arrays — the
+ * buffer the frame-sharded NCCL all-reduce sums, so no pack pass is needed.
  * `scratch`: gsvc_rast_backward_scratch_bytes(P) bytes of device memory (contents undefined on return).
  */
 GSVC_RAST_API int gsvc_rast_backward(const gsvc_rast_settings *st, int32_t P, int32_t sh_M, int64_t capacity,
@@ -137,7 +140,8 @@ GSVC_RAST_API int gsvc_rast_backward(const gsvc_rast_settings *st, int32_t P, in
                        const float *rotations, const float *cov3D_precomp, const int32_t *radii, const void *geom,
                        const void *image, const void *binning, void *scratch, const float *dL_dout, float *dL_dmeans3D,
                        float *dL_dmeans2D, float *dL_dcolors, float *dL_dopacities, float *dL_dscales,
-                       float *dL_drotations, float *dL_dcov3D, float *dL_dshs, void *stream);
+                       float *dL_drotations, float *dL_dcov3D, float *dL_dshs, float *dL_packed,
+                       void *stream);
 
 /*
  * Stage exports for bit-exact parity tests (not used on the hot path).

@@ -274,3 +274,24 @@ def test_toast_two_view_composition(cuda_device):
     ref = (of["color"] + ob["color"][:, :, ::-1]) / 2
     frag = of["fragile"] | ob["fragile"][:, ::-1]
     assert np.abs(img.detach().cpu().numpy() - ref)[:, ~frag].max() <= FWD_ATOL
+
+
+def test_packed_backward_writes_the_allreduce_buffer(cuda_device):
+    """sharding.packed_backward: the [P,14] buffer receives exactly the gradients the dense outputs carry."""
+    from gsvc_b200 import sharding
+    scene = make_scene(P=9000, W=160, H=96, F=160, seed=23)
+    g, m2d, color, radii, n = _run_product(scene, cuda_device)
+    dL = torch.randn(color.shape, generator=torch.Generator().manual_seed(4)).to(cuda_device)
+    names = [k for k, _ in sharding.GRAD_LAYOUT]
+    dense = torch.autograd.grad(color, [g[k] for k in names], grad_outputs=dL, retain_graph=True)
+    buf = torch.full((9000, 14), float("nan"), device=cuda_device)
+    with sharding.packed_backward(buf):
+        views = torch.autograd.grad(color, [g[k] for k in names] + [m2d], grad_outputs=dL)
+    ref = sharding.pack_grads({k: d for k, d in zip(names, dense)})
+    # two backward passes differ in the order of the fp32 atomics, so compare to rounding, not bitwise
+    assert not torch.isnan(buf).any()
+    assert (buf - ref).abs().max() <= 1e-5 * ref.abs().max()
+    unpacked = sharding.unpack_grads(buf)
+    for k, v, d in zip(names, views, dense):
+        assert v.shape == d.shape and torch.equal(v, unpacked[k].reshape(d.shape))   # views of the buffer itself
+    assert views[-1].shape == (9000, 3)
