@@ -43,12 +43,12 @@ SIGNATURES = {
     "gsvc_rast_backward_scratch_bytes": (_sz, [_i32]),
     "gsvc_rast_visible_filter": (C.c_int, [_SP, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsvc_rast_forward_launch": (C.c_int, [_SP, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64,
-                                           _vp, _vp, _vp, C.c_uint32, _vp]),
+                                           _vp, _vp, _vp, _vp, C.c_uint32, _vp]),
     "gsvc_rast_wait_count": (_i64, [_vp, C.c_uint32, _vp]),
     "gsvc_rast_forward_render": (C.c_int, [_SP, _i32, _vp, _vp, _vp, _i64, _vp, _vp]),
     "gsvc_rast_forward": (_i64, [_SP, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ALLOC_FN, _vp, _vp, _vp, _vp]),
     "gsvc_rast_backward": (C.c_int, [_SP, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                     _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+                                     _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsvc_rast_export_keys": (C.c_int, [_SP, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsvc_rast_export_geom": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsvc_rast_export_image": (C.c_int, [_SP, _vp, _vp, _vp, _vp]),

@@ -180,8 +180,8 @@ int gsvc_rast_visible_filter(const gsvc_rast_settings* st, int32_t P, const floa
 int gsvc_rast_forward_launch(const gsvc_rast_settings* st, int32_t P, int32_t sh_M, const float* means3D,
                              const float* shs, const float* colors_precomp, const float* opacities,
                              const float* scales, const float* rotations, const float* cov3D_precomp, void* geom,
-                             void* image, void* binning, int64_t capacity, float* out_color, int32_t* radii,
-                             uint64_t* count_slot_host, uint32_t ticket, void* stream_)
+                             void* image, void* binning, int64_t capacity, void* bwd_scratch, float* out_color,
+                             int32_t* radii, uint64_t* count_slot_host, uint32_t ticket, void* stream_)
 {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DevSettings d;
@@ -197,7 +197,7 @@ int gsvc_rast_forward_launch(const gsvc_rast_settings* st, int32_t P, int32_t sh
     GeomView g = geom_view(geom, P < 1 ? 1 : P, d.sh_M);
     ImageView im = image_view(image, d.W, d.H);
     PreInputs in{P, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp};
-    { StageScope t(ST_PREPROCESS, stream); CK(launch_preprocess(d, in, radii, g, im, stream), "preprocess"); }
+    { StageScope t(ST_PREPROCESS, stream); CK(launch_preprocess(d, in, radii, g, im, static_cast<float4*>(bwd_scratch), stream), "preprocess"); }
     {
         StageScope t(ST_TILE_SCAN, stream);
         CK(launch_tile_scan(d, im, reinterpret_cast<unsigned long long*>(count_slot_host), ticket & 0xFFFFFFu, stream),
@@ -262,7 +262,8 @@ int64_t gsvc_rast_forward(const gsvc_rast_settings* st, int32_t P, int32_t sh_M,
     if (!geom || !image) return fail(GSVC_RAST_ERR_INVALID, "alloc callback returned NULL");
     // phase A: preprocess + tile scan; the exact instance count sizes the binning buffer
     int rc = gsvc_rast_forward_launch(st, P, sh_M, means3D, shs, colors_precomp, opacities, scales, rotations,
-                                      cov3D_precomp, geom, image, nullptr, 0, out_color, radii, nullptr, 0, stream_);
+                                      cov3D_precomp, geom, image, nullptr, 0, nullptr, out_color, radii, nullptr, 0,
+                                      stream_);
     if (rc) return rc;
     ImageView im = image_view(image, st->image_width, st->image_height);
     unsigned long long R = 0;
@@ -281,7 +282,8 @@ int64_t gsvc_rast_forward(const gsvc_rast_settings* st, int32_t P, int32_t sh_M,
 int gsvc_rast_backward(const gsvc_rast_settings* st, int32_t P, int32_t sh_M, int64_t capacity,
                        const float* means3D, const float* shs, const float* colors_precomp, const float* scales,
                        const float* rotations, const float* cov3D_precomp, const int32_t* radii, const void* geom,
-                       const void* image, const void* binning, void* scratch, const float* dL_dout,
+                       const void* image, const void* binning, void* scratch, int32_t scratch_is_zero,
+                       const float* dL_dout,
                        float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacities,
                        float* dL_dscales, float* dL_drotations, float* dL_dcov3D, float* dL_dshs, float* dL_packed,
                        void* stream_)
@@ -303,7 +305,7 @@ int gsvc_rast_backward(const gsvc_rast_settings* st, int32_t P, int32_t sh_M, in
     BinView b = bin_view(const_cast<void*>(binning), capacity);
     float4* acc = static_cast<float4*>(scratch);
     PreInputs in{P, means3D, shs, colors_precomp, nullptr, scales, rotations, cov3D_precomp};
-    { StageScope t(ST_RENDER_BWD, stream); CK(launch_render_backward(d, P, g, im, b, dL_dout, acc, stream), "render_backward"); }
+    { StageScope t(ST_RENDER_BWD, stream); CK(launch_render_backward(d, P, g, im, b, dL_dout, acc, scratch_is_zero != 0, stream), "render_backward"); }
     if (dL_packed && (shs || cov3D_precomp))
         return fail(GSVC_RAST_ERR_INVALID, "dL_packed needs colors_precomp and the scale/rotation pair");
     BwdOutputs out{dL_dmeans3D, dL_dmeans2D, dL_dcolors, dL_dopacities, dL_dscales, dL_drotations, dL_dcov3D, dL_dshs,

@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(int T, ImageVie
 {
     __shared__ unsigned long long warp_sums[SCAN_THREADS / 32];
     __shared__ unsigned long long s_prefix;
+    pdl_prologue();
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, b = blockIdx.x;
     const int t = b * SCAN_THREADS + tid;
     const unsigned int c = t < T ? im.tile_count[t] : 0u;
@@ -89,9 +90,9 @@ cudaError_t launch_tile_scan(const DevSettings& s, ImageView im, unsigned long l
                              cudaStream_t st)
 {
     const int T = s.gx * s.gy;
-    tile_scan_kernel<<<(T + SCAN_THREADS - 1) / SCAN_THREADS, SCAN_THREADS, 0, st>>>(T, im, host_slot, ticket);
     count_launch();
-    return cudaGetLastError();
+    return launch_pdl(tile_scan_kernel, dim3((T + SCAN_THREADS - 1) / SCAN_THREADS), dim3(SCAN_THREADS), st, T, im,
+                      host_slot, ticket);
 }
 
 // ---- scatter: one instance (depth_key << 32 | id) per (Gaussian, tile in rect) into its tile bucket ----
@@ -115,6 +116,7 @@ __device__ __forceinline__ void scatter_one(int t, unsigned long long item, Imag
 __global__ void __launch_bounds__(256) scatter_kernel(int P, int gx, GeomView geo, ImageView im, BinView bin,
                                                       unsigned long long cap)
 {
+    pdl_prologue();
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     ushort4 r = make_ushort4(0, 0, 0, 0);
@@ -165,9 +167,8 @@ cudaError_t launch_scatter(const DevSettings& s, int P, GeomView g, ImageView im
                            cudaStream_t st)
 {
     if (P <= 0) return cudaSuccess;
-    scatter_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, s.gx, g, im, b, (unsigned long long)cap);
     count_launch();
-    return cudaGetLastError();
+    return launch_pdl(scatter_kernel, dim3((P + 255) / 256), dim3(256), st, P, s.gx, g, im, b, (unsigned long long)cap);
 }
 
 // ---- per-tile sort of the 64-bit composites -----------------------------------------------------
@@ -217,6 +218,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_tiles_kernel(int T, ImageVi
 {
     __shared__ unsigned long long s_items[SORT_SMEM_ITEMS];
     __shared__ int s_big[SORT_WARPS];
+    pdl_prologue();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int t = blockIdx.x * SORT_WARPS + warp;
     uint2 rg = make_uint2(0u, 0u);
@@ -271,9 +273,9 @@ cudaError_t launch_sort_tiles(const DevSettings& s, ImageView im, BinView b, lon
 {
     const int T = s.gx * s.gy;
     if (T <= 0) return cudaSuccess;
-    sort_tiles_kernel<<<(T + SORT_WARPS - 1) / SORT_WARPS, SORT_THREADS, 0, st>>>(T, im, b, (unsigned long long)cap);
     count_launch();
-    return cudaGetLastError();
+    return launch_pdl(sort_tiles_kernel, dim3((T + SORT_WARPS - 1) / SORT_WARPS), dim3(SORT_THREADS), st, T, im, b,
+                      (unsigned long long)cap);
 }
 
 // ---- export for the bit-exact stage tests --------------------------------------------------------

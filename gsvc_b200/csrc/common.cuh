@@ -150,6 +150,33 @@ __host__ __device__ inline unsigned int ordered_u32(float z)
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
+// ---- programmatic dependent launch (sm_90+): every kernel of a forward / backward chain is launched with
+// programmaticStreamSerializationAllowed, signals launch_dependents on entry and waits for its predecessor's
+// memory before touching any data, so launch latency and prologue of kernel N+1 overlap the tail of kernel N.
+__device__ __forceinline__ void pdl_prologue()
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ---- launch stages implemented in the .cu files ------------------------------------------------
 struct PreInputs {
     int P;
@@ -164,7 +191,7 @@ struct PreInputs {
 
 cudaError_t launch_visible_filter(const DevSettings& s, const PreInputs& in, int32_t* radii, cudaStream_t st);
 cudaError_t launch_preprocess(const DevSettings& s, const PreInputs& in, int32_t* radii, GeomView g, ImageView im,
-                              cudaStream_t st);
+                              float4* acc_to_zero, cudaStream_t st);
 cudaError_t launch_tile_scan(const DevSettings& s, ImageView im, unsigned long long* host_slot, unsigned int ticket,
                              cudaStream_t st);
 cudaError_t launch_scatter(const DevSettings& s, int P, GeomView g, ImageView im, BinView b, long long cap,
@@ -173,7 +200,7 @@ cudaError_t launch_sort_tiles(const DevSettings& s, ImageView im, BinView b, lon
 cudaError_t launch_render_forward(const DevSettings& s, GeomView g, ImageView im, BinView b, long long cap,
                                   float* out_color, cudaStream_t st);
 cudaError_t launch_render_backward(const DevSettings& s, int P, GeomView g, ImageView im, BinView b,
-                                   const float* dL_dout, float4* acc, cudaStream_t st);
+                                   const float* dL_dout, float4* acc, bool acc_is_zero, cudaStream_t st);
 struct BwdOutputs {
     float* dL_dmeans3D; float* dL_dmeans2D; float* dL_dcolors; float* dL_dopacities;
     float* dL_dscales; float* dL_drotations; float* dL_dcov3D; float* dL_dshs;

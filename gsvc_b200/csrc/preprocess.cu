@@ -105,10 +105,18 @@ __device__ __forceinline__ void sh_to_rgb(int deg, const float* sh, const float 
 // FILTER = true: visible_filter (radii only).  FILTER = false: full preprocess + per-tile instance counting.
 template <bool FILTER>
 __global__ void __launch_bounds__(256) preprocess_kernel(DevSettings s, PreInputs in, int32_t* __restrict__ radii,
-                                                         GeomView geo, unsigned int* __restrict__ tile_count)
+                                                         GeomView geo, unsigned int* __restrict__ tile_count,
+                                                         float4* __restrict__ acc_to_zero)
 {
+    pdl_prologue();
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= in.P) return;
+    if (!FILTER && acc_to_zero) {
+        // the blend backward accumulates into these 9 sums with atomics: zero them here (a store the
+        // stream kernel hides) instead of a separate memset launch in the backward
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        acc_to_zero[3 * (size_t)g] = z; acc_to_zero[3 * (size_t)g + 1] = z; acc_to_zero[3 * (size_t)g + 2] = z;
+    }
 
     const float p[3] = {__ldg(in.means3D + 3 * g), __ldg(in.means3D + 3 * g + 1), __ldg(in.means3D + 3 * g + 2)};
     const float w0[3] = {ldV(s, 0, 0), ldV(s, 0, 1), ldV(s, 0, 2)};
@@ -195,13 +203,13 @@ cudaError_t launch_visible_filter(const DevSettings& s, const PreInputs& in, int
 {
     if (in.P <= 0) return cudaSuccess;
     GeomView none{};
-    preprocess_kernel<true><<<(in.P + 255) / 256, 256, 0, st>>>(s, in, radii, none, nullptr);
     count_launch();
-    return cudaGetLastError();
+    return launch_pdl(preprocess_kernel<true>, dim3((in.P + 255) / 256), dim3(256), st, s, in, radii, none,
+                      (unsigned int*)nullptr, (float4*)nullptr);
 }
 
 cudaError_t launch_preprocess(const DevSettings& s, const PreInputs& in, int32_t* radii, GeomView g, ImageView im,
-                              cudaStream_t st)
+                              float4* acc_to_zero, cudaStream_t st)
 {
     // one memset clears the per-tile counters and the scan's per-CTA partials that sit right behind them
     const size_t T = (size_t)s.gx * s.gy;
@@ -209,9 +217,9 @@ cudaError_t launch_preprocess(const DevSettings& s, const PreInputs& in, int32_t
     cudaError_t e = cudaMemsetAsync(im.tile_count, 0, nbytes, st);
     if (e != cudaSuccess) return e;
     if (in.P <= 0) return cudaSuccess;
-    preprocess_kernel<false><<<(in.P + 255) / 256, 256, 0, st>>>(s, in, radii, g, im.tile_count);
     count_launch();
-    return cudaGetLastError();
+    return launch_pdl(preprocess_kernel<false>, dim3((in.P + 255) / 256), dim3(256), st, s, in, radii, g, im.tile_count,
+                      acc_to_zero);
 }
 
 }  // namespace gsvc

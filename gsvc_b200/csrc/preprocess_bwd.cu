@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(DevSettings s,
                                                                   const int32_t* __restrict__ radii, GeomView geo,
                                                                   const float4* __restrict__ acc, BwdOutputs out)
 {
+    pdl_prologue();
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= in.P) return;
     const bool vis = radii[g] > 0;
@@ -236,9 +237,8 @@ cudaError_t launch_preprocess_backward(const DevSettings& s, const PreInputs& in
                                        const float4* acc, BwdOutputs out, cudaStream_t st)
 {
     if (in.P <= 0) return cudaSuccess;
-    preprocess_backward_kernel<<<(in.P + 255) / 256, 256, 0, st>>>(s, in, radii, g, acc, out);
     count_launch();
-    return cudaGetLastError();
+    return launch_pdl(preprocess_backward_kernel, dim3((in.P + 255) / 256), dim3(256), st, s, in, radii, g, acc, out);
 }
 
 }  // namespace gsvc

@@ -110,6 +110,7 @@ render_forward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, un
 {
     __shared__ float4 s_feat[3 * BATCH];
 
+    pdl_prologue();
     const int tile = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31;
     const BlockGeom bg = block_geom(tile, s.gx, tid);
@@ -181,9 +182,9 @@ cudaError_t launch_render_forward(const DevSettings& s, GeomView g, ImageView im
 {
     const int T = s.gx * s.gy;
     if (T <= 0) return cudaSuccess;
-    render_forward_kernel<<<T, BLEND_THREADS, 0, st>>>(s, g, im, b, (unsigned long long)cap, out_color);
     count_launch();
-    return cudaGetLastError();
+    return launch_pdl(render_forward_kernel, dim3(T), dim3(BLEND_THREADS), st, s, g, im, b, (unsigned long long)cap,
+                      out_color);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -234,6 +235,7 @@ render_backward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, c
     __shared__ unsigned int s_id[BATCH];
     __shared__ unsigned int s_max[BLEND_THREADS / 32];
 
+    pdl_prologue();
     const int tile = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31;
     const BlockGeom bg = block_geom(tile, s.gx, tid);
@@ -339,15 +341,17 @@ render_backward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, c
 }
 
 cudaError_t launch_render_backward(const DevSettings& s, int P, GeomView g, ImageView im, BinView b,
-                                   const float* dL_dout, float4* acc, cudaStream_t st)
+                                   const float* dL_dout, float4* acc, bool acc_is_zero, cudaStream_t st)
 {
-    cudaError_t e = cudaMemsetAsync(acc, 0, (size_t)P * 48, st);
-    if (e != cudaSuccess) return e;
+    if (!acc_is_zero) {
+        cudaError_t e = cudaMemsetAsync(acc, 0, (size_t)P * 48, st);
+        if (e != cudaSuccess) return e;
+    }
     const int T = s.gx * s.gy;
     if (T <= 0 || P <= 0) return cudaSuccess;
-    render_backward_kernel<<<T, BLEND_THREADS, 0, st>>>(s, g, im, b, dL_dout, reinterpret_cast<float*>(acc));
     count_launch();
-    return cudaGetLastError();
+    return launch_pdl(render_backward_kernel, dim3(T), dim3(BLEND_THREADS), st, s, g, im, b, dL_dout,
+                      reinterpret_cast<float*>(acc));
 }
 
 }  // namespace gsvc

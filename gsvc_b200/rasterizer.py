@@ -153,15 +153,18 @@ class _RasterizeGaussians(torch.autograd.Function):
             hint_key = (device.index, P, H, W)
             hint = _capacity_hint.get(hint_key)
             cap = 0 if hint is None else int(hint * 1.25) + 4096
-            # one allocation for all native state: [geom | image | binning]
+            # one allocation for all native state: [geom | image | backward accumulators | binning]
+            need_grad = any(ctx.needs_input_grad)
             n_geom = _align(L.gsvc_rast_geom_bytes(P, sh_M))
             n_img = _align(L.gsvc_rast_image_bytes(W, H))
+            n_acc = _align(L.gsvc_rast_backward_scratch_bytes(P)) if need_grad else 0
             n_bin = L.gsvc_rast_binning_bytes(cap) if cap > 0 else 0
-            state = _bytes(n_geom + n_img + n_bin, device)
+            state = _bytes(n_geom + n_img + n_acc + n_bin, device)
             base = state.data_ptr()
             geom_p, image_p = base, base + n_geom
+            acc_p = base + n_geom + n_img if need_grad else None   # zeroed by the preprocess kernel
             binning = None
-            bin_p = base + n_geom + n_img if cap > 0 else None
+            bin_p = base + n_geom + n_img + n_acc if cap > 0 else None
             color = torch.empty((3, H, W), dtype=_F32, device=device)
             radii = torch.empty((P,), dtype=torch.int32, device=device)
             stream = _stream_ptr(device)
@@ -169,7 +172,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             try:
                 _lib.check(L.gsvc_rast_forward_launch(
                     ns.ref, P, sh_M, _ptr(means3D_c), _ptr(sh_c), _ptr(col_c), _ptr(op_c), _ptr(sc_c), _ptr(rot_c),
-                    _ptr(cov_c), geom_p, image_p, bin_p, cap, color.data_ptr(), radii.data_ptr(), slot, ticket,
+                    _ptr(cov_c), geom_p, image_p, bin_p, cap, acc_p, color.data_ptr(), radii.data_ptr(), slot, ticket,
                     stream), "gsvc_rast_forward_launch")
                 # The reference API returns num_rendered as a Python int (renderer.py:90).  The scan kernel
                 # publishes it into pinned memory as soon as it is known, so this wait ends while the
@@ -197,7 +200,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.num_rendered = num_rendered
         ctx.sh_M = sh_M
         ctx.capacity = cap
-        ctx.offsets = (n_geom, n_img)
+        ctx.offsets = (n_geom, n_img, n_acc)
         ctx.save_for_backward(means3D_c, sh_c, col_c, sc_c, rot_c, cov_c, radii, state, binning)
         ctx.mark_non_differentiable(radii)
         return color, radii, num_rendered
@@ -209,9 +212,9 @@ class _RasterizeGaussians(torch.autograd.Function):
         means3D, sh, col, sc, rot, cov, radii, state, binning = ctx.saved_tensors
         device = means3D.device
         P = means3D.shape[0]
-        n_geom, n_img = ctx.offsets
+        n_geom, n_img, n_acc = ctx.offsets
         base = state.data_ptr()
-        bin_p = binning.data_ptr() if binning is not None else base + n_geom + n_img
+        bin_p = binning.data_ptr() if binning is not None else base + n_geom + n_img + n_acc
         with torch.cuda.device(device):
             ns = _NativeSettings(rs, device)
             g_out = _dev_f32(grad_out_color, device, "grad_out_color")
@@ -225,19 +228,23 @@ class _RasterizeGaussians(torch.autograd.Function):
             # one allocation for every gradient (contiguous slices) and the accumulator scratch
             widths = (3, 3, 1, 3 if col is not None else 0, ctx.sh_M * 3 if sh is not None else 0,
                       3 if sc is not None else 0, 4 if rot is not None else 0, 6 if cov is not None else 0)
-            n_scratch = L.gsvc_rast_backward_scratch_bytes(P) // 4
+            n_scratch = 0 if n_acc else L.gsvc_rast_backward_scratch_bytes(P) // 4
+            # the accumulators inside the forward state were zeroed by the preprocess kernel; a backward
+            # dirties them, so a second backward over the same graph (retain_graph) asks for a clear
+            acc_clean = 1 if (n_acc and not getattr(ctx, "acc_dirty", False)) else 0
+            ctx.acc_dirty = True
             flat = torch.empty((sum(widths) * P + n_scratch + 64 + 4 * len(widths),), dtype=_F32, device=device)
             outs, off = [], 0
             for w in widths:
                 outs.append(flat[off:off + w * P] if w else None)
                 off = (off + w * P + 3) & ~3  # every slice starts 16-byte aligned (float4 stores)
             off = (off + 63) & ~63  # 256-byte aligned scratch
-            scratch_p = flat.data_ptr() + 4 * off
+            scratch_p = base + n_geom + n_img if n_acc else flat.data_ptr() + 4 * off
             g_means3D, g_means2D, g_opac, g_col, g_sh, g_sc, g_rot, g_cov = outs
             try:
                 _lib.check(L.gsvc_rast_backward(
                     ns.ref, P, ctx.sh_M, ctx.capacity, _ptr(means3D), _ptr(sh), _ptr(col), _ptr(sc), _ptr(rot),
-                    _ptr(cov), _ptr(radii), base, base + n_geom, bin_p, scratch_p, _ptr(g_out),
+                    _ptr(cov), _ptr(radii), base, base + n_geom, bin_p, scratch_p, acc_clean, _ptr(g_out),
                     _ptr(g_means3D), _ptr(g_means2D), _ptr(g_col), _ptr(g_opac), _ptr(g_sc), _ptr(g_rot),
                     _ptr(g_cov), _ptr(g_sh), _ptr(packed), _stream_ptr(device)), "gsvc_rast_backward")
             except Exception:

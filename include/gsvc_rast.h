@@ -95,13 +95,19 @@ GSVC_RAST_API int gsvc_rast_visible_filter(const gsvc_rast_settings *st, int32_t
  * finishes — so gsvc_rast_wait_count() returns early and the caller can go on enqueueing work.
  * The caller MUST check num_rendered <= capacity; if not, out_color is invalid and
  * gsvc_rast_forward_render must be re-run with a larger binning buffer (geom/image stay valid).
+ * `bwd_scratch` (optional): gsvc_rast_backward_scratch_bytes(P) bytes that a later gsvc_rast_backward will
+ * use; the preprocess kernel zeroes them on the fly, which saves the backward a memset launch
+ * (pass scratch_is_zero = 1 there).
  * Outputs: out_color [3,H,W], radii [P].
+ * All kernels of the chain are launched with programmatic dependent launch (their launch latency and
+ * prologue overlap the predecessor's tail).
  */
 GSVC_RAST_API int gsvc_rast_forward_launch(const gsvc_rast_settings *st, int32_t P, int32_t sh_M, const float *means3D,
                              const float *shs, const float *colors_precomp, const float *opacities,
                              const float *scales, const float *rotations, const float *cov3D_precomp,
-                             void *geom, void *image, void *binning, int64_t capacity, float *out_color,
-                             int32_t *radii, uint64_t *count_slot_host, uint32_t ticket, void *stream);
+                             void *geom, void *image, void *binning, int64_t capacity, void *bwd_scratch,
+                             float *out_color, int32_t *radii, uint64_t *count_slot_host, uint32_t ticket,
+                             void *stream);
 
 /* Wait (spin on the pinned word, no stream synchronisation) until the launch with this ticket has
  * published num_rendered; returns it, or a negative status. */
@@ -133,12 +139,15 @@ GSVC_RAST_API int64_t gsvc_rast_forward(const gsvc_rast_settings *st, int32_t P,
  * `dL_packed` (optional, colors_precomp + scale/rotation inputs only): [P,14] rows of
  * (means3D 3, colours 3, opacity 1, scales 3, rotation 4) written INSTEAD of those five dense arrays — the
  * buffer the frame-sharded NCCL all-reduce sums, so no pack pass is needed.
- * `scratch`: gsvc_rast_backward_scratch_bytes(P) bytes of device memory (contents undefined on return).
+ * `scratch`: gsvc_rast_backward_scratch_bytes(P) bytes of device memory; scratch_is_zero = 1 promises it is
+ * all-zero on entry (as gsvc_rast_forward_launch's bwd_scratch leaves it; a backward dirties it, so a second
+ * backward over the same state must pass 0), 0 makes the call clear it first.
  */
 GSVC_RAST_API int gsvc_rast_backward(const gsvc_rast_settings *st, int32_t P, int32_t sh_M, int64_t capacity,
                        const float *means3D, const float *shs, const float *colors_precomp, const float *scales,
                        const float *rotations, const float *cov3D_precomp, const int32_t *radii, const void *geom,
-                       const void *image, const void *binning, void *scratch, const float *dL_dout, float *dL_dmeans3D,
+                       const void *image, const void *binning, void *scratch, int32_t scratch_is_zero,
+                       const float *dL_dout, float *dL_dmeans3D,
                        float *dL_dmeans2D, float *dL_dcolors, float *dL_dopacities, float *dL_dscales,
                        float *dL_drotations, float *dL_dcov3D, float *dL_dshs, float *dL_packed,
                        void *stream);

@@ -71,7 +71,7 @@ def test_argument_errors_do_not_need_a_gpu(lib):
     assert b"exactly one" in lib.gsvc_rast_last_error()
     # both colour sources / none
     rc = lib.gsvc_rast_forward_launch(C.byref(s), 10, 0, 0x1000, None, None, 0x1000, 0x1000, 0x1000, None,
-                                      0x1000, 0x1000, None, 0, 0x1000, 0x1000, None, 0, None)
+                                      0x1000, 0x1000, None, 0, None, 0x1000, 0x1000, None, 0, None)
     assert rc == _lib.ERR_INVALID and b"SHs or precomputed colors" in lib.gsvc_rast_last_error()
     assert lib.gsvc_rast_wait_count(None, 1, None) == _lib.ERR_INVALID
     with pytest.raises(_lib.RasterizerError):
