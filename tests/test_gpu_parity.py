@@ -295,3 +295,57 @@ def test_packed_backward_writes_the_allreduce_buffer(cuda_device):
     for k, v, d in zip(names, views, dense):
         assert v.shape == d.shape and torch.equal(v, unpacked[k].reshape(d.shape))   # views of the buffer itself
     assert views[-1].shape == (9000, 3)
+
+
+def test_large_gaussians_nonzero_bg_scale_modifier_and_debug(cuda_device):
+    """Huge splats (hundreds of tiles each: the warp-cooperative scatter path), scale_modifier != 1, a
+    non-zero background in the backward, debug=True (sync + check after every kernel), float64 and
+    non-contiguous inputs."""
+    from gsvc_b200.rasterizer import GaussianRasterizer
+    scene = make_scene(P=600, W=320, H=200, F=320, seed=41, bg=(0.7, 0.2, 0.4), scale_modifier=1.7)
+    gs = scene["gaussians"]
+    gs["scales"] = gs["scales"] * 6.0                       # sigma up to ~180 px after the modifier
+    gs["opacities"] = gs["opacities"] * 0.3
+    gi = np_inputs(gs)
+    fo = c_oracle.forward(scene["oracle_settings"], gi["means3D"], gi["opacities"], gi["scales"], gi["rotations"],
+                          colors_precomp=gi["colors_precomp"])
+    assert (fo["pre"]["tiles_touched"] > 64).sum() > 50
+    rs = product_settings(scene, cuda_device, debug=True)
+    g = {k: v.to(cuda_device) for k, v in gs.items()}
+    # non-contiguous means3D / float64 colours must be accepted (converted), not mis-read
+    wide = torch.zeros(600, 6, device=cuda_device)
+    wide[:, ::2] = g["means3D"]
+    g["means3D"] = wide[:, ::2]
+    g["colors_precomp"] = g["colors_precomp"].double()
+    for v in g.values():
+        v.requires_grad_(True)
+    m2d = torch.zeros(600, 3, device=cuda_device, requires_grad=True)
+    color, radii, n = GaussianRasterizer(raster_settings=rs)(
+        means3D=g["means3D"], means2D=m2d, shs=None, colors_precomp=g["colors_precomp"], opacities=g["opacities"],
+        scales=g["scales"], rotations=g["rotations"], cov3D_precomp=None)
+    assert n == fo["num_rendered"]
+    np.testing.assert_array_equal(radii.cpu().numpy(), fo["radii"])
+    _check_forward(fo, color)
+    dL = torch.randn(color.shape, generator=torch.Generator().manual_seed(12))
+    color.backward(dL.to(cuda_device))
+    go = c_oracle.backward(fo, dL.numpy())
+    ok = ~go["touched_fragile"]
+    for k in ("means3D", "scales", "rotations", "opacities", "colors_precomp"):
+        a = g[k].grad.float().cpu().numpy().reshape(600, -1)[ok]
+        b = go[k].reshape(600, -1)[ok]
+        assert _rel_err(a, b) <= GRAD_RTOL, f"{k}: {_rel_err(a, b)}"
+    assert _rel_err(m2d.grad.cpu().numpy()[ok], go["means2D"][ok]) <= GRAD_RTOL
+
+
+def test_retain_graph_double_backward_is_consistent(cuda_device):
+    """A second backward over the same forward state must clear the dirtied accumulators first."""
+    scene = make_scene(P=5000, W=128, H=96, F=128, seed=19)
+    g, m2d, color, radii, n = _run_product(scene, cuda_device)
+    dL = torch.randn(color.shape, generator=torch.Generator().manual_seed(3)).to(cuda_device)
+    ins = [g["means3D"], g["scales"], g["opacities"]]
+    a = torch.autograd.grad(color, ins, grad_outputs=dL, retain_graph=True)
+    b = torch.autograd.grad(color, ins, grad_outputs=dL, retain_graph=True)
+    c = torch.autograd.grad(color, ins, grad_outputs=2 * dL)
+    for x, y, z in zip(a, b, c):
+        assert (x - y).abs().max() <= 1e-5 * x.abs().max()
+        assert (z - 2 * x).abs().max() <= 1e-5 * z.abs().max()
