@@ -2,28 +2,32 @@
 // (the reference reaches them through
 //  /root/reference/ortho_gaussian_renderer/renderer.py:90-98 and loss.backward(), pipeline/train.py:462).
 //
-// One CTA per 16x16 tile; its 8 warps each own an 8x4-pixel block (one pixel per lane).  Gaussians
-// of the tile's depth-sorted list are gathered with float4 loads into shared memory in batches of
-// 256.  Both kernels are instruction-issue bound (ncu: >85 % issue-active, <2 % DRAM), so the design
-// goal is to execute fewer and cheaper pixel-Gaussian evaluations, not to move fewer bytes:
-//   * exact sub-tile culling — per chunk of 32 staged Gaussians every lane tests ONE Gaussian's
-//     alpha >= 1/255 bounding box (half extents precomputed by the preprocess kernel, inflated for
-//     rounding) against the warp's 8x4 block; a ballot gives the warp its private work list.  Only
-//     pairs the reference would `continue` past (alpha < 1/255, no state change) are skipped, so
-//     results are unchanged;
-//   * the conic is pre-scaled by -log2(e)/2 while staging, so a pair costs 5 FP32 ops + one
+// One CTA (128 threads) per 16x16 tile; each of its 4 warps owns an 8x8-pixel block and every lane
+// two pixels of it (rows r and r+4 of one column).  Gaussians of the tile's depth-sorted list are
+// gathered with float4 loads into shared memory in batches of 256.  Both kernels are
+// instruction-issue bound (ncu: ~85 % issue-active, < 5 % DRAM), so the design goal is to execute
+// fewer and cheaper pixel-Gaussian evaluations, not to move fewer bytes:
+//   * exact sub-tile culling — per chunk of 32 staged Gaussians every lane tests ONE Gaussian: can
+//     its alpha >= 1/255 ellipse reach the warp's 8x8 block (closed-form maximum of the concave
+//     exponent over the rectangle)?  A ballot gives the warp its private work list.  Only pairs the
+//     reference would `continue` past (alpha < 1/255, no state change) are skipped, so results are
+//     unchanged;
+//   * two pixels per lane share the Gaussian fetch, the x terms of the exponent, the loop control and
+//     — in the backward — the warp reduction, which is the single most expensive step;
+//   * the conic is pre-scaled by -log2(e)/2 while staging, so a pair costs ~5 FP32 ops + one
 //     ex2.approx (MUFU) up to the alpha test; staged records are 48 B interleaved so one address
 //     serves all three LDS.128;
-//   * warp-ballot early termination once all 32 pixels of a block are saturated (T < 1e-4 stop rule);
-//   * backward: the 9 per-Gaussian gradient terms are reduced across the warp with a
-//     transpose-butterfly (14 shuffles instead of 45) and only then added to global memory, 8 lanes
-//     issuing the 8 atomics of one Gaussian in a single instruction.
+//   * warp-ballot early termination once all 64 pixels of a block are saturated (T < 1e-4 stop rule);
+//   * backward: branch-free per-pair arithmetic on raw moments (the per-Gaussian kernel finishes
+//     dL/dpix and dL/dconic), 9 sums reduced across the warp with a transpose-butterfly (14 shuffles
+//     instead of 45), and 9 lanes issue the 9 atomics of one Gaussian in a single instruction.
 #include "common.cuh"
 
 namespace gsvc {
 
-constexpr int BLEND_THREADS = TILE_PIX;  // 256
-constexpr int BATCH = 256;
+constexpr int BLEND_THREADS = 128;  // 4 warps x (8x8 pixels), 2 pixels per lane
+constexpr int BLEND_WARPS = BLEND_THREADS / 32;
+constexpr int BATCH = 256;          // Gaussians staged per round (2 per thread)
 constexpr unsigned FULL = 0xffffffffu;
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -41,20 +45,20 @@ __device__ __forceinline__ float rcp_approx(float x)
 }
 
 struct BlockGeom {
-    int px, py;                    // this lane's pixel
-    float xmin, xmax, ymin, ymax;  // pixel-centre bounds of the warp's 8x4 block
+    int px, py;                    // this lane's first pixel; the second one is (px, py + 4)
+    float xmin, xmax, ymin, ymax;  // pixel-centre bounds of the warp's 8x8 block
 };
 
 __device__ __forceinline__ BlockGeom block_geom(int tile, int gx, int tid)
 {
     const int tx = tile % gx, ty = tile / gx;
     const int warp = tid >> 5, lane = tid & 31;
-    const int bx0 = tx * TILE + (warp & 1) * 8, by0 = ty * TILE + (warp >> 1) * 4;
+    const int bx0 = tx * TILE + (warp & 1) * 8, by0 = ty * TILE + (warp >> 1) * 8;
     BlockGeom b;
     b.px = bx0 + (lane & 7);
     b.py = by0 + (lane >> 3);
     b.xmin = (float)bx0; b.xmax = (float)(bx0 + 7);
-    b.ymin = (float)by0; b.ymax = (float)(by0 + 3);
+    b.ymin = (float)by0; b.ymax = (float)(by0 + 7);
     return b;
 }
 
@@ -114,26 +118,31 @@ render_forward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, un
     const int tile = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31;
     const BlockGeom bg = block_geom(tile, s.gx, tid);
-    const bool inside = bg.px < s.W && bg.py < s.H;
+    const bool inA = bg.px < s.W && bg.py < s.H, inB = bg.px < s.W && bg.py + 4 < s.H;
     const float pxf = (float)bg.px, pyf = (float)bg.py;
 
     const uint2 rg = im.ranges[tile];
     if ((unsigned long long)rg.y > cap) return;  // capacity overflow: host re-runs with a larger buffer
     const int n = (int)(rg.y - rg.x);
 
-    float T = 1.f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
-    unsigned int last = 0;
-    bool done = !inside;
+    float TA = 1.f, A0 = 0.f, A1 = 0.f, A2 = 0.f;   // pixel A = (px, py)
+    float TB = 1.f, B0 = 0.f, B1 = 0.f, B2 = 0.f;   // pixel B = (px, py + 4)
+    unsigned int lastA = 0, lastB = 0;
+    bool doneA = !inA, doneB = !inB;
 
     for (int base = 0; base < n; base += BATCH) {
         // block-wide vote doubles as the barrier that protects the staging buffer
-        if (__syncthreads_count(done) == BLEND_THREADS) break;
-        if (base + tid < n) stage(s_feat, tid, geo, bin.point_list[rg.x + base + tid]);
+        if (__syncthreads_count(doneA && doneB) == BLEND_THREADS) break;
+#pragma unroll
+        for (int r = 0; r < BATCH / BLEND_THREADS; r++) {
+            const int slot = tid + r * BLEND_THREADS;
+            if (base + slot < n) stage(s_feat, slot, geo, bin.point_list[rg.x + base + slot]);
+        }
         __syncthreads();
         const int cnt = min(BATCH, n - base);
         for (int c = 0; c < cnt; c += 32) {
-            // warp-ballot early termination: all 32 pixels of the block saturated
-            if (__ballot_sync(FULL, !done) == 0u) break;
+            // warp-ballot early termination: all 64 pixels of the block saturated
+            if (__ballot_sync(FULL, !(doneA && doneB)) == 0u) break;
             bool hit = false;
             if (c + lane < cnt) hit = block_hit(bg, s_feat + 3 * (c + lane));
             unsigned int m = __ballot_sync(FULL, hit);
@@ -145,35 +154,55 @@ render_forward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, un
                 const float4* e = chunk + 3 * k;
                 const float4 f0 = e[0];
                 const float4 f1 = e[1];
-                const float dx = f0.x - pxf, dy = f0.y - pyf;
-                const float u = fmaf(f1.x, dx, f1.y * dy);            // A' dx + B' dy
-                const float p2 = fmaf(u, dx, (f1.z * dy) * dy);       // log2 of the falloff
-                const float alpha = fminf(ALPHA_MAX, f1.w * ex2_approx(p2));
+                const float dx = f0.x - pxf, dyA = f0.y - pyf, dyB = dyA - 4.f;
+                const float t = f1.x * dx;                                          // A' dx
+                const float qA = fmaf(fmaf(f1.y, dyA, t), dx, (f1.z * dyA) * dyA);  // log2 of the falloff
+                const float qB = fmaf(fmaf(f1.y, dyB, t), dx, (f1.z * dyB) * dyB);
+                const float aA = fminf(ALPHA_MAX, f1.w * ex2_approx(qA));
+                const float aB = fminf(ALPHA_MAX, f1.w * ex2_approx(qB));
                 // the reference `continue`s on power > 0 and on alpha < 1/255
-                if (!done && !(p2 > 0.f) && !(alpha < ALPHA_MIN)) {
-                    const float test_T = T * (1.f - alpha);
-                    if (test_T < T_STOP) {
-                        done = true;
-                    } else {
-                        const float4 f2 = e[2];
-                        const float w = alpha * T;
-                        C0 = fmaf(f2.x, w, C0);
-                        C1 = fmaf(f2.y, w, C1);
-                        C2 = fmaf(f2.z, w, C2);
-                        T = test_T;
-                        last = pos1 + (unsigned int)k;
+                const bool okA = !doneA && !(qA > 0.f) && !(aA < ALPHA_MIN);
+                const bool okB = !doneB && !(qB > 0.f) && !(aB < ALPHA_MIN);
+                if (okA || okB) {
+                    const float4 f2 = e[2];
+                    const unsigned int pos = pos1 + (unsigned int)k;
+                    const float tTA = TA * (1.f - aA), tTB = TB * (1.f - aB);
+                    const bool stopA = okA && (tTA < T_STOP), stopB = okB && (tTB < T_STOP);
+                    doneA |= stopA;
+                    doneB |= stopB;
+                    if (okA && !stopA) {
+                        const float w = aA * TA;
+                        A0 = fmaf(f2.x, w, A0); A1 = fmaf(f2.y, w, A1); A2 = fmaf(f2.z, w, A2);
+                        TA = tTA;
+                        lastA = pos;
+                    }
+                    if (okB && !stopB) {
+                        const float w = aB * TB;
+                        B0 = fmaf(f2.x, w, B0); B1 = fmaf(f2.y, w, B1); B2 = fmaf(f2.z, w, B2);
+                        TB = tTB;
+                        lastB = pos;
                     }
                 }
             }
         }
     }
-    if (inside) {
-        const size_t N = (size_t)s.W * s.H, pix = (size_t)bg.py * s.W + bg.px;
-        out_color[pix] = C0 + T * __ldg(s.bg + 0);
-        out_color[N + pix] = C1 + T * __ldg(s.bg + 1);
-        out_color[2 * N + pix] = C2 + T * __ldg(s.bg + 2);
-        im.final_T[pix] = T;
-        im.n_contrib[pix] = last;
+    const size_t N = (size_t)s.W * s.H;
+    const float bg0 = __ldg(s.bg + 0), bg1 = __ldg(s.bg + 1), bg2 = __ldg(s.bg + 2);
+    if (inA) {
+        const size_t pix = (size_t)bg.py * s.W + bg.px;
+        out_color[pix] = A0 + TA * bg0;
+        out_color[N + pix] = A1 + TA * bg1;
+        out_color[2 * N + pix] = A2 + TA * bg2;
+        im.final_T[pix] = TA;
+        im.n_contrib[pix] = lastA;
+    }
+    if (inB) {
+        const size_t pix = (size_t)(bg.py + 4) * s.W + bg.px;
+        out_color[pix] = B0 + TB * bg0;
+        out_color[N + pix] = B1 + TB * bg1;
+        out_color[2 * N + pix] = B2 + TB * bg2;
+        im.final_T[pix] = TB;
+        im.n_contrib[pix] = lastB;
     }
 }
 
@@ -227,57 +256,102 @@ __device__ __forceinline__ float warp_sum(float v)
     return v;
 }
 
+// Per-pixel replay state of the backward.
+struct PixBwd {
+    float T, T_final_neg_bg;   // running transmittance; -T_final * (bg . dL/dC)
+    float g0, g1, g2;          // dL/dC of the pixel
+    float a0, a1, a2;          // colour composited behind the current Gaussian
+    float last_alpha;          // alpha of the previous (deeper) processed Gaussian
+    unsigned int last;         // n_contrib
+};
+
+// One (pixel, Gaussian) pair, branch-free: a pair that does not contribute is blended with alpha = 0,
+// which leaves T, the behind-colour recursion and every sum unchanged (bit-identically).
+// Returns w = opacity * Gs * dL/dalpha (the weight of the conic / position moments); adds the colour
+// and opacity terms to (s_op, s_r, s_g, s_b).
+__device__ __forceinline__ float pair_backward(PixBwd& p, bool use, float alpha, float Gs, float opacity,
+                                               const float4 f2, float lc0, float lc1, float lc2, float& s_op,
+                                               float& s_r, float& s_g, float& s_b)
+{
+    const float ae = use ? alpha : 0.f;
+    const float ra = rcp_approx(1.f - ae);
+    p.T *= ra;
+    const float om = 1.f - p.last_alpha;
+    p.a0 = fmaf(p.last_alpha, lc0, om * p.a0);
+    p.a1 = fmaf(p.last_alpha, lc1, om * p.a1);
+    p.a2 = fmaf(p.last_alpha, lc2, om * p.a2);
+    p.last_alpha = ae;
+    float dla = (f2.x - p.a0) * p.g0 + (f2.y - p.a1) * p.g1 + (f2.z - p.a2) * p.g2;
+    dla = fmaf(dla, p.T, p.T_final_neg_bg * ra);
+    dla = use ? dla : 0.f;                 // U4: straight-through the 0.99 cap otherwise
+    const float dchan = ae * p.T;
+    s_r = fmaf(dchan, p.g0, s_r);
+    s_g = fmaf(dchan, p.g1, s_g);
+    s_b = fmaf(dchan, p.g2, s_b);
+    const float gd = Gs * dla;
+    s_op += gd;
+    return opacity * gd;
+}
+
 __global__ void __launch_bounds__(BLEND_THREADS)
 render_backward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, const float* __restrict__ dL_dout,
                        float* __restrict__ acc /* [P][12] */)
 {
     __shared__ float4 s_feat[3 * BATCH];
     __shared__ unsigned int s_id[BATCH];
-    __shared__ unsigned int s_max[BLEND_THREADS / 32];
+    __shared__ unsigned int s_max[BLEND_WARPS];
 
     pdl_prologue();
     const int tile = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31;
     const BlockGeom bg = block_geom(tile, s.gx, tid);
-    const bool inside = bg.px < s.W && bg.py < s.H;
+    const bool inA = bg.px < s.W && bg.py < s.H, inB = bg.px < s.W && bg.py + 4 < s.H;
     const float pxf = (float)bg.px, pyf = (float)bg.py;
-    const size_t N = (size_t)s.W * s.H, pix = (size_t)bg.py * s.W + bg.px;
+    const size_t N = (size_t)s.W * s.H;
+    const size_t pixA = (size_t)bg.py * s.W + bg.px, pixB = (size_t)(bg.py + 4) * s.W + bg.px;
 
     const uint2 rg = im.ranges[tile];
     const int n = (int)(rg.y - rg.x);
     if (n <= 0) return;
 
-    const float T_final = inside ? im.final_T[pix] : 0.f;
-    const unsigned int last = inside ? im.n_contrib[pix] : 0u;
-    float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-    if (inside) { g0 = dL_dout[pix]; g1 = dL_dout[N + pix]; g2 = dL_dout[2 * N + pix]; }
-    const float bgT = -T_final * (__ldg(s.bg) * g0 + __ldg(s.bg + 1) * g1 + __ldg(s.bg + 2) * g2);
+    const float bg0 = __ldg(s.bg), bg1 = __ldg(s.bg + 1), bg2 = __ldg(s.bg + 2);
+    PixBwd A{}, B{};
+    if (inA) {
+        A.T = im.final_T[pixA]; A.last = im.n_contrib[pixA];
+        A.g0 = dL_dout[pixA]; A.g1 = dL_dout[N + pixA]; A.g2 = dL_dout[2 * N + pixA];
+        A.T_final_neg_bg = -A.T * (bg0 * A.g0 + bg1 * A.g1 + bg2 * A.g2);
+    }
+    if (inB) {
+        B.T = im.final_T[pixB]; B.last = im.n_contrib[pixB];
+        B.g0 = dL_dout[pixB]; B.g1 = dL_dout[N + pixB]; B.g2 = dL_dout[2 * N + pixB];
+        B.T_final_neg_bg = -B.T * (bg0 * B.g0 + bg1 * B.g1 + bg2 * B.g2);
+    }
 
     // nothing behind the deepest contributor of the tile matters: start the replay there
-    const unsigned int wmax = __reduce_max_sync(FULL, last);
+    const unsigned int wmax = __reduce_max_sync(FULL, max(A.last, B.last));
     if (lane == 0) s_max[tid >> 5] = wmax;
     __syncthreads();
     unsigned int bmax = 0;
 #pragma unroll
-    for (int w = 0; w < BLEND_THREADS / 32; w++) bmax = max(bmax, s_max[w]);
+    for (int w = 0; w < BLEND_WARPS; w++) bmax = max(bmax, s_max[w]);
     const int m_len = (int)bmax;  // list entries [0, m_len) are replayed, back to front
 
     // lanes 0,4,..,28 own the 8 reduced sums (index lane/4), lane 1 the ninth: one atomic instruction
     const bool red_lane = (lane & 3) == 0 || lane == 1;
     const int red_off = lane == 1 ? 8 : (lane >> 2);
-
-    float T = T_final;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f;      // colour composited behind the current Gaussian
-    float lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;   // previous (deeper) contributor's colour and alpha
-    float last_alpha = 0.f;
+    float lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;   // colour of the previous (deeper) processed Gaussian
 
     for (int base = 0; base < m_len; base += BATCH) {
         __syncthreads();
-        const int kpos = m_len - 1 - (base + tid);  // list position staged by this thread
-        if (kpos >= 0) {
-            const unsigned int id = bin.point_list[rg.x + kpos];
-            s_id[tid] = id;
-            stage(s_feat, tid, geo, id);
+#pragma unroll
+        for (int r = 0; r < BATCH / BLEND_THREADS; r++) {
+            const int slot = tid + r * BLEND_THREADS;
+            const int kpos = m_len - 1 - (base + slot);  // list position staged in this slot
+            if (kpos >= 0) {
+                const unsigned int id = bin.point_list[rg.x + kpos];
+                s_id[slot] = id;
+                stage(s_feat, slot, geo, id);
+            }
         }
         __syncthreads();
         const int cnt = min(BATCH, m_len - base);
@@ -295,45 +369,35 @@ render_backward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, c
                 const float4* e = chunk + 3 * k;
                 const float4 f0 = e[0];
                 const float4 f1 = e[1];
-                const float dx = f0.x - pxf, dy = f0.y - pyf;
-                const float u = fmaf(f1.x, dx, f1.y * dy);
-                const float p2 = fmaf(u, dx, (f1.z * dy) * dy);
-                const float Gs = ex2_approx(p2);
-                const float alpha = fminf(ALPHA_MAX, f1.w * Gs);
-                const bool use = ((unsigned int)(pos0 - k) < last) && !(p2 > 0.f) && !(alpha < ALPHA_MIN);
-                if (!__any_sync(FULL, use)) continue;
+                const float dx = f0.x - pxf, dyA = f0.y - pyf, dyB = dyA - 4.f;
+                const float t = f1.x * dx;
+                const float qA = fmaf(fmaf(f1.y, dyA, t), dx, (f1.z * dyA) * dyA);
+                const float qB = fmaf(fmaf(f1.y, dyB, t), dx, (f1.z * dyB) * dyB);
+                const float GsA = ex2_approx(qA), GsB = ex2_approx(qB);
+                const float aA = fminf(ALPHA_MAX, f1.w * GsA), aB = fminf(ALPHA_MAX, f1.w * GsB);
+                const unsigned int pos = (unsigned int)(pos0 - k);
+                const bool useA = (pos < A.last) && !(qA > 0.f) && !(aA < ALPHA_MIN);
+                const bool useB = (pos < B.last) && !(qB > 0.f) && !(aB < ALPHA_MIN);
+                if (!__any_sync(FULL, useA || useB)) continue;
 
-                // Branch-free: a pair that does not contribute is blended with alpha = 0, which leaves T, the
-                // behind-colour recursion and every sum unchanged (bit-identically), so no lane diverges.
                 // Per-pair sums are raw moments of w = Gs * dL/dGs; the per-Gaussian kernel turns them into
-                // dL/dpix and dL/dconic (it knows A,B,C), which keeps 9 FP32 ops out of this loop:
+                // dL/dpix and dL/dconic (it knows A,B,C), which keeps ~9 FP32 ops out of this loop:
                 //   v = (S w dx, S w dy, S w dx^2, S w dx dy, S w dy^2, S Gs dL/dalpha, dL/dr, dL/dg), d_b = dL/db
                 const float4 f2 = e[2];
-                const float ae = use ? alpha : 0.f;
-                const float ra = rcp_approx(1.f - ae);
-                T *= ra;
-                const float om = 1.f - last_alpha;
-                a0 = fmaf(last_alpha, lc0, om * a0);
-                a1 = fmaf(last_alpha, lc1, om * a1);
-                a2 = fmaf(last_alpha, lc2, om * a2);
-                lc0 = f2.x; lc1 = f2.y; lc2 = f2.z;
-                last_alpha = ae;
-                float dla = (f2.x - a0) * g0 + (f2.y - a1) * g1 + (f2.z - a2) * g2;
-                dla = fmaf(dla, T, bgT * ra);
-                dla = use ? dla : 0.f;                       // U4: straight-through the 0.99 cap otherwise
-                const float dchan = ae * T;
                 float v[8];
-                v[5] = Gs * dla;
-                const float w = f1.w * v[5];
-                v[0] = w * dx;
-                v[1] = w * dy;
+                float d_b = 0.f;
+                v[5] = 0.f; v[6] = 0.f; v[7] = 0.f;
+                const float wA = pair_backward(A, useA, aA, GsA, f1.w, f2, lc0, lc1, lc2, v[5], v[6], v[7], d_b);
+                const float wB = pair_backward(B, useB, aB, GsB, f1.w, f2, lc0, lc1, lc2, v[5], v[6], v[7], d_b);
+                lc0 = f2.x; lc1 = f2.y; lc2 = f2.z;
+                const float wyA = wA * dyA, wyB = wB * dyB;
+                v[0] = (wA + wB) * dx;
+                v[1] = wyA + wyB;
                 v[2] = v[0] * dx;
-                v[3] = v[0] * dy;
-                v[4] = v[1] * dy;
-                v[6] = dchan * g0;
-                v[7] = dchan * g1;
+                v[3] = v[1] * dx;
+                v[4] = fmaf(wyA, dyA, wyB * dyB);
                 const float sum8 = warp_reduce8(v, lane);
-                const float d_b = warp_sum(dchan * g2);
+                d_b = warp_sum(d_b);
                 if (red_lane) atomicAdd(acc + (size_t)s_id[c + k] * 12 + red_off, lane == 1 ? d_b : sum8);
             }
         }
