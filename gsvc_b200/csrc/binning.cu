@@ -96,22 +96,10 @@ cudaError_t launch_tile_scan(const DevSettings& s, ImageView im, unsigned long l
 }
 
 // ---- scatter: one instance (depth_key << 32 | id) per (Gaussian, tile in rect) into its tile bucket ----
-// Slot = tile_offset + atomicAdd(cursor): the atomic's round trip (~700 cycles) is the cost, so
-//   * small rectangles (<= SCATTER_SMALL tiles, the common case) are handled by their own lane with
-//     all atomics issued before the first store (independent round trips overlap);
-//   * large rectangles (up to hundreds of tiles for a 30 px sigma) are spread over the 32 lanes of
-//     the warp, so no lane serialises a long chain.
-constexpr int SCATTER_SMALL = 8;
-
-__device__ __forceinline__ void scatter_one(int t, unsigned long long item, ImageView& im, BinView& bin,
-                                            unsigned long long cap)
-{
-    const unsigned long long slot = (unsigned long long)im.tile_offset[t] + atomicAdd(im.tile_cursor + t, 1u);
-    if (slot < cap)
-        bin.inst[slot] = item;
-    else
-        im.hdr->overflow = 1u;
-}
+// Slot = tile_offset + atomicAdd(cursor).  The atomic's round trip is the cost, so the warp walks the
+// flattened list of all its (Gaussian, tile) pairs (common.cuh) and issues SCATTER_ILP full-width atomics
+// before it consumes the first result: a warp needs ~(pairs / 128) round trips, whatever the rectangle sizes.
+constexpr int SCATTER_ILP = 4;
 
 __global__ void __launch_bounds__(256) scatter_kernel(int P, int gx, GeomView geo, ImageView im, BinView bin,
                                                       unsigned long long cap)
@@ -126,39 +114,28 @@ __global__ void __launch_bounds__(256) scatter_kernel(int P, int gx, GeomView ge
     unsigned long long item = 0ull;
     if (area > 0) item = ((unsigned long long)ordered_u32(geo.feat2[g].w) << 32) | (unsigned int)g;
 
-    if (area > 0 && area <= SCATTER_SMALL) {
-        unsigned int slot[SCATTER_SMALL];
-        int tl[SCATTER_SMALL];
+    const WarpTiles wt = warp_tiles_begin(area, r.x, r.y, w > 0 ? w : 1);
+    for (int base = 0; base < wt.total; base += 32 * SCATTER_ILP) {
+        int tile[SCATTER_ILP];
+        unsigned int slot[SCATTER_ILP];
+        unsigned long long it[SCATTER_ILP];
 #pragma unroll
-        for (int i = 0; i < SCATTER_SMALL; i++) {
-            tl[i] = -1;
-            if (i < area) {
-                const int ty = r.y + i / w, tx = r.x + i - (i / w) * w;
-                tl[i] = ty * gx + tx;
-                slot[i] = atomicAdd(im.tile_cursor + tl[i], 1u);
-            }
+        for (int u = 0; u < SCATTER_ILP; u++) {
+            int owner;
+            tile[u] = warp_tiles_get(wt, base + 32 * u + lane, gx, owner);
+            it[u] = __shfl_sync(0xffffffffu, item, owner);
+            slot[u] = 0u;
+            if (tile[u] >= 0) slot[u] = atomicAdd(im.tile_cursor + tile[u], 1u);
         }
 #pragma unroll
-        for (int i = 0; i < SCATTER_SMALL; i++) {
-            if (tl[i] >= 0) {
-                const unsigned long long sl = (unsigned long long)im.tile_offset[tl[i]] + slot[i];
+        for (int u = 0; u < SCATTER_ILP; u++) {
+            if (tile[u] >= 0) {
+                const unsigned long long sl = (unsigned long long)im.tile_offset[tile[u]] + slot[u];
                 if (sl < cap)
-                    bin.inst[sl] = item;
+                    bin.inst[sl] = it[u];
                 else
                     im.hdr->overflow = 1u;
             }
-        }
-    }
-    unsigned int big = __ballot_sync(0xffffffffu, area > SCATTER_SMALL);
-    while (big) {
-        const int src = __ffs(big) - 1;
-        big &= big - 1;
-        const int bx = __shfl_sync(0xffffffffu, (int)r.x, src), by = __shfl_sync(0xffffffffu, (int)r.y, src);
-        const int bw = __shfl_sync(0xffffffffu, w, src), ba = __shfl_sync(0xffffffffu, area, src);
-        const unsigned long long bitem = __shfl_sync(0xffffffffu, item, src);
-        for (int i = lane; i < ba; i += 32) {
-            const int row = i / bw;
-            scatter_one((by + row) * gx + bx + (i - row * bw), bitem, im, bin, cap);
         }
     }
 }
@@ -213,6 +190,61 @@ __device__ __forceinline__ void bitonic_sort(Ptr a, int n, int tid, int nthreads
     }
 }
 
+// Warp-level specialisation: padded size 2^LG known at compile time, so every stage is straight-line code
+// (constant index arithmetic, constant trip counts) — roughly half the instructions of the generic loop.
+template <int LG>
+__device__ __forceinline__ void bitonic_warp(unsigned long long* a, int n, int lane)
+{
+    constexpr int HALF = (1 << LG) >> 1;
+#pragma unroll
+    for (int p = 1; p <= LG; p++) {
+        const int k = 1 << p, hk = k >> 1;
+#pragma unroll
+        for (int i0 = 0; i0 < HALF; i0 += 32) {
+            const int i = i0 + lane;
+            if (HALF >= 32 || i < HALF) {
+                const int blk = i >> (p - 1), pos = i & (hk - 1);
+                const int lo = blk * k + pos, hi = blk * k + k - 1 - pos;
+                if (hi < n) {
+                    const unsigned long long x = a[lo], y = a[hi];
+                    if (x > y) { a[lo] = y; a[hi] = x; }
+                }
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = p - 2; q >= 0; q--) {
+            const int j = 1 << q;
+#pragma unroll
+            for (int i0 = 0; i0 < HALF; i0 += 32) {
+                const int i = i0 + lane;
+                if (HALF >= 32 || i < HALF) {
+                    const int lo = ((i >> q) << (q + 1)) + (i & (j - 1)), hi = lo + j;
+                    if (hi < n) {
+                        const unsigned long long x = a[lo], y = a[hi];
+                        if (x > y) { a[lo] = y; a[hi] = x; }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+__device__ __forceinline__ void bitonic_warp_dispatch(unsigned long long* a, int n, int lane)
+{
+    if (n <= 1) return;
+    if (n <= 2) bitonic_warp<1>(a, n, lane);
+    else if (n <= 4) bitonic_warp<2>(a, n, lane);
+    else if (n <= 8) bitonic_warp<3>(a, n, lane);
+    else if (n <= 16) bitonic_warp<4>(a, n, lane);
+    else if (n <= 32) bitonic_warp<5>(a, n, lane);
+    else if (n <= 64) bitonic_warp<6>(a, n, lane);
+    else if (n <= 128) bitonic_warp<7>(a, n, lane);
+    else if (n <= 256) bitonic_warp<8>(a, n, lane);
+    else bitonic_warp<9>(a, n, lane);
+}
+
 __global__ void __launch_bounds__(SORT_THREADS) sort_tiles_kernel(int T, ImageView im, BinView bin,
                                                                   unsigned long long cap)
 {
@@ -234,7 +266,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_tiles_kernel(int T, ImageVi
         const unsigned long long* src = bin.inst + rg.x;
         for (int i = lane; i < n; i += 32) mine[i] = src[i];
         __syncwarp();
-        bitonic_sort<false>(mine, n, lane, 32);
+        bitonic_warp_dispatch(mine, n, lane);
         for (int i = lane; i < n; i += 32) {
             const unsigned long long v = mine[i];
             bin.point_list[rg.x + i] = (unsigned int)v;

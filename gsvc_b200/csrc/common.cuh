@@ -177,6 +177,50 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, c
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// ---- warp-flattened enumeration of (Gaussian, tile) pairs ---------------------------------------------
+// Every lane owns one Gaussian with a tile rectangle of `area` tiles (0 = none).  Instead of each lane
+// looping over its own rectangle (a divergent loop whose length is the largest rectangle of the warp, up to
+// hundreds of tiles), the warp enumerates the concatenation of all its rectangles 32 pairs at a time:
+// pair index -> owner lane by a 5-step binary search over the inclusive scan of the areas.
+struct WarpTiles {
+    int incl, excl, total;  // inclusive / exclusive scan of area over the warp, and its total
+    int rx, ry, rw;         // this lane's rectangle origin and width
+};
+
+__device__ __forceinline__ WarpTiles warp_tiles_begin(int area, int rx, int ry, int rw)
+{
+    const int lane = threadIdx.x & 31;
+    int v = area;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += o;
+    }
+    WarpTiles w;
+    w.incl = v; w.excl = v - area; w.total = __shfl_sync(0xffffffffu, v, 31);
+    w.rx = rx; w.ry = ry; w.rw = rw;
+    return w;
+}
+
+// Pair `idx` of the warp (all 32 lanes must call): returns its tile id (or -1 if idx >= total) and the owner lane.
+__device__ __forceinline__ int warp_tiles_get(const WarpTiles& w, int idx, int gx, int& owner)
+{
+    int o = 0;
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+        const int v = __shfl_sync(0xffffffffu, w.incl, o + step - 1);
+        if (v <= idx) o += step;
+    }
+    o = min(o, 31);
+    const int local = idx - __shfl_sync(0xffffffffu, w.excl, o);
+    const int rw = __shfl_sync(0xffffffffu, w.rw, o);
+    const int rx = __shfl_sync(0xffffffffu, w.rx, o), ry = __shfl_sync(0xffffffffu, w.ry, o);
+    owner = o;
+    if (idx >= w.total) return -1;
+    const int row = local / rw;
+    return (ry + row) * gx + rx + (local - row * rw);
+}
+
 // ---- launch stages implemented in the .cu files ------------------------------------------------
 struct PreInputs {
     int P;

@@ -109,9 +109,13 @@ __global__ void __launch_bounds__(256) preprocess_kernel(DevSettings s, PreInput
                                                          float4* __restrict__ acc_to_zero)
 {
     pdl_prologue();
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= in.P) return;
-    if (!FILTER && acc_to_zero) {
+    // Lanes past the end stay in the warp (they redo the last Gaussian with all stores masked) so that the
+    // warp-wide tile walk at the end runs converged.
+    const int g_raw = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = g_raw < in.P;
+    if (FILTER && !valid) return;
+    const int g = valid ? g_raw : in.P - 1;
+    if (!FILTER && acc_to_zero && valid) {
         // the blend backward accumulates into these 9 sums with atomics: zero them here (a store the
         // stream kernel hides) instead of a separate memset launch in the backward
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -129,7 +133,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(DevSettings s, PreInput
     int rminx = 0, rminy = 0, rmaxx = 0, rmaxy = 0;
     float a = 0.f, b = 0.f, c = 0.f, det = 0.f, px = 0.f, py = 0.f;
     // U6: TSW slab — keep |z_view| <= threshold (preprocess.py:109-116)
-    bool ok = !(fabsf(vz) > s.threshold);
+    bool ok = valid && !(fabsf(vz) > s.threshold);
     if (ok) {
         float cov[6];
         if (in.cov3D_precomp) {
@@ -158,45 +162,51 @@ __global__ void __launch_bounds__(256) preprocess_kernel(DevSettings s, PreInput
         rmaxy = (int)fminf(fgy, fmaxf(0.f, truncf((py + rad_f + (float)(TILE - 1)) / ft)));
         ok = (rmaxx - rminx) * (rmaxy - rminy) > 0;
     }
-    radii[g] = ok ? radius : 0;
+    if (valid) radii[g] = ok ? radius : 0;
     if (FILTER) return;
 
-    if (!ok) {
+    if (ok) {
+        const float det_inv = 1.f / det;
+        const float cA = c * det_inv, cB = -b * det_inv, cC = a * det_inv;
+        const float op = __ldg(in.opacities + g);
+        float rgb[3];
+        if (in.colors_precomp) {
+            rgb[0] = __ldg(in.colors_precomp + 3 * g);
+            rgb[1] = __ldg(in.colors_precomp + 3 * g + 1);
+            rgb[2] = __ldg(in.colors_precomp + 3 * g + 2);
+        } else {
+            uint8_t cl[3];
+            sh_to_rgb(s.sh_degree, in.shs + (size_t)g * s.sh_M * 3, p, s.campos, rgb, cl);
+            geo.clamped[3 * (size_t)g] = cl[0];
+            geo.clamped[3 * (size_t)g + 1] = cl[1];
+            geo.clamped[3 * (size_t)g + 2] = cl[2];
+        }
+        // Half extents of the alpha >= 1/255 ellipse's bounding box (kept for diagnostics; the blend kernels
+        // cull with the exact ellipse test): alpha = op*exp(power) >= 1/255  <=>  1/2 d^T Q d <= ln(255 op).
+        float hx = 0.f, hy = 0.f;
+        const float tau = logf(255.0f * op);
+        if (tau > 0.f) {
+            const float t2 = 2.0f * tau * 1.0001f + 1e-4f;
+            hx = sqrtf(t2 * a) * 1.0001f + 1e-3f;
+            hy = sqrtf(t2 * c) * 1.0001f + 1e-3f;
+        }
+        geo.feat0[g] = make_float4(px, py, hx, hy);
+        geo.feat1[g] = make_float4(cA, cB, cC, op);
+        geo.feat2[g] = make_float4(rgb[0], rgb[1], rgb[2], vz);
+        geo.rect[g] = make_ushort4((unsigned short)rminx, (unsigned short)rminy, (unsigned short)rmaxx,
+                                   (unsigned short)rmaxy);
+    } else if (valid) {
         geo.rect[g] = make_ushort4(0, 0, 0, 0);
-        return;
     }
-    const float det_inv = 1.f / det;
-    const float cA = c * det_inv, cB = -b * det_inv, cC = a * det_inv;
-    const float op = __ldg(in.opacities + g);
-    float rgb[3];
-    if (in.colors_precomp) {
-        rgb[0] = __ldg(in.colors_precomp + 3 * g);
-        rgb[1] = __ldg(in.colors_precomp + 3 * g + 1);
-        rgb[2] = __ldg(in.colors_precomp + 3 * g + 2);
-    } else {
-        uint8_t cl[3];
-        sh_to_rgb(s.sh_degree, in.shs + (size_t)g * s.sh_M * 3, p, s.campos, rgb, cl);
-        geo.clamped[3 * (size_t)g] = cl[0];
-        geo.clamped[3 * (size_t)g + 1] = cl[1];
-        geo.clamped[3 * (size_t)g + 2] = cl[2];
+    // per-tile instance histogram (the counting sort's digit): the warp walks the flattened list of all its
+    // (Gaussian, tile) pairs, 32 at a time, so every RED instruction is full width whatever the rectangle sizes
+    const int rw = rmaxx - rminx;
+    const WarpTiles wt = warp_tiles_begin(ok ? rw * (rmaxy - rminy) : 0, rminx, rminy, rw > 0 ? rw : 1);
+    for (int base = 0; base < wt.total; base += 32) {
+        int owner;
+        const int t = warp_tiles_get(wt, base + (threadIdx.x & 31), s.gx, owner);
+        if (t >= 0) atomicAdd(tile_count + t, 1u);
     }
-    // Exact-culling aid: alpha = op*exp(power) >= 1/255  <=>  1/2 d^T Q d <= tau, tau = ln(255 op).  The ellipse's
-    // axis-aligned half extents are sqrt(2 tau a), sqrt(2 tau c) (cov2D = Q^-1).  Inflated so that fp32 rounding
-    // in the blend kernels can never make a culled pixel pass the 1/255 test.
-    float hx = 0.f, hy = 0.f;
-    const float tau = logf(255.0f * op);
-    if (tau > 0.f) {
-        const float t2 = 2.0f * tau * 1.0001f + 1e-4f;
-        hx = sqrtf(t2 * a) * 1.0001f + 1e-3f;
-        hy = sqrtf(t2 * c) * 1.0001f + 1e-3f;
-    }
-    geo.feat0[g] = make_float4(px, py, hx, hy);
-    geo.feat1[g] = make_float4(cA, cB, cC, op);
-    geo.feat2[g] = make_float4(rgb[0], rgb[1], rgb[2], vz);
-    geo.rect[g] = make_ushort4((unsigned short)rminx, (unsigned short)rminy, (unsigned short)rmaxx,
-                               (unsigned short)rmaxy);
-    for (int ty = rminy; ty < rmaxy; ty++)
-        for (int tx = rminx; tx < rmaxx; tx++) atomicAdd(tile_count + ty * s.gx + tx, 1u);
 }
 
 cudaError_t launch_visible_filter(const DevSettings& s, const PreInputs& in, int32_t* radii, cudaStream_t st)
