@@ -123,6 +123,14 @@ __global__ void __launch_bounds__(256) preprocess_kernel(DevSettings s, PreInput
     }
 
     const float p[3] = {__ldg(in.means3D + 3 * g), __ldg(in.means3D + 3 * g + 1), __ldg(in.means3D + 3 * g + 2)};
+    // scales / quaternion are fetched together with the position (one memory round trip per Gaussian, at the
+    // price of 28 wasted bytes for the third of the Gaussians the slab test culls)
+    float sc[3] = {0.f, 0.f, 0.f};
+    float4 q_pre = make_float4(1.f, 0.f, 0.f, 0.f);
+    if (!in.cov3D_precomp) {
+        sc[0] = __ldg(in.scales + 3 * g); sc[1] = __ldg(in.scales + 3 * g + 1); sc[2] = __ldg(in.scales + 3 * g + 2);
+        q_pre = __ldg(reinterpret_cast<const float4*>(in.rotations) + g);
+    }
     const float w0[3] = {ldV(s, 0, 0), ldV(s, 0, 1), ldV(s, 0, 2)};
     const float w1[3] = {ldV(s, 1, 0), ldV(s, 1, 1), ldV(s, 1, 2)};
     const float vx = w0[0] * p[0] + w0[1] * p[1] + w0[2] * p[2] + ldV(s, 0, 3);
@@ -140,9 +148,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(DevSettings s, PreInput
 #pragma unroll
             for (int k = 0; k < 6; k++) cov[k] = __ldg(in.cov3D_precomp + 6 * (size_t)g + k);
         } else {
-            const float sc[3] = {__ldg(in.scales + 3 * g), __ldg(in.scales + 3 * g + 1), __ldg(in.scales + 3 * g + 2)};
-            const float4 q = __ldg(reinterpret_cast<const float4*>(in.rotations) + g);
-            cov3d_from_scale_rot(sc, s.scale_modifier, q, cov);
+            cov3d_from_scale_rot(sc, s.scale_modifier, q_pre, cov);
         }
         cov2d_ortho(cov, w0, w1, s.scale, a, b, c);
         det = a * c - b * b;
