@@ -230,7 +230,7 @@ def run_product_arm(args, rank, local_rank, world):
             return rast(means3D=p["means3D"], means2D=p["means3D"], shs=None, colors_precomp=p["colors_precomp"],
                         opacities=p["opacities"], scales=p["scales"], rotations=p["rotations"], cov3D_precomp=None)
 
-    def train_step(p=params):
+    def train_step(p=params, packed=None):
         means2D = torch.zeros_like(p["means3D"], requires_grad=True)
         color, radii, n = rast(means3D=p["means3D"], means2D=means2D, shs=None, colors_precomp=p["colors_precomp"],
                                opacities=p["opacities"], scales=p["scales"], rotations=p["rotations"],
@@ -244,7 +244,11 @@ def run_product_arm(args, rank, local_rank, world):
                 grads = torch.autograd.grad(color, [p[k] for k, _ in GRAD_LAYOUT], grad_outputs=dL)
             pending[b] = dist.all_reduce(grad_bufs[b], op=dist.ReduceOp.SUM, async_op=True)
             return color, radii, n, grads, b
-        grads = torch.autograd.grad(color, [p[k] for k, _ in GRAD_LAYOUT], grad_outputs=dL)
+        if packed is not None:
+            with packed_backward(packed):
+                grads = torch.autograd.grad(color, [p[k] for k, _ in GRAD_LAYOUT], grad_outputs=dL)
+        else:
+            grads = torch.autograd.grad(color, [p[k] for k, _ in GRAD_LAYOUT], grad_outputs=dL)
         return color, radii, n, grads, None
 
     def sync_all():
@@ -312,11 +316,26 @@ def run_product_arm(args, rank, local_rank, world):
     # optimizer consumes) back to pinned host memory, inside the timed region.  Copies run on their own streams
     # and are double-buffered, as a host integration would do.  (The rendered image stays on the device, where
     # the reference computes its loss: pipeline/train.py:407-444.)
-    host_in = {k: v.detach().cpu().pin_memory() for k, v in g.items()}
+    # one pinned host buffer / one device buffer per slot: [means3D | colours | opacity | scales | rotation] segments
+    seg = [(k, w) for k, w in GRAD_LAYOUT]
+    host_flat = torch.empty(14 * P, dtype=torch.float32).pin_memory()
+    off = 0
+    for k, w in seg:
+        host_flat[off:off + w * P].copy_(g[k].detach().reshape(-1).cpu())
+        off += w * P
+    dev_flat = [torch.empty(14 * P, dtype=torch.float32, device=device) for _ in range(2)]
+
+    def views(flat):
+        out, o = {}, 0
+        for k, w in seg:
+            out[k] = flat[o:o + w * P].view(P, w)
+            o += w * P
+        return out
+
+    dev_in = [views(f) for f in dev_flat]
     host_grads = [torch.empty((P, 14), dtype=torch.float32).pin_memory() for _ in range(2)]
-    dev_in = [{k: torch.empty_like(v, device=device) for k, v in host_in.items()} for _ in range(2)]
     dev_grads = [torch.empty((P, 14), dtype=torch.float32, device=device) for _ in range(2)]
-    h2d = sum(v.numel() * 4 for v in host_in.values())
+    h2d = host_flat.numel() * 4
     d2h = host_grads[0].numel() * 4
     s_h2d, s_d2h = torch.cuda.Stream(device), torch.cuda.Stream(device)
     main = torch.cuda.current_stream(device)
@@ -327,26 +346,26 @@ def run_product_arm(args, rank, local_rank, world):
         b = i & 1
         with torch.cuda.stream(s_h2d):
             if compute_done[b] is not None:
-                s_h2d.wait_event(compute_done[b])        # the device input set is free again
-            for k, v in host_in.items():
-                dev_in[b][k].copy_(v, non_blocking=True)
+                s_h2d.wait_event(compute_done[b])        # the device input slot is free again
+            dev_flat[b].copy_(host_flat, non_blocking=True)
             in_ready = s_h2d.record_event()
         main.wait_event(in_ready)
         if d2h_done[b] is not None:
             main.wait_event(d2h_done[b])                 # the device gradient buffer has been read out
         p = {k: v.requires_grad_(True) for k, v in dev_in[b].items()}
-        color, radii, n, grads, gb = train_step(p)
         if world == 1:
-            pack_grads({k: gr for (k, _), gr in zip(GRAD_LAYOUT, grads)}, out=dev_grads[b])
+            color, radii, n, grads, _ = train_step(p, packed=dev_grads[b])   # backward writes the [P,14] buffer
+            src = dev_grads[b]
         else:
+            color, radii, n, grads, gb = train_step(p)
             pending[gb].wait()
-            dev_grads[b].copy_(grad_bufs[gb])
+            src = grad_bufs[gb]
         for v in dev_in[b].values():
             v.requires_grad_(False)
         compute_done[b] = main.record_event()
         with torch.cuda.stream(s_d2h):
             s_d2h.wait_event(compute_done[b])
-            host_grads[b].copy_(dev_grads[b], non_blocking=True)
+            host_grads[b].copy_(src, non_blocking=True)
             d2h_done[b] = s_d2h.record_event()
         return n
 

@@ -197,6 +197,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                 raise
 
         ctx.raster_settings = rs
+        ctx.ns = ns
         ctx.num_rendered = num_rendered
         ctx.sh_M = sh_M
         ctx.capacity = cap
@@ -216,7 +217,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         base = state.data_ptr()
         bin_p = binning.data_ptr() if binning is not None else base + n_geom + n_img + n_acc
         with torch.cuda.device(device):
-            ns = _NativeSettings(rs, device)
+            ns = ctx.ns
             g_out = _dev_f32(grad_out_color, device, "grad_out_color")
             # frame-sharded training: write (means3D, colours, opacity, scales, rotation) gradients straight into
             # the caller's [P,14] all-reduce buffer (gsvc_b200.sharding.packed_backward) and return views of it
