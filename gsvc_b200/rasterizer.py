@@ -46,6 +46,24 @@ _capacity_hint: dict = {}
 _count_slots = threading.local()
 
 
+_captured_caps: dict = {}
+
+
+def last_num_rendered() -> int:
+    """num_rendered most recently published by the device to this thread's pinned counter (after a
+    synchronize it is the value of the last forward, eager or replayed from a CUDA graph)."""
+    st = _count_slots
+    return int(st.slot[0].item()) & ((1 << 40) - 1) if hasattr(st, "slot") else 0
+
+
+def captured_capacity_ok(device, P: int, H: int, W: int) -> bool:
+    """After replaying a CUDA graph that contains the rasterizer (and synchronizing): did the binning capacity
+    fixed at capture time hold the instances of the last replay?  If not, the replay's image is invalid and
+    the step must be re-captured (or run eagerly)."""
+    cap = _captured_caps.get((torch.device(device).index, P, H, W))
+    return cap is None or last_num_rendered() <= cap
+
+
 class _PackedTarget:
     buf = None  # process-wide on purpose: autograd runs backward on its own thread
 
@@ -153,6 +171,16 @@ class _RasterizeGaussians(torch.autograd.Function):
             hint_key = (device.index, P, H, W)
             hint = _capacity_hint.get(hint_key)
             cap = 0 if hint is None else int(hint * 1.25) + 4096
+            # CUDA-graph capture (torch.cuda.graph around the caller's step): nothing may wait on the device, so
+            # the instance count of the last eager call stands in for num_rendered and the binning capacity is
+            # fixed generously; captured_capacity_ok() tells the caller after a replay whether it sufficed.
+            capturing = torch.cuda.is_current_stream_capturing()
+            if capturing:
+                if hint is None:
+                    raise RasterizerError("run the rasterizer once eagerly with these shapes before capturing it "
+                                          "in a CUDA graph (the binning capacity comes from that call)")
+                cap = int(hint * 1.5) + 65536
+                _captured_caps[hint_key] = cap
             # one allocation for all native state: [geom | image | backward accumulators | binning]
             need_grad = any(ctx.needs_input_grad)
             n_geom = _align(L.gsvc_rast_geom_bytes(P, sh_M))
@@ -177,7 +205,10 @@ class _RasterizeGaussians(torch.autograd.Function):
                 # The reference API returns num_rendered as a Python int (renderer.py:90).  The scan kernel
                 # publishes it into pinned memory as soon as it is known, so this wait ends while the
                 # scatter / sort / blend kernels are still running: no stream synchronisation.
-                num_rendered = _lib.check(L.gsvc_rast_wait_count(slot, ticket, stream), "gsvc_rast_wait_count")
+                if capturing:
+                    num_rendered = hint
+                else:
+                    num_rendered = _lib.check(L.gsvc_rast_wait_count(slot, ticket, stream), "gsvc_rast_wait_count")
                 if num_rendered > 0xFFFFFFFF:
                     raise RasterizerError(f"num_rendered {num_rendered} exceeds 32-bit tile ranges")
                 if num_rendered > cap or cap == 0:
@@ -188,7 +219,8 @@ class _RasterizeGaussians(torch.autograd.Function):
                     bin_p = binning.data_ptr()
                     _lib.check(L.gsvc_rast_forward_render(ns.ref, P, geom_p, image_p, bin_p, cap, color.data_ptr(),
                                                           stream), "gsvc_rast_forward_render")
-                _capacity_hint[hint_key] = num_rendered
+                if not capturing:
+                    _capacity_hint[hint_key] = num_rendered
             except Exception:
                 if rs.debug:
                     torch.save((means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
