@@ -311,82 +311,62 @@ def run_product_arm(args, rank, local_rank, world):
     fwd_stage_avg = _lib.stage_times()
     _lib.stage_timing(False)
 
-    # ---- end to end through the public API with HOST buffers: every step copies its inputs (all Gaussian
-    # parameters) from pinned host memory and reads its result (the packed [P,14] parameter gradients a host
-    # optimizer consumes) back to pinned host memory, inside the timed region.  Copies run on their own streams
-    # and are double-buffered, as a host integration would do.  (The rendered image stays on the device, where
-    # the reference computes its loss: pipeline/train.py:407-444.)
-    # one pinned host buffer / one device buffer per slot: [means3D | colours | opacity | scales | rotation] segments
-    seg = [(k, w) for k, w in GRAD_LAYOUT]
+    # ---- end to end through the public API with HOST buffers (gsvc_b200.hostpipe.HostStepPipeline): every step
+    # copies its inputs (all Gaussian parameters, one [14*P] pinned buffer) from host memory and reads its result
+    # (the packed [P,14] parameter gradients a host optimizer consumes) back to pinned host memory, inside the
+    # timed region.  Copies run on their own streams, ring-buffered over 2 slots, and the copy of step i+1 is
+    # enqueued before step i's forward blocks the host on num_rendered.  (The rendered image stays on the device,
+    # where the reference computes its loss: pipeline/train.py:407-444.)
+    from gsvc_b200.hostpipe import HostStepPipeline
+    pipe = HostStepPipeline(P, device, slots=2, use_graphs=os.environ.get("GSVC_E2E_GRAPHS", "1") != "0")
     host_flat = torch.empty(14 * P, dtype=torch.float32).pin_memory()
     off = 0
-    for k, w in seg:
+    for k, w in GRAD_LAYOUT:
         host_flat[off:off + w * P].copy_(g[k].detach().reshape(-1).cpu())
         off += w * P
-    dev_flat = [torch.empty(14 * P, dtype=torch.float32, device=device) for _ in range(2)]
+    h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
+    reduce = (lambda buf: dist.all_reduce(buf, op=dist.ReduceOp.SUM)) if world > 1 else None
 
-    def views(flat):
-        out, o = {}, 0
-        for k, w in seg:
-            out[k] = flat[o:o + w * P].view(P, w)
-            o += w * P
-        return out
+    def e2e_steps(n):
+        pipe.prefetch(host_flat)
+        for i in range(n):
+            if i + 1 < n:
+                pipe.prefetch(host_flat)        # step i+1's copy is in flight while step i computes
+            pipe.step(rast, dL, reduce)
 
-    dev_in = [views(f) for f in dev_flat]
-    host_grads = [torch.empty((P, 14), dtype=torch.float32).pin_memory() for _ in range(2)]
-    dev_grads = [torch.empty((P, 14), dtype=torch.float32, device=device) for _ in range(2)]
-    h2d = host_flat.numel() * 4
-    d2h = host_grads[0].numel() * 4
-    s_h2d, s_d2h = torch.cuda.Stream(device), torch.cuda.Stream(device)
-    main = torch.cuda.current_stream(device)
-    compute_done = [None, None]
-    d2h_done = [None, None]
-
-    def e2e_step(i):
-        b = i & 1
-        with torch.cuda.stream(s_h2d):
-            if compute_done[b] is not None:
-                s_h2d.wait_event(compute_done[b])        # the device input slot is free again
-            dev_flat[b].copy_(host_flat, non_blocking=True)
-            in_ready = s_h2d.record_event()
-        main.wait_event(in_ready)
-        if d2h_done[b] is not None:
-            main.wait_event(d2h_done[b])                 # the device gradient buffer has been read out
-        p = {k: v.requires_grad_(True) for k, v in dev_in[b].items()}
-        if world == 1:
-            color, radii, n, grads, _ = train_step(p, packed=dev_grads[b])   # backward writes the [P,14] buffer
-            src = dev_grads[b]
-        else:
-            color, radii, n, grads, gb = train_step(p)
-            pending[gb].wait()
-            src = grad_bufs[gb]
-        for v in dev_in[b].values():
-            v.requires_grad_(False)
-        compute_done[b] = main.record_event()
-        with torch.cuda.stream(s_d2h):
-            s_d2h.wait_event(compute_done[b])
-            host_grads[b].copy_(src, non_blocking=True)
-            d2h_done[b] = s_d2h.record_event()
-        return n
-
-    for i in range(4):
-        e2e_step(i)
+    e2e_steps(6)      # per slot: one eager step (sizes the binning buffer), then the CUDA-graph capture
 
     def e2e_run():
         sync_all()
         e_start = torch.cuda.Event(enable_timing=True)
         e_end = torch.cuda.Event(enable_timing=True)
-        e_start.record(s_h2d)
-        for i in range(args.steps):
-            e2e_step(i)
-        e_end.record(s_d2h)
+        e_start.record(pipe.s_h2d)
+        e2e_steps(args.steps)
+        e_end.record(pipe.s_d2h)
         sync_all()
         t = torch.tensor([e_start.elapsed_time(e_end)], dtype=torch.float64, device=device)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def copy_gbs(dst, src, stream):
+        """PCIe rate of one direction alone, same buffers as the e2e steps (explains the e2e number)."""
+        with torch.cuda.stream(stream):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            dst.copy_(src, non_blocking=True)
+            a.record()
+            for _ in range(10):
+                dst.copy_(src, non_blocking=True)
+            b.record()
+        b.synchronize()
+        return 10 * src.numel() * 4 / (a.elapsed_time(b) * 1e-3) / 1e9
+
     e2e_ms = min(e2e_run() for _ in range(REPEATS))
+    torch.cuda.synchronize(device)
+    if not pipe.capacity_ok(rast):
+        raise SystemExit("e2e: the captured instance capacity was exceeded (cannot happen with a fixed scene)")
+    pcie = {"h2d_GBs": round(copy_gbs(pipe.dev_flat[0], host_flat, pipe.s_h2d), 2),
+            "d2h_GBs": round(copy_gbs(pipe.host_grads[0].view(-1), pipe.dev_grads[0].view(-1), pipe.s_d2h), 2)}
     # ---- the second native entry point, visible_filter over 1M anchors (prefilter_voxel, preprocess.py:99-104):
     # a pure stream kernel — the one stage whose HBM roofline fraction is meaningful as such
     vf = None
@@ -446,7 +426,9 @@ def run_product_arm(args, rank, local_rank, world):
                                  "instance; ncu: ~84 % issue-active, < 5 % DRAM); the HBM fraction of a stream kernel of "
                                  "this path is reported under visible_filter; see DESIGN.md §4"},
             "e2e": {"value": world * 1000.0 * args.steps / e2e_ms, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps, "pcie_alone": pcie,
+                    "api": "gsvc_b200.hostpipe.HostStepPipeline (pinned host params in, pinned host [P,14] grads out; "
+                           + ("forward+backward replayed from a CUDA graph per slot)" if pipe.use_graphs else "eager launches)")},
             "visible_filter": dict(vf, frac=vf["achieved_GBs"] / peak),
             "gpu_launches": launches,
             "clocks": clk,

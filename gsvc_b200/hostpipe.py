@@ -1,0 +1,145 @@
+"""Host-buffer front end of the rasterizer step: pinned host parameters in, pinned host gradients out.
+
+The reference keeps everything on the device (ortho_gaussian_renderer/renderer.py:37 hard-codes
+"cuda"), but a host integration (a CPU-side optimizer, a decoder that produces each frame's
+Gaussians on the host — pipeline/stream_encode.py:42-110) feeds `render()` from host memory.  This
+class is that call path and the one `bench.py` times as `e2e`:
+
+    pipe = HostStepPipeline(P, device)
+    pipe.prefetch(host_params)            # [14*P] fp32 pinned: means3D | colours | opacity | scales | rotation
+    slot = pipe.step(rasterizer, dL)      # forward + backward of the oldest prefetched parameter set
+    grads = pipe.grads(slot)              # [P,14] fp32 pinned (GRAD_LAYOUT), valid after this call returns
+
+Copies run on their own streams and every buffer is ring-buffered over `slots` entries, so with one
+`prefetch` issued ahead of each `step` the three engines (H2D copy, SMs, D2H copy) work on three
+different steps at once and the step time is max(copy in, compute, copy out) instead of their sum.
+The forward's only host wait (num_rendered, published by the tile scan) happens after the next
+step's copy is already in flight.
+"""
+from __future__ import annotations
+
+from collections import deque
+from typing import Callable, Dict, Optional
+
+import torch
+
+from .rasterizer import GaussianRasterizer, RasterizerError
+from .sharding import GRAD_LAYOUT, GRAD_WIDTH, packed_backward
+
+
+class HostStepPipeline:
+    def __init__(self, P: int, device, slots: int = 2, use_graphs: bool = True):
+        """`use_graphs`: after one eager step per slot (which sizes the binning buffer), the slot's forward +
+        backward (8 kernels) is captured in a CUDA graph and replayed, so a step costs the host one graph launch
+        instead of ~10 launches and the autograd bookkeeping; `capacity_ok()` reports whether the instance capacity
+        fixed at capture time held (if not the slot is re-captured from an eager step)."""
+        if slots < 2:
+            raise ValueError("need at least 2 slots to overlap copies with compute")
+        self.P, self.slots = int(P), int(slots)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RasterizerError("HostStepPipeline needs a CUDA device: gsvc_b200 has no CPU fallback")
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self.dev_flat = [torch.empty(GRAD_WIDTH * P, **f32) for _ in range(slots)]
+        self.dev_grads = [torch.empty((P, GRAD_WIDTH), **f32) for _ in range(slots)]
+        self.host_grads = [torch.empty((P, GRAD_WIDTH), dtype=torch.float32).pin_memory() for _ in range(slots)]
+        self.s_h2d, self.s_d2h = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
+        self.in_ready = [None] * slots       # H2D of the slot finished
+        self.compute_done = [None] * slots   # forward+backward that read the slot's parameters finished
+        self.d2h_done = [None] * slots       # the slot's gradients are in host memory
+        self.n_prefetched = 0
+        self.n_stepped = 0
+        self.ready = deque()
+        self.use_graphs = bool(use_graphs)
+        self.graphs = [None] * slots         # per slot: (key, CUDAGraph) once captured
+        self.eager_seen = [None] * slots     # per slot: key of the last eager step (capture needs one first)
+        self.h2d_bytes = GRAD_WIDTH * P * 4
+        self.d2h_bytes = GRAD_WIDTH * P * 4
+
+    def views(self, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
+        out, o, P = {}, 0, self.P
+        for k, w in GRAD_LAYOUT:
+            out[k] = flat[o:o + w * P].view(P, w)
+            o += w * P
+        return out
+
+    def prefetch(self, host_flat: torch.Tensor) -> None:
+        """Enqueue the host→device copy of one step's parameters ([14*P] fp32, pinned)."""
+        if len(self.ready) >= self.slots:
+            raise RasterizerError("all slots hold un-stepped parameters: call step() before prefetching more")
+        if not host_flat.is_pinned():
+            raise RasterizerError("host parameters must be in pinned memory (the copy has to be asynchronous)")
+        b = self.n_prefetched % self.slots
+        self.n_prefetched += 1
+        with torch.cuda.stream(self.s_h2d):
+            if self.compute_done[b] is not None:
+                self.s_h2d.wait_event(self.compute_done[b])   # the step that read this slot has finished
+            self.dev_flat[b].copy_(host_flat.view(-1), non_blocking=True)
+            self.in_ready[b] = self.s_h2d.record_event()
+        self.ready.append(b)
+
+    def step(self, rast: GaussianRasterizer, dL: torch.Tensor,
+             reduce: Optional[Callable[[torch.Tensor], None]] = None) -> int:
+        """Forward + backward of the oldest prefetched parameter set on the current stream, then the
+        device→host copy of its packed gradients.  `reduce(buf)` (frame-sharded training) is called on the
+        [P,14] buffer after the backward and must leave the current stream ordered after its collective."""
+        if not self.ready:
+            raise RasterizerError("step() without a prefetched parameter set")
+        b = self.ready.popleft()
+        main = torch.cuda.current_stream(self.device)
+        main.wait_event(self.in_ready[b])
+        if self.d2h_done[b] is not None:
+            main.wait_event(self.d2h_done[b])                 # the slot's gradient buffer has been read out
+        key = (id(rast), dL.data_ptr(), tuple(dL.shape))
+        g = self.graphs[b]
+        if g is not None and g[0] != key:
+            g = self.graphs[b] = None
+        if g is None and self.use_graphs and self.eager_seen[b] == key:
+            # second step on this slot with the same rasterizer and seed gradient: capture it
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._compute(b, rast, dL)
+            g = self.graphs[b] = (key, graph, rast.raster_settings)
+        if g is not None:
+            g[1].replay()
+        else:
+            self.last_num_rendered = self._compute(b, rast, dL)
+            self.eager_seen[b] = key
+        if reduce is not None:
+            reduce(self.dev_grads[b])
+        self.compute_done[b] = main.record_event()
+        with torch.cuda.stream(self.s_d2h):
+            self.s_d2h.wait_event(self.compute_done[b])
+            self.host_grads[b].copy_(self.dev_grads[b], non_blocking=True)
+            self.d2h_done[b] = self.s_d2h.record_event()
+        self.n_stepped += 1
+        return b
+
+    def _compute(self, b: int, rast: GaussianRasterizer, dL: torch.Tensor) -> int:
+        p = {k: v.requires_grad_(True) for k, v in self.views(self.dev_flat[b]).items()}
+        means2D = torch.zeros_like(p["means3D"], requires_grad=True)
+        color, radii, n = rast(means3D=p["means3D"], means2D=means2D, shs=None, colors_precomp=p["colors_precomp"],
+                               opacities=p["opacities"], scales=p["scales"], rotations=p["rotations"],
+                               cov3D_precomp=None)
+        with packed_backward(self.dev_grads[b]):
+            torch.autograd.grad(color, [p[k] for k, _ in GRAD_LAYOUT], grad_outputs=dL)
+        return n
+
+    def capacity_ok(self, rast: GaussianRasterizer) -> bool:
+        """After a synchronisation: did the instance capacity of the captured graphs hold the last replayed step?
+        (False: call `recapture()`; the gradients of that step are invalid.)"""
+        from . import rasterizer as R
+        rs = rast.raster_settings
+        return R.captured_capacity_ok(self.device, self.P, int(rs.image_height), int(rs.image_width))
+
+    def recapture(self) -> None:
+        self.graphs = [None] * self.slots
+        self.eager_seen = [None] * self.slots
+
+    def grads(self, slot: int) -> torch.Tensor:
+        """The [P,14] gradients of the step that returned `slot` (pinned host memory); blocks until they landed."""
+        ev = self.d2h_done[slot]
+        if ev is None:
+            raise RasterizerError(f"slot {slot} has no finished step")
+        ev.synchronize()
+        return self.host_grads[slot]
