@@ -128,11 +128,15 @@ render_forward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, un
     float TA = 1.f, A0 = 0.f, A1 = 0.f, A2 = 0.f;   // pixel A = (px, py)
     float TB = 1.f, B0 = 0.f, B1 = 0.f, B2 = 0.f;   // pixel B = (px, py + 4)
     unsigned int lastA = 0, lastB = 0;
-    bool doneA = !inA, doneB = !inB;
+    // A pixel that is finished (outside the image, or stopped by the T < 1e-4 rule) is represented by an
+    // unreachable alpha floor, so "still live" costs no instruction in the pair loop: the reference's
+    // alpha >= 1/255 test is made against this per-pixel register.
+    constexpr float DONE = 2.f;   // alpha <= 0.99 < DONE
+    float minA = inA ? ALPHA_MIN : DONE, minB = inB ? ALPHA_MIN : DONE;
 
     for (int base = 0; base < n; base += BATCH) {
         // block-wide vote doubles as the barrier that protects the staging buffer
-        if (__syncthreads_count(doneA && doneB) == BLEND_THREADS) break;
+        if (__syncthreads_count(minA > 1.f && minB > 1.f) == BLEND_THREADS) break;
 #pragma unroll
         for (int r = 0; r < BATCH / BLEND_THREADS; r++) {
             const int slot = tid + r * BLEND_THREADS;
@@ -142,7 +146,7 @@ render_forward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, un
         const int cnt = min(BATCH, n - base);
         for (int c = 0; c < cnt; c += 32) {
             // warp-ballot early termination: all 64 pixels of the block saturated
-            if (__ballot_sync(FULL, !(doneA && doneB)) == 0u) break;
+            if (__ballot_sync(FULL, !(minA > 1.f && minB > 1.f)) == 0u) break;
             bool hit = false;
             if (c + lane < cnt) hit = block_hit(bg, s_feat + 3 * (c + lane));
             unsigned int m = __ballot_sync(FULL, hit);
@@ -154,34 +158,32 @@ render_forward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, un
                 const float4* e = chunk + 3 * k;
                 const float4 f0 = e[0];
                 const float4 f1 = e[1];
+                const float4 f2 = e[2];
                 const float dx = f0.x - pxf, dyA = f0.y - pyf, dyB = dyA - 4.f;
                 const float t = f1.x * dx;                                          // A' dx
                 const float qA = fmaf(fmaf(f1.y, dyA, t), dx, (f1.z * dyA) * dyA);  // log2 of the falloff
                 const float qB = fmaf(fmaf(f1.y, dyB, t), dx, (f1.z * dyB) * dyB);
                 const float aA = fminf(ALPHA_MAX, f1.w * ex2_approx(qA));
                 const float aB = fminf(ALPHA_MAX, f1.w * ex2_approx(qB));
-                // the reference `continue`s on power > 0 and on alpha < 1/255
-                const bool okA = !doneA && !(qA > 0.f) && !(aA < ALPHA_MIN);
-                const bool okB = !doneB && !(qB > 0.f) && !(aB < ALPHA_MIN);
-                if (okA || okB) {
-                    const float4 f2 = e[2];
-                    const unsigned int pos = pos1 + (unsigned int)k;
-                    const float tTA = TA * (1.f - aA), tTB = TB * (1.f - aB);
-                    const bool stopA = okA && (tTA < T_STOP), stopB = okB && (tTB < T_STOP);
-                    doneA |= stopA;
-                    doneB |= stopB;
-                    if (okA && !stopA) {
-                        const float w = aA * TA;
-                        A0 = fmaf(f2.x, w, A0); A1 = fmaf(f2.y, w, A1); A2 = fmaf(f2.z, w, A2);
-                        TA = tTA;
-                        lastA = pos;
-                    }
-                    if (okB && !stopB) {
-                        const float w = aB * TB;
-                        B0 = fmaf(f2.x, w, B0); B1 = fmaf(f2.y, w, B1); B2 = fmaf(f2.z, w, B2);
-                        TB = tTB;
-                        lastB = pos;
-                    }
+                // the reference `continue`s on power > 0 and on alpha < 1/255 (and never gets here once done)
+                const bool okA = !(qA > 0.f) && !(aA < minA);
+                const bool okB = !(qB > 0.f) && !(aB < minB);
+                const unsigned int pos = pos1 + (unsigned int)k;
+                const float tTA = TA * (1.f - aA), tTB = TB * (1.f - aB);
+                // T' < 1e-4: the pixel stops and this Gaussian is NOT added
+                if (okA && tTA < T_STOP) minA = DONE;
+                if (okB && tTB < T_STOP) minB = DONE;
+                if (okA && !(tTA < T_STOP)) {
+                    const float w = aA * TA;
+                    A0 = fmaf(f2.x, w, A0); A1 = fmaf(f2.y, w, A1); A2 = fmaf(f2.z, w, A2);
+                    TA = tTA;
+                    lastA = pos;
+                }
+                if (okB && !(tTB < T_STOP)) {
+                    const float w = aB * TB;
+                    B0 = fmaf(f2.x, w, B0); B1 = fmaf(f2.y, w, B1); B2 = fmaf(f2.z, w, B2);
+                    TB = tTB;
+                    lastB = pos;
                 }
             }
         }
