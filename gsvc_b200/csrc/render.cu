@@ -44,6 +44,70 @@ __device__ __forceinline__ float rcp_approx(float x)
     return y;
 }
 
+// ---- packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2) ---------------------------------------------
+// Each lane blends two pixels (A = low half, B = high half) with identical instruction streams, and both
+// blend kernels are bound by instruction issue, not by the FP32 pipes (ncu: ~85 % issue-active, fma pipe
+// ~35 %).  One f32x2 instruction does the work of two scalar ones in a single issue slot (measured on
+// B200: scripts/ubench/ffma2.cu); ptxas folds broadcast scalars, immediates and negations into its operands.
+struct f2 { unsigned long long v; };
+__device__ __forceinline__ f2 mk2(float lo, float hi)
+{
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f2 bc2(float s) { return mk2(s, s); }
+__device__ __forceinline__ float lo(f2 a)
+{
+    float x, y;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v));
+    return x;
+}
+__device__ __forceinline__ float hi(f2 a)
+{
+    float x, y;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v));
+    return y;
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c)
+{
+    f2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+    return r;
+}
+// c += a * b in place (ties the accumulator to one register pair across loop iterations)
+__device__ __forceinline__ void fma2_acc(f2& c, f2 a, f2 b)
+{
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c.v) : "l"(a.v), "l"(b.v));
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b)
+{
+    f2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b)
+{
+    f2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ f2 sub2(f2 a, f2 b)
+{
+    f2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ f2 neg2(f2 a) { return mk2(-lo(a), -hi(a)); }
+
+// log2 of the falloff of one staged Gaussian at this lane's two pixels:
+//   q = A' dx^2 + B' dx dy + C' dy^2 = (A' dx) dx + dy (B' dx + C' dy)      (dx is shared: same column)
+__device__ __forceinline__ f2 falloff_log2(const float4 f1, float dx, f2 dy2)
+{
+    const float t = f1.x * dx;
+    return fma2(dy2, fma2(bc2(f1.z), dy2, bc2(f1.y * dx)), bc2(t * dx));
+}
+
 struct BlockGeom {
     int px, py;                    // this lane's first pixel; the second one is (px, py + 4)
     float xmin, xmax, ymin, ymax;  // pixel-centre bounds of the warp's 8x8 block
@@ -125,8 +189,10 @@ render_forward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, un
     if ((unsigned long long)rg.y > cap) return;  // capacity overflow: host re-runs with a larger buffer
     const int n = (int)(rg.y - rg.x);
 
-    float TA = 1.f, A0 = 0.f, A1 = 0.f, A2 = 0.f;   // pixel A = (px, py)
-    float TB = 1.f, B0 = 0.f, B1 = 0.f, B2 = 0.f;   // pixel B = (px, py + 4)
+    // pixel A = (px, py) in the low halves, pixel B = (px, py + 4) in the high halves
+    float TA = 1.f, A0 = 0.f, A1 = 0.f, A2 = 0.f;
+    float TB = 1.f, B0 = 0.f, B1 = 0.f, B2 = 0.f;
+    const f2 npy2 = mk2(-pyf, -(pyf + 4.f));
     unsigned int lastA = 0, lastB = 0;
     // A pixel that is finished (outside the image, or stopped by the T < 1e-4 rule) is represented by an
     // unreachable alpha floor, so "still live" costs no instruction in the pair loop: the reference's
@@ -158,33 +224,29 @@ render_forward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, un
                 const float4* e = chunk + 3 * k;
                 const float4 f0 = e[0];
                 const float4 f1 = e[1];
-                const float4 f2 = e[2];
-                const float dx = f0.x - pxf, dyA = f0.y - pyf, dyB = dyA - 4.f;
-                const float t = f1.x * dx;                                          // A' dx
-                const float qA = fmaf(fmaf(f1.y, dyA, t), dx, (f1.z * dyA) * dyA);  // log2 of the falloff
-                const float qB = fmaf(fmaf(f1.y, dyB, t), dx, (f1.z * dyB) * dyB);
-                const float aA = fminf(ALPHA_MAX, f1.w * ex2_approx(qA));
-                const float aB = fminf(ALPHA_MAX, f1.w * ex2_approx(qB));
+                const float4 f2v = e[2];
+                const f2 q2 = falloff_log2(f1, f0.x - pxf, add2(bc2(f0.y), npy2));
+                const float qA = lo(q2), qB = hi(q2);
+                const f2 a2 = mul2(bc2(f1.w), mk2(ex2_approx(qA), ex2_approx(qB)));
+                const float aA = fminf(ALPHA_MAX, lo(a2)), aB = fminf(ALPHA_MAX, hi(a2));
                 // the reference `continue`s on power > 0 and on alpha < 1/255 (and never gets here once done)
                 const bool okA = !(qA > 0.f) && !(aA < minA);
                 const bool okB = !(qB > 0.f) && !(aB < minB);
                 const unsigned int pos = pos1 + (unsigned int)k;
-                const float tTA = TA * (1.f - aA), tTB = TB * (1.f - aB);
+                const f2 ac = mk2(aA, aB), T2 = mk2(TA, TB);
+                const f2 tT2 = mul2(T2, sub2(bc2(1.f), ac));
+                const f2 w2 = mul2(ac, T2);
+                const float tTA = lo(tT2), tTB = hi(tT2);
                 // T' < 1e-4: the pixel stops and this Gaussian is NOT added
                 if (okA && tTA < T_STOP) minA = DONE;
                 if (okB && tTB < T_STOP) minB = DONE;
-                if (okA && !(tTA < T_STOP)) {
-                    const float w = aA * TA;
-                    A0 = fmaf(f2.x, w, A0); A1 = fmaf(f2.y, w, A1); A2 = fmaf(f2.z, w, A2);
-                    TA = tTA;
-                    lastA = pos;
-                }
-                if (okB && !(tTB < T_STOP)) {
-                    const float w = aB * TB;
-                    B0 = fmaf(f2.x, w, B0); B1 = fmaf(f2.y, w, B1); B2 = fmaf(f2.z, w, B2);
-                    TB = tTB;
-                    lastB = pos;
-                }
+                const bool addA = okA && !(tTA < T_STOP), addB = okB && !(tTB < T_STOP);
+                const f2 wz = mk2(addA ? lo(w2) : 0.f, addB ? hi(w2) : 0.f);   // adding 0 leaves the colour bit-identical
+                { const f2 c = fma2(bc2(f2v.x), wz, mk2(A0, B0)); A0 = lo(c); B0 = hi(c); }
+                { const f2 c = fma2(bc2(f2v.y), wz, mk2(A1, B1)); A1 = lo(c); B1 = hi(c); }
+                { const f2 c = fma2(bc2(f2v.z), wz, mk2(A2, B2)); A2 = lo(c); B2 = hi(c); }
+                if (addA) { TA = tTA; lastA = pos; }
+                if (addB) { TB = tTB; lastB = pos; }
             }
         }
     }
@@ -258,39 +320,18 @@ __device__ __forceinline__ float warp_sum(float v)
     return v;
 }
 
-// Per-pixel replay state of the backward.
-struct PixBwd {
-    float T;                   // running transmittance (T_i before the current Gaussian)
-    float Sg;                  // g . (colour composited behind the current Gaussian, incl. T_final * bg):
-                               //   Sg_i = sum_{j>i} (c_j . g) alpha_j T_j + T_final (bg . g)
-    float g0, g1, g2;          // dL/dC of the pixel
-    unsigned int last;         // n_contrib
+// Per-lane replay state of the backward: both pixels of the lane (A = low half, B = high half).
+//   T   running transmittance (T_i before the current Gaussian)
+//   Sg  g . (colour composited behind the current Gaussian, incl. T_final * bg):
+//         Sg_i = sum_{j>i} (c_j . g) alpha_j T_j + T_final (bg . g)
+//   g*  dL/dC of the pixel
+// With dC/dalpha_i = c_i T_i - (sum_{j>i} c_j alpha_j T_j + T_final bg) / (1 - alpha_i) contracted with
+// g = dL/dC up front, the behind-colour recursion is ONE scalar per pixel (Sg) instead of three channels.
+struct PairBwd {
+    float TA, TB, SgA, SgB;
+    f2 g0, g1, g2;
+    unsigned int lastA, lastB;   // n_contrib
 };
-
-// One (pixel, Gaussian) pair, branch-free: a pair that does not contribute is blended with alpha = 0,
-// which leaves T, the behind-colour sum and every gradient sum unchanged (bit-identically).
-//   dC/dalpha_i = c_i T_i - (sum_{j>i} c_j alpha_j T_j + T_final bg) / (1 - alpha_i)
-// contracted with g = dL/dC up front, so the behind-colour recursion is ONE scalar per pixel (Sg) instead of
-// three colour channels.  Returns w = opacity * Gs * dL/dalpha (the weight of the conic / position moments);
-// adds the colour and opacity terms to (s_op, s_r, s_g, s_b).
-__device__ __forceinline__ float pair_backward(PixBwd& p, bool use, float alpha, float Gs, float opacity,
-                                               const float4 f2, float& s_op, float& s_r, float& s_g, float& s_b)
-{
-    const float ae = use ? alpha : 0.f;
-    const float ra = rcp_approx(1.f - ae);
-    p.T *= ra;
-    const float cg = fmaf(f2.x, p.g0, fmaf(f2.y, p.g1, f2.z * p.g2));
-    float dla = fmaf(p.T, cg, -(ra * p.Sg));
-    dla = use ? dla : 0.f;                 // U4: straight-through the 0.99 cap otherwise
-    const float dchan = ae * p.T;
-    s_r = fmaf(dchan, p.g0, s_r);
-    s_g = fmaf(dchan, p.g1, s_g);
-    s_b = fmaf(dchan, p.g2, s_b);
-    p.Sg = fmaf(dchan, cg, p.Sg);
-    const float gd = Gs * dla;
-    s_op += gd;
-    return opacity * gd;
-}
 
 __global__ void __launch_bounds__(BLEND_THREADS)
 render_backward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, const float* __restrict__ dL_dout,
@@ -314,20 +355,25 @@ render_backward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, c
     if (n <= 0) return;
 
     const float bg0 = __ldg(s.bg), bg1 = __ldg(s.bg + 1), bg2 = __ldg(s.bg + 2);
-    PixBwd A{}, B{};
-    if (inA) {
-        A.T = im.final_T[pixA]; A.last = im.n_contrib[pixA];
-        A.g0 = dL_dout[pixA]; A.g1 = dL_dout[N + pixA]; A.g2 = dL_dout[2 * N + pixA];
-        A.Sg = A.T * (bg0 * A.g0 + bg1 * A.g1 + bg2 * A.g2);
+    PairBwd S{};
+    {
+        float gA0 = 0.f, gA1 = 0.f, gA2 = 0.f, gB0 = 0.f, gB1 = 0.f, gB2 = 0.f;
+        if (inA) {
+            S.TA = im.final_T[pixA]; S.lastA = im.n_contrib[pixA];
+            gA0 = dL_dout[pixA]; gA1 = dL_dout[N + pixA]; gA2 = dL_dout[2 * N + pixA];
+            S.SgA = S.TA * (bg0 * gA0 + bg1 * gA1 + bg2 * gA2);
+        }
+        if (inB) {
+            S.TB = im.final_T[pixB]; S.lastB = im.n_contrib[pixB];
+            gB0 = dL_dout[pixB]; gB1 = dL_dout[N + pixB]; gB2 = dL_dout[2 * N + pixB];
+            S.SgB = S.TB * (bg0 * gB0 + bg1 * gB1 + bg2 * gB2);
+        }
+        S.g0 = mk2(gA0, gB0); S.g1 = mk2(gA1, gB1); S.g2 = mk2(gA2, gB2);
     }
-    if (inB) {
-        B.T = im.final_T[pixB]; B.last = im.n_contrib[pixB];
-        B.g0 = dL_dout[pixB]; B.g1 = dL_dout[N + pixB]; B.g2 = dL_dout[2 * N + pixB];
-        B.Sg = B.T * (bg0 * B.g0 + bg1 * B.g1 + bg2 * B.g2);
-    }
+    const f2 npy2 = mk2(-pyf, -(pyf + 4.f));
 
     // nothing behind the deepest contributor of the tile matters: start the replay there
-    const unsigned int wmax = __reduce_max_sync(FULL, max(A.last, B.last));
+    const unsigned int wmax = __reduce_max_sync(FULL, max(S.lastA, S.lastB));
     if (lane == 0) s_max[tid >> 5] = wmax;
     __syncthreads();
     unsigned int bmax = 0;
@@ -367,33 +413,51 @@ render_backward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, c
                 const float4* e = chunk + 3 * k;
                 const float4 f0 = e[0];
                 const float4 f1 = e[1];
-                const float dx = f0.x - pxf, dyA = f0.y - pyf, dyB = dyA - 4.f;
-                const float t = f1.x * dx;
-                const float qA = fmaf(fmaf(f1.y, dyA, t), dx, (f1.z * dyA) * dyA);
-                const float qB = fmaf(fmaf(f1.y, dyB, t), dx, (f1.z * dyB) * dyB);
-                const float GsA = ex2_approx(qA), GsB = ex2_approx(qB);
-                const float aA = fminf(ALPHA_MAX, f1.w * GsA), aB = fminf(ALPHA_MAX, f1.w * GsB);
+                const float4 f2v = e[2];
+                const float dx = f0.x - pxf;
+                const f2 dy2 = add2(bc2(f0.y), npy2);
+                const f2 q2 = falloff_log2(f1, dx, dy2);
+                const float qA = lo(q2), qB = hi(q2);
+                const f2 Gs2 = mk2(ex2_approx(qA), ex2_approx(qB));
+                const f2 a2 = mul2(bc2(f1.w), Gs2);
+                const float aA = fminf(ALPHA_MAX, lo(a2)), aB = fminf(ALPHA_MAX, hi(a2));
                 const unsigned int pos = (unsigned int)(pos0 - k);
-                const bool useA = (pos < A.last) && !(qA > 0.f) && !(aA < ALPHA_MIN);
-                const bool useB = (pos < B.last) && !(qB > 0.f) && !(aB < ALPHA_MIN);
+                const bool useA = (pos < S.lastA) && !(qA > 0.f) && !(aA < ALPHA_MIN);
+                const bool useB = (pos < S.lastB) && !(qB > 0.f) && !(aB < ALPHA_MIN);
                 // (no warp vote here: after the exact culling above 99.9 % of the evaluations that reach this point
                 //  contribute to at least one pixel — ncu source counters — and a pair that does not adds zeros)
 
+                // Branch-free: a pair that does not contribute is blended with alpha = 0, which leaves T, the
+                // behind-colour sum and every gradient sum unchanged (bit-identically).
+                const f2 ae2 = mk2(useA ? aA : 0.f, useB ? aB : 0.f);
+                const f2 om2 = sub2(bc2(1.f), ae2);
+                const f2 ra2 = mk2(rcp_approx(lo(om2)), rcp_approx(hi(om2)));
+                const f2 T2 = mul2(mk2(S.TA, S.TB), ra2);                 // T_i = T_{i+1} / (1 - alpha_i)
+                S.TA = lo(T2); S.TB = hi(T2);
+                const f2 cg2 = fma2(bc2(f2v.x), S.g0, fma2(bc2(f2v.y), S.g1, mul2(bc2(f2v.z), S.g2)));
+                const f2 Sg2 = mk2(S.SgA, S.SgB);
+                const f2 dlar = fma2(T2, cg2, neg2(mul2(ra2, Sg2)));       // dL/dalpha
+                const f2 dla2 = mk2(useA ? lo(dlar) : 0.f, useB ? hi(dlar) : 0.f);  // U4: straight through the 0.99 cap
+                const f2 dchan2 = mul2(ae2, T2);
+                { const f2 n = fma2(dchan2, cg2, Sg2); S.SgA = lo(n); S.SgB = hi(n); }
+                const f2 gd2 = mul2(Gs2, dla2);
+                const f2 w2 = mul2(bc2(f1.w), gd2);                        // w = opacity * Gs * dL/dalpha
+                const f2 wy2 = mul2(w2, dy2);
+                const f2 wyy2 = mul2(wy2, dy2);
+                const f2 cr2 = mul2(dchan2, S.g0), cgn2 = mul2(dchan2, S.g1), cb2 = mul2(dchan2, S.g2);
                 // Per-pair sums are raw moments of w = Gs * dL/dGs; the per-Gaussian kernel turns them into
                 // dL/dpix and dL/dconic (it knows A,B,C), which keeps ~9 FP32 ops out of this loop:
                 //   v = (S w dx, S w dy, S w dx^2, S w dx dy, S w dy^2, S Gs dL/dalpha, dL/dr, dL/dg), d_b = dL/db
-                const float4 f2 = e[2];
                 float v[8];
-                float d_b = 0.f;
-                v[5] = 0.f; v[6] = 0.f; v[7] = 0.f;
-                const float wA = pair_backward(A, useA, aA, GsA, f1.w, f2, v[5], v[6], v[7], d_b);
-                const float wB = pair_backward(B, useB, aB, GsB, f1.w, f2, v[5], v[6], v[7], d_b);
-                const float wyA = wA * dyA, wyB = wB * dyB;
-                v[0] = (wA + wB) * dx;
-                v[1] = wyA + wyB;
+                v[0] = (lo(w2) + hi(w2)) * dx;
+                v[1] = lo(wy2) + hi(wy2);
                 v[2] = v[0] * dx;
                 v[3] = v[1] * dx;
-                v[4] = fmaf(wyA, dyA, wyB * dyB);
+                v[4] = lo(wyy2) + hi(wyy2);
+                v[5] = lo(gd2) + hi(gd2);
+                v[6] = lo(cr2) + hi(cr2);
+                v[7] = lo(cgn2) + hi(cgn2);
+                float d_b = lo(cb2) + hi(cb2);
                 const float sum8 = warp_reduce8(v, lane);
                 d_b = warp_sum(d_b);
                 if (red_lane) atomicAdd(acc + (size_t)s_id[c + k] * 12 + red_off, lane == 1 ? d_b : sum8);
