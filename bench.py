@@ -293,15 +293,46 @@ def run_product_arm(args, rank, local_rank, world):
         if w is not None:
             w.wait()
 
+    # ---- the timed step: forward + backward replayed from a CUDA graph (gsvc_b200.graphed.GraphedStep), one graph
+    # per gradient buffer.  The eager call must hand num_rendered back as a Python int, i.e. one host wait per
+    # forward, which leaves the SMs idle for ~25 us per step now that the kernels are this short; the eager number
+    # is reported beside it.
+    from gsvc_b200.graphed import GraphedStep
+    L.gsvc_rast_launch_count(1)
+    graphs = [GraphedStep(rast, params, dL, packed=grad_bufs[b]) for b in range(2)]
+    kernels_per_step = int(L.gsvc_rast_launch_count(1)) // (2 * (graphs[0].warmup + 1))
+    fwd_graph = GraphedStep(rast, params, None)
+
+    def train_step_graphed():
+        b = step_no[0] & 1
+        step_no[0] += 1
+        if pending[b] is not None:
+            pending[b].wait()                  # stream-level wait: the buffer's previous all-reduce has finished
+        out = graphs[b]()
+        if world > 1:
+            pending[b] = dist.all_reduce(grad_bufs[b], op=dist.ReduceOp.SUM, async_op=True)
+        return out
+
+    def forward_graphed():
+        return fwd_graph()
+
+    for _ in range(4):
+        train_step_graphed()
+        forward_graphed()
+    torch.cuda.synchronize(device)
+
     clocks = ClockSampler(local_rank)
     clocks.start()
     # best of REPEATS measurements of exactly K steps each (a shared host occasionally stalls a step for
     # milliseconds; the minimum over repeats is the reproducible figure, as for MEASURED_PEAKS.json)
     REPEATS = 3
-    L.gsvc_rast_launch_count(1)
-    total_ms = min(timed(train_step, args.steps)[0] for _ in range(REPEATS))   # nothing but the kernels on the stream
-    launches = int(L.gsvc_rast_launch_count(1)) // REPEATS
-    fwd_ms = min(timed(forward_only, args.steps)[0] for _ in range(REPEATS))
+    total_ms = min(timed(train_step_graphed, args.steps)[0] for _ in range(REPEATS))
+    if not graphs[0].capacity_ok():
+        raise SystemExit("the captured instance capacity was exceeded (cannot happen with a fixed scene)")
+    launches = kernels_per_step * args.steps
+    fwd_ms = min(timed(forward_graphed, args.steps)[0] for _ in range(REPEATS))
+    eager_ms = min(timed(train_step, args.steps)[0] for _ in range(REPEATS))      # the plain drop-in call
+    eager_fwd_ms = min(timed(forward_only, args.steps)[0] for _ in range(REPEATS))
     # the same K steps again with a CUDA-event pair around every kernel (events between kernels defeat the
     # programmatic-dependent-launch overlap, so this pass is a little slower: it only feeds the roofline)
     _lib.stage_timing(True)
@@ -411,9 +442,14 @@ def run_product_arm(args, rank, local_rank, world):
             "config": {"workload": WORKLOAD, "P": P, "V": V, "R": num_rendered, "N": N, "T": T,
                        "frames": f"frame {f0}+rank of F=600, front view", "l2": "256 MiB flush between timed steps (outside the per-step events)",
                        "timing": "best of 3 repeats of exactly K steps; per-step CUDA events summed; max over ranks",
+                       "step": "forward+backward of the view replayed from a CUDA graph (gsvc_b200.graphed.GraphedStep); "
+                               "the eager drop-in call is reported under `eager`",
                        "parallelism": f"frame-sharded x{world}" + (", NCCL fp32 sum all-reduce of [P,14] grads per step" if world > 1 else "")},
             "fwd_frames_per_s": world * 1000.0 * args.steps / fwd_ms,
             "fwd_ms_per_view": fwd_ms / args.steps,
+            "eager": {"iters_per_s": world * 1000.0 * args.steps / eager_ms, "ms_per_step": eager_ms / args.steps,
+                      "fwd_frames_per_s": world * 1000.0 * args.steps / eager_fwd_ms,
+                      "note": "GaussianRasterizer called eagerly through autograd (one host wait per forward for num_rendered)"},
             "ms_per_step_with_stage_events": staged_ms / args.steps,
             "stage_ms": {k: round(v, 5) for k, v in stage_avg.items()},
             "fwd_stage_ms": {k: round(v, 5) for k, v in fwd_stage_avg.items()},

@@ -1,0 +1,91 @@
+"""CUDA-graph replay of a rasterizer step on static tensors.
+
+The eager call has one unavoidable host wait per forward — `num_rendered` must come back as a Python
+int (ortho_gaussian_renderer/renderer.py:90) — so the host can never run more than one step ahead of
+the device, and with the blend kernels at ~0.1 ms the Python/autograd launch path between "count
+published" and "backward enqueued" shows up as idle SM time.  A training loop whose tensors keep
+their addresses (parameters updated in place by the optimizer, a fixed seed-gradient / loss buffer)
+can instead capture forward + backward once and replay it: one graph launch per step, no host wait,
+the 8 kernels back to back with their programmatic-dependent-launch edges preserved.
+
+    step = GraphedStep(rasterizer, params, dL)        # params: dict of static CUDA tensors (GRAD_LAYOUT keys)
+    color, radii, grads = step()                       # replay; outputs are static tensors, overwritten each call
+    ...
+    if not step.capacity_ok(): step.recapture()        # after a synchronisation, e.g. once per N steps
+
+The binning capacity is fixed at capture time from an eager warm-up (+50 % + 64 Ki instances);
+`capacity_ok()` compares it with the instance count the device published for the last replay.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import rasterizer as R
+from .rasterizer import GaussianRasterizer, RasterizerError
+from .sharding import GRAD_LAYOUT, GRAD_WIDTH, packed_backward
+
+
+class GraphedStep:
+    def __init__(self, rast: GaussianRasterizer, params: Dict[str, torch.Tensor], dL: Optional[torch.Tensor],
+                 packed: Optional[torch.Tensor] = None, warmup: int = 2):
+        """`dL` None: forward only.  `packed`: optional [P,14] buffer the backward writes (sharding.GRAD_LAYOUT);
+        allocated here if omitted."""
+        self.rast, self.params, self.dL = rast, params, dL
+        m = params["means3D"]
+        if not m.is_cuda:
+            raise RasterizerError("GraphedStep needs CUDA tensors: gsvc_b200 has no CPU fallback")
+        self.device, self.P = m.device, int(m.shape[0])
+        self.backward = dL is not None
+        if self.backward and packed is None:
+            packed = torch.empty((self.P, GRAD_WIDTH), dtype=torch.float32, device=self.device)
+        self.packed = packed
+        self.warmup = max(int(warmup), 1)
+        self.graph = None
+        self.color = self.radii = None
+        self.recapture()
+
+    def _run(self):
+        p = self.params
+        if not self.backward:
+            with torch.no_grad():
+                color, radii, n = self.rast(means3D=p["means3D"], means2D=p["means3D"], shs=None,
+                                            colors_precomp=p["colors_precomp"], opacities=p["opacities"],
+                                            scales=p["scales"], rotations=p["rotations"], cov3D_precomp=None)
+            return color, radii, n
+        leaves = {k: p[k].detach().requires_grad_(True) for k, _ in GRAD_LAYOUT}
+        means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
+        color, radii, n = self.rast(means3D=leaves["means3D"], means2D=means2D, shs=None,
+                                    colors_precomp=leaves["colors_precomp"], opacities=leaves["opacities"],
+                                    scales=leaves["scales"], rotations=leaves["rotations"], cov3D_precomp=None)
+        with packed_backward(self.packed):
+            torch.autograd.grad(color, [leaves[k] for k, _ in GRAD_LAYOUT], grad_outputs=self.dL)
+        return color, radii, n
+
+    def recapture(self) -> None:
+        """(Re)build the graph: eager warm-up on a side stream (sets the capacity hint), then capture."""
+        cur = torch.cuda.current_stream(self.device)
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(self.warmup):
+                _, _, n = self._run()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self.num_rendered_at_capture = n
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.color, self.radii, _ = self._run()
+
+    def __call__(self):
+        self.graph.replay()
+        return self.color, self.radii, self.packed
+
+    def num_rendered(self) -> int:
+        """Instance count of the last replay (call after a synchronisation)."""
+        return R.last_num_rendered()
+
+    def capacity_ok(self) -> bool:
+        rs = self.rast.raster_settings
+        return R.captured_capacity_ok(self.device, self.P, int(rs.image_height), int(rs.image_width))
