@@ -10,7 +10,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libgsvc_rast.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # gsvc_rast_status
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_OVERFLOW = 0, -1, -2, -3, -4
@@ -28,10 +28,21 @@ class Settings(C.Structure):
     ]
 
 
+class View(C.Structure):
+    """struct gsvc_rast_view — one view of a batched call (gsvc_rast_*_views)."""
+    _fields_ = [
+        ("viewmatrix", C.c_void_p), ("vm_stride_r", C.c_int64), ("vm_stride_c", C.c_int64),
+        ("campos", C.c_float * 3), ("out_image", C.c_int32), ("flip_x", C.c_int32), ("weight", C.c_float),
+    ]
+
+
+MAX_VIEWS = 16
+
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_int32, C.c_size_t)
 
 _vp, _i32, _i64, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
 _SP = C.POINTER(Settings)
+_VP = C.POINTER(View)
 
 # name -> (restype, argtypes); must list every symbol include/gsvc_rast.h declares
 SIGNATURES = {
@@ -39,6 +50,7 @@ SIGNATURES = {
     "gsvc_rast_last_error": (C.c_char_p, []),
     "gsvc_rast_geom_bytes": (_sz, [_i32, _i32]),
     "gsvc_rast_image_bytes": (_sz, [_i32, _i32]),
+    "gsvc_rast_image_bytes_views": (_sz, [_i32, _i32, _i32]),
     "gsvc_rast_binning_bytes": (_sz, [_i64]),
     "gsvc_rast_backward_scratch_bytes": (_sz, [_i32]),
     "gsvc_rast_visible_filter": (C.c_int, [_SP, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -49,9 +61,15 @@ SIGNATURES = {
     "gsvc_rast_forward": (_i64, [_SP, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ALLOC_FN, _vp, _vp, _vp, _vp]),
     "gsvc_rast_backward": (C.c_int, [_SP, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                      _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "gsvc_rast_export_keys": (C.c_int, [_SP, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gsvc_rast_forward_views_launch": (C.c_int, [_SP, _i32, _VP, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                                 _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, C.c_uint32, _vp]),
+    "gsvc_rast_forward_views_render": (C.c_int, [_SP, _i32, _VP, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "gsvc_rast_backward_views": (C.c_int, [_SP, _i32, _VP, _i32, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                           _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                           _vp]),
+    "gsvc_rast_export_keys": (C.c_int, [_SP, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsvc_rast_export_geom": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "gsvc_rast_export_image": (C.c_int, [_SP, _vp, _vp, _vp, _vp]),
+    "gsvc_rast_export_image": (C.c_int, [_SP, _i32, _vp, _vp, _vp, _vp]),
     "gsvc_rast_launch_count": (_i64, [_i32]),
     "gsvc_rast_stage_timing": (C.c_int, [_i32]),
     "gsvc_rast_stage_times": (C.c_int, [C.POINTER(C.c_float)]),

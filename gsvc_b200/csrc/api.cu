@@ -57,20 +57,50 @@ static int fail(int code, const char* fmt, ...)
         }                                                                                                    \
     } while (0)
 
-static int make_settings(const gsvc_rast_settings* st, int sh_M, DevSettings& d)
+static int make_settings_views(const gsvc_rast_settings* st, int n_views, const gsvc_rast_view* views, int n_out,
+                               int sh_M, DevSettings& d)
 {
     if (!st) return fail(GSVC_RAST_ERR_INVALID, "settings is NULL");
     if (st->image_width <= 0 || st->image_height <= 0) return fail(GSVC_RAST_ERR_INVALID, "image size must be positive");
-    if (!st->viewmatrix) return fail(GSVC_RAST_ERR_INVALID, "viewmatrix is NULL");
+    if (n_views < 1 || n_views > MAX_VIEWS)
+        return fail(GSVC_RAST_ERR_INVALID, "n_views must be in 1..%d, got %d", MAX_VIEWS, n_views);
+    if (!views) return fail(GSVC_RAST_ERR_INVALID, "views is NULL");
+    if (n_out < 1 || n_out > n_views) return fail(GSVC_RAST_ERR_INVALID, "n_out must be in 1..n_views");
     d.W = st->image_width; d.H = st->image_height;
     d.gx = (d.W + TILE - 1) / TILE; d.gy = (d.H + TILE - 1) / TILE;
     if (d.gx > 65535 || d.gy > 65535) return fail(GSVC_RAST_ERR_INVALID, "image too large for 16-bit tile coordinates");
+    if ((long long)d.gx * d.gy * n_views > 0x7fffffffll) return fail(GSVC_RAST_ERR_INVALID, "too many tiles");
     d.x_min = st->x_min; d.y_min = st->y_min; d.scale = st->scale; d.threshold = st->threshold;
     d.scale_modifier = st->scale_modifier;
-    d.bg = st->bg; d.V = st->viewmatrix; d.vs_r = st->vm_stride_r; d.vs_c = st->vm_stride_c;
+    d.bg = st->bg;
     d.sh_degree = st->sh_degree; d.sh_M = sh_M;
-    d.campos[0] = st->campos[0]; d.campos[1] = st->campos[1]; d.campos[2] = st->campos[2];
+    d.n_views = n_views;
+    int used[MAX_VIEWS] = {0};
+    d.accumulate = 0;
+    memset(&d.vt, 0, sizeof(d.vt));
+    for (int v = 0; v < n_views; v++) {
+        if (!views[v].viewmatrix) return fail(GSVC_RAST_ERR_INVALID, "viewmatrix of view %d is NULL", v);
+        if (views[v].out_image < 0 || views[v].out_image >= n_out)
+            return fail(GSVC_RAST_ERR_INVALID, "out_image of view %d is %d, expected 0..%d", v, views[v].out_image, n_out - 1);
+        d.vt.V[v] = views[v].viewmatrix; d.vt.vs_r[v] = views[v].vm_stride_r; d.vt.vs_c[v] = views[v].vm_stride_c;
+        for (int k = 0; k < 3; k++) d.vt.campos[v][k] = views[v].campos[k];
+        d.vt.out_image[v] = views[v].out_image; d.vt.flip_x[v] = views[v].flip_x != 0; d.vt.weight[v] = views[v].weight;
+        if (used[views[v].out_image]++) d.accumulate = 1;
+    }
+    for (int o = 0; o < n_out; o++)
+        if (!used[o]) return fail(GSVC_RAST_ERR_INVALID, "output image %d has no view", o);
     return 0;
+}
+
+static int make_settings(const gsvc_rast_settings* st, int sh_M, DevSettings& d)
+{
+    if (!st) return fail(GSVC_RAST_ERR_INVALID, "settings is NULL");
+    if (!st->viewmatrix) return fail(GSVC_RAST_ERR_INVALID, "viewmatrix is NULL");
+    gsvc_rast_view one;
+    one.viewmatrix = st->viewmatrix; one.vm_stride_r = st->vm_stride_r; one.vm_stride_c = st->vm_stride_c;
+    one.campos[0] = st->campos[0]; one.campos[1] = st->campos[1]; one.campos[2] = st->campos[2];
+    one.out_image = 0; one.flip_x = 0; one.weight = 1.0f;
+    return make_settings_views(st, 1, &one, 1, sh_M, d);
 }
 
 static int check_inputs(int P, int sh_M, int sh_degree, const float* means3D, const float* shs,
@@ -117,6 +147,10 @@ int gsvc_rast_abi_version(void) { return GSVC_RAST_ABI_VERSION; }
 const char* gsvc_rast_last_error(void) { return g_err; }
 size_t gsvc_rast_geom_bytes(int32_t P, int32_t sh_M) { return geom_bytes(P < 1 ? 1 : P, sh_M); }
 size_t gsvc_rast_image_bytes(int32_t W, int32_t H) { return image_bytes(W < 1 ? 1 : W, H < 1 ? 1 : H); }
+size_t gsvc_rast_image_bytes_views(int32_t W, int32_t H, int32_t n_views)
+{
+    return image_bytes(W < 1 ? 1 : W, H < 1 ? 1 : H, n_views < 1 ? 1 : n_views);
+}
 size_t gsvc_rast_binning_bytes(int64_t cap) { return bin_bytes(cap < 1 ? 1 : cap); }
 size_t gsvc_rast_backward_scratch_bytes(int32_t P) { return bwd_scratch_bytes(P < 1 ? 1 : P); }
 int64_t gsvc_rast_launch_count(int32_t reset)
@@ -177,26 +211,27 @@ int gsvc_rast_visible_filter(const gsvc_rast_settings* st, int32_t P, const floa
     return 0;
 }
 
-int gsvc_rast_forward_launch(const gsvc_rast_settings* st, int32_t P, int32_t sh_M, const float* means3D,
-                             const float* shs, const float* colors_precomp, const float* opacities,
-                             const float* scales, const float* rotations, const float* cov3D_precomp, void* geom,
-                             void* image, void* binning, int64_t capacity, void* bwd_scratch, float* out_color,
-                             int32_t* radii, uint64_t* count_slot_host, uint32_t ticket, void* stream_)
+static int forward_launch_core(const gsvc_rast_settings* st, const DevSettings& d, int n_out, int32_t P, int32_t sh_M,
+                               const float* means3D, const float* shs, const float* colors_precomp,
+                               const float* opacities, const float* scales, const float* rotations,
+                               const float* cov3D_precomp, void* geom, void* image, void* binning, int64_t capacity,
+                               void* bwd_scratch, float* out_color, int32_t* radii, uint64_t* count_slot_host,
+                               uint32_t ticket, cudaStream_t stream)
 {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    DevSettings d;
-    int rc = make_settings(st, shs ? sh_M : 0, d);
-    if (rc) return rc;
-    rc = check_inputs(P, sh_M, st->sh_degree, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, true);
+    int rc = check_inputs(P, sh_M, st->sh_degree, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, true);
     if (rc) return rc;
     if (!st->bg) return fail(GSVC_RAST_ERR_INVALID, "bg is NULL");
     if (!geom || !image || !out_color || (P > 0 && !radii))
         return fail(GSVC_RAST_ERR_INVALID, "geom/image/out_color/radii must be non-NULL");
     if (capacity > 0 && !binning) return fail(GSVC_RAST_ERR_INVALID, "binning is NULL");
+    if ((long long)P * d.n_views > 0x7fffffffll) return fail(GSVC_RAST_ERR_INVALID, "P * n_views exceeds 31 bits");
     const bool dbg = st->debug != 0;
-    GeomView g = geom_view(geom, P < 1 ? 1 : P, d.sh_M);
-    ImageView im = image_view(image, d.W, d.H);
+    const int PV = (P < 1 ? 1 : P) * d.n_views;
+    GeomView g = geom_view(geom, PV, d.sh_M);
+    ImageView im = image_view(image, d.W, d.H, d.n_views);
     PreInputs in{P, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp};
+    if (d.accumulate)   // views that share an output image add into it
+        CK(cudaMemsetAsync(out_color, 0, (size_t)n_out * 3 * d.W * d.H * sizeof(float), stream), "zero out_color");
     { StageScope t(ST_PREPROCESS, stream); CK(launch_preprocess(d, in, radii, g, im, static_cast<float4*>(bwd_scratch), stream), "preprocess"); }
     {
         StageScope t(ST_TILE_SCAN, stream);
@@ -208,6 +243,35 @@ int gsvc_rast_forward_launch(const gsvc_rast_settings* st, int32_t P, int32_t sh
         if (rc) return rc;
     }
     return 0;
+}
+
+int gsvc_rast_forward_launch(const gsvc_rast_settings* st, int32_t P, int32_t sh_M, const float* means3D,
+                             const float* shs, const float* colors_precomp, const float* opacities,
+                             const float* scales, const float* rotations, const float* cov3D_precomp, void* geom,
+                             void* image, void* binning, int64_t capacity, void* bwd_scratch, float* out_color,
+                             int32_t* radii, uint64_t* count_slot_host, uint32_t ticket, void* stream_)
+{
+    DevSettings d;
+    int rc = make_settings(st, shs ? sh_M : 0, d);
+    if (rc) return rc;
+    return forward_launch_core(st, d, 1, P, sh_M, means3D, shs, colors_precomp, opacities, scales, rotations,
+                               cov3D_precomp, geom, image, binning, capacity, bwd_scratch, out_color, radii,
+                               count_slot_host, ticket, static_cast<cudaStream_t>(stream_));
+}
+
+int gsvc_rast_forward_views_launch(const gsvc_rast_settings* st, int32_t n_views, const gsvc_rast_view* views_host,
+                                   int32_t n_out, int32_t P, int32_t sh_M, const float* means3D, const float* shs,
+                                   const float* colors_precomp, const float* opacities, const float* scales,
+                                   const float* rotations, const float* cov3D_precomp, void* geom, void* image,
+                                   void* binning, int64_t capacity, void* bwd_scratch, float* out_color,
+                                   int32_t* radii, uint64_t* count_slot_host, uint32_t ticket, void* stream_)
+{
+    DevSettings d;
+    int rc = make_settings_views(st, n_views, views_host, n_out, shs ? sh_M : 0, d);
+    if (rc) return rc;
+    return forward_launch_core(st, d, n_out, P, sh_M, means3D, shs, colors_precomp, opacities, scales, rotations,
+                               cov3D_precomp, geom, image, binning, capacity, bwd_scratch, out_color, radii,
+                               count_slot_host, ticket, static_cast<cudaStream_t>(stream_));
 }
 
 int64_t gsvc_rast_wait_count(const uint64_t* count_slot_host, uint32_t ticket, void* stream_)
@@ -231,22 +295,41 @@ int64_t gsvc_rast_wait_count(const uint64_t* count_slot_host, uint32_t ticket, v
     return fail(GSVC_RAST_ERR_CUDA, "wait_count: the tile scan never published ticket %u", (unsigned)want);
 }
 
-int gsvc_rast_forward_render(const gsvc_rast_settings* st, int32_t P, const void* geom, void* image, void* binning,
-                             int64_t capacity, float* out_color, void* stream_)
+static int forward_render_core(const gsvc_rast_settings* st, const DevSettings& d, int n_out, int32_t P,
+                               const void* geom, void* image, void* binning, int64_t capacity, float* out_color,
+                               cudaStream_t stream)
 {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    DevSettings d;
-    int rc = make_settings(st, 0, d);
-    if (rc) return rc;
     if (!geom || !image || !binning || !out_color || capacity <= 0)
         return fail(GSVC_RAST_ERR_INVALID, "geom/image/binning/out_color must be non-NULL and capacity > 0");
     const bool dbg = st->debug != 0;
     // sh_M only affects the tail of the geom layout (clamp flags), which these stages never touch
-    GeomView g = geom_view(const_cast<void*>(geom), P < 1 ? 1 : P, 0);
-    ImageView im = image_view(image, d.W, d.H);
+    GeomView g = geom_view(const_cast<void*>(geom), (P < 1 ? 1 : P) * d.n_views, 0);
+    ImageView im = image_view(image, d.W, d.H, d.n_views);
     // the scatter cursors were consumed by a previous attempt: reset them
-    CK(cudaMemsetAsync(im.tile_cursor, 0, (size_t)d.gx * d.gy * sizeof(unsigned int), stream), "cursor reset");
+    CK(cudaMemsetAsync(im.tile_cursor, 0, (size_t)d.gx * d.gy * d.n_views * sizeof(unsigned int), stream), "cursor reset");
+    if (d.accumulate)
+        CK(cudaMemsetAsync(out_color, 0, (size_t)n_out * 3 * d.W * d.H * sizeof(float), stream), "zero out_color");
     return render_stages(d, P, g, im, binning, capacity, out_color, stream, dbg);
+}
+
+int gsvc_rast_forward_render(const gsvc_rast_settings* st, int32_t P, const void* geom, void* image, void* binning,
+                             int64_t capacity, float* out_color, void* stream_)
+{
+    DevSettings d;
+    int rc = make_settings(st, 0, d);
+    if (rc) return rc;
+    return forward_render_core(st, d, 1, P, geom, image, binning, capacity, out_color, static_cast<cudaStream_t>(stream_));
+}
+
+int gsvc_rast_forward_views_render(const gsvc_rast_settings* st, int32_t n_views, const gsvc_rast_view* views_host,
+                                   int32_t n_out, int32_t P, const void* geom, void* image, void* binning,
+                                   int64_t capacity, float* out_color, void* stream_)
+{
+    DevSettings d;
+    int rc = make_settings_views(st, n_views, views_host, n_out, 0, d);
+    if (rc) return rc;
+    return forward_render_core(st, d, n_out, P, geom, image, binning, capacity, out_color,
+                               static_cast<cudaStream_t>(stream_));
 }
 
 int64_t gsvc_rast_forward(const gsvc_rast_settings* st, int32_t P, int32_t sh_M, const float* means3D,
@@ -279,6 +362,32 @@ int64_t gsvc_rast_forward(const gsvc_rast_settings* st, int32_t P, int32_t sh_M,
     return (int64_t)R;
 }
 
+static int backward_core(const gsvc_rast_settings* st, const DevSettings& d, int32_t P, int32_t sh_M, int64_t capacity,
+                         const float* means3D, const float* shs, const float* colors_precomp, const float* scales,
+                         const float* rotations, const float* cov3D_precomp, const int32_t* radii, const void* geom,
+                         const void* image, const void* binning, void* scratch, int32_t scratch_is_zero,
+                         const float* dL_dout, BwdOutputs out, cudaStream_t stream)
+{
+    int rc = check_inputs(P, sh_M, st->sh_degree, means3D, shs, colors_precomp, reinterpret_cast<const float*>(1), scales,
+                          rotations, cov3D_precomp, true);
+    if (rc) return rc;
+    if (!st->bg) return fail(GSVC_RAST_ERR_INVALID, "bg is NULL");
+    if (!geom || !image || !scratch || !dL_dout || (P > 0 && !radii))
+        return fail(GSVC_RAST_ERR_INVALID, "geom/image/scratch/dL_dout/radii must be non-NULL");
+    if (capacity <= 0 || !binning) return fail(GSVC_RAST_ERR_INVALID, "binning is NULL or capacity <= 0");
+    if (out.packed && (shs || cov3D_precomp))
+        return fail(GSVC_RAST_ERR_INVALID, "dL_packed needs colors_precomp and the scale/rotation pair");
+    const bool dbg = st->debug != 0;
+    GeomView g = geom_view(const_cast<void*>(geom), (P < 1 ? 1 : P) * d.n_views, d.sh_M);
+    ImageView im = image_view(const_cast<void*>(image), d.W, d.H, d.n_views);
+    BinView b = bin_view(const_cast<void*>(binning), capacity);
+    float4* acc = static_cast<float4*>(scratch);
+    PreInputs in{P, means3D, shs, colors_precomp, nullptr, scales, rotations, cov3D_precomp};
+    { StageScope t(ST_RENDER_BWD, stream); CK(launch_render_backward(d, P, g, im, b, dL_dout, acc, scratch_is_zero != 0, stream), "render_backward"); }
+    { StageScope t(ST_PREPROCESS_BWD, stream); CK(launch_preprocess_backward(d, in, radii, g, acc, out, stream), "preprocess_backward"); }
+    return 0;
+}
+
 int gsvc_rast_backward(const gsvc_rast_settings* st, int32_t P, int32_t sh_M, int64_t capacity,
                        const float* means3D, const float* shs, const float* colors_precomp, const float* scales,
                        const float* rotations, const float* cov3D_precomp, const int32_t* radii, const void* geom,
@@ -288,42 +397,46 @@ int gsvc_rast_backward(const gsvc_rast_settings* st, int32_t P, int32_t sh_M, in
                        float* dL_dscales, float* dL_drotations, float* dL_dcov3D, float* dL_dshs, float* dL_packed,
                        void* stream_)
 {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DevSettings d;
     int rc = make_settings(st, shs ? sh_M : 0, d);
     if (rc) return rc;
-    rc = check_inputs(P, sh_M, st->sh_degree, means3D, shs, colors_precomp, reinterpret_cast<const float*>(1), scales,
-                      rotations, cov3D_precomp, true);
-    if (rc) return rc;
-    if (!st->bg) return fail(GSVC_RAST_ERR_INVALID, "bg is NULL");
-    if (!geom || !image || !scratch || !dL_dout || (P > 0 && !radii))
-        return fail(GSVC_RAST_ERR_INVALID, "geom/image/scratch/dL_dout/radii must be non-NULL");
-    if (capacity <= 0 || !binning) return fail(GSVC_RAST_ERR_INVALID, "binning is NULL or capacity <= 0");
-    const bool dbg = st->debug != 0;
-    GeomView g = geom_view(const_cast<void*>(geom), P < 1 ? 1 : P, d.sh_M);
-    ImageView im = image_view(const_cast<void*>(image), d.W, d.H);
-    BinView b = bin_view(const_cast<void*>(binning), capacity);
-    float4* acc = static_cast<float4*>(scratch);
-    PreInputs in{P, means3D, shs, colors_precomp, nullptr, scales, rotations, cov3D_precomp};
-    { StageScope t(ST_RENDER_BWD, stream); CK(launch_render_backward(d, P, g, im, b, dL_dout, acc, scratch_is_zero != 0, stream), "render_backward"); }
-    if (dL_packed && (shs || cov3D_precomp))
-        return fail(GSVC_RAST_ERR_INVALID, "dL_packed needs colors_precomp and the scale/rotation pair");
     BwdOutputs out{dL_dmeans3D, dL_dmeans2D, dL_dcolors, dL_dopacities, dL_dscales, dL_drotations, dL_dcov3D, dL_dshs,
                    dL_packed};
-    { StageScope t(ST_PREPROCESS_BWD, stream); CK(launch_preprocess_backward(d, in, radii, g, acc, out, stream), "preprocess_backward"); }
-    return 0;
+    return backward_core(st, d, P, sh_M, capacity, means3D, shs, colors_precomp, scales, rotations, cov3D_precomp, radii,
+                         geom, image, binning, scratch, scratch_is_zero, dL_dout, out, static_cast<cudaStream_t>(stream_));
 }
 
-int gsvc_rast_export_keys(const gsvc_rast_settings* st, int64_t capacity, const void* image, const void* binning,
-                          uint64_t* sorted_keys, uint32_t* point_list, uint32_t* ranges, void* stream_)
+int gsvc_rast_backward_views(const gsvc_rast_settings* st, int32_t n_views, const gsvc_rast_view* views_host,
+                             int32_t n_out, int32_t P, int32_t sh_M, int64_t capacity, const float* means3D,
+                             const float* shs, const float* colors_precomp, const float* scales,
+                             const float* rotations, const float* cov3D_precomp, const int32_t* radii,
+                             const void* geom, const void* image, const void* binning, void* scratch,
+                             int32_t scratch_is_zero, const float* dL_dout, float* dL_dmeans3D, float* dL_dmeans2D,
+                             float* dL_dcolors, float* dL_dopacities, float* dL_dscales, float* dL_drotations,
+                             float* dL_dcov3D, float* dL_dshs, float* dL_packed, void* stream_)
+{
+    DevSettings d;
+    int rc = make_settings_views(st, n_views, views_host, n_out, shs ? sh_M : 0, d);
+    if (rc) return rc;
+    BwdOutputs out{dL_dmeans3D, dL_dmeans2D, dL_dcolors, dL_dopacities, dL_dscales, dL_drotations, dL_dcov3D, dL_dshs,
+                   dL_packed};
+    return backward_core(st, d, P, sh_M, capacity, means3D, shs, colors_precomp, scales, rotations, cov3D_precomp, radii,
+                         geom, image, binning, scratch, scratch_is_zero, dL_dout, out, static_cast<cudaStream_t>(stream_));
+}
+
+int gsvc_rast_export_keys(const gsvc_rast_settings* st, int32_t n_views, int64_t capacity, const void* image,
+                          const void* binning, uint64_t* sorted_keys, uint32_t* point_list, uint32_t* ranges,
+                          void* stream_)
 {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DevSettings d;
     int rc = make_settings(st, 0, d);
     if (rc) return rc;
+    if (n_views < 1 || n_views > MAX_VIEWS) return fail(GSVC_RAST_ERR_INVALID, "n_views out of range");
+    d.n_views = n_views;
     if (!image || !binning) return fail(GSVC_RAST_ERR_INVALID, "image/binning is NULL");
     const bool dbg = st->debug != 0;
-    ImageView im = image_view(const_cast<void*>(image), d.W, d.H);
+    ImageView im = image_view(const_cast<void*>(image), d.W, d.H, n_views);
     BinView b = bin_view(const_cast<void*>(binning), capacity > 0 ? capacity : 1);
     CK(launch_export_keys(d, im, b, capacity, reinterpret_cast<unsigned long long*>(sorted_keys), point_list,
                           ranges, stream),
@@ -342,17 +455,18 @@ int gsvc_rast_export_geom(int32_t P, int32_t sh_M, const void* geom, float* dept
     return 0;
 }
 
-int gsvc_rast_export_image(const gsvc_rast_settings* st, const void* image, float* final_T, uint32_t* n_contrib,
-                           void* stream_)
+int gsvc_rast_export_image(const gsvc_rast_settings* st, int32_t n_views, const void* image, float* final_T,
+                           uint32_t* n_contrib, void* stream_)
 {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DevSettings d;
     int rc = make_settings(st, 0, d);
     if (rc) return rc;
+    if (n_views < 1 || n_views > MAX_VIEWS) return fail(GSVC_RAST_ERR_INVALID, "n_views out of range");
     if (!image) return fail(GSVC_RAST_ERR_INVALID, "image is NULL");
     const bool dbg = false;
-    ImageView im = image_view(const_cast<void*>(image), d.W, d.H);
-    const size_t N = (size_t)d.W * d.H;
+    ImageView im = image_view(const_cast<void*>(image), d.W, d.H, n_views);
+    const size_t N = (size_t)d.W * d.H * n_views;
     if (final_T) CK(cudaMemcpyAsync(final_T, im.final_T, N * 4, cudaMemcpyDeviceToDevice, stream), "export final_T");
     if (n_contrib) CK(cudaMemcpyAsync(n_contrib, im.n_contrib, N * 4, cudaMemcpyDeviceToDevice, stream), "export n_contrib");
     return 0;

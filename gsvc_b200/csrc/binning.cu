@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(int T, ImageVie
 cudaError_t launch_tile_scan(const DevSettings& s, ImageView im, unsigned long long* host_slot, unsigned int ticket,
                              cudaStream_t st)
 {
-    const int T = s.gx * s.gy;
+    const int T = s.gx * s.gy * s.n_views;
     count_launch();
     return launch_pdl(tile_scan_kernel, dim3((T + SCAN_THREADS - 1) / SCAN_THREADS), dim3(SCAN_THREADS), st, T, im,
                       host_slot, ticket);
@@ -101,18 +101,21 @@ cudaError_t launch_tile_scan(const DevSettings& s, ImageView im, unsigned long l
 // before it consumes the first result: a warp needs ~(pairs / 128) round trips, whatever the rectangle sizes.
 constexpr int SCATTER_ILP = 4;
 
-__global__ void __launch_bounds__(256) scatter_kernel(int P, int gx, GeomView geo, ImageView im, BinView bin,
+__global__ void __launch_bounds__(256) scatter_kernel(int P, int gx, int Tv, GeomView geo, ImageView im, BinView bin,
                                                       unsigned long long cap)
 {
     pdl_prologue();
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
+    const int v = blockIdx.y;                       // view of the batch: virtual Gaussian v*P + g, tiles v*Tv + t
+    const size_t gv = (size_t)v * P + g;
+    const int tbase = v * Tv;
     ushort4 r = make_ushort4(0, 0, 0, 0);
-    if (g < P) r = geo.rect[g];
+    if (g < P) r = geo.rect[gv];
     const int w = (int)r.z - (int)r.x, h = (int)r.w - (int)r.y;
     const int area = (w > 0 && h > 0) ? w * h : 0;
     unsigned long long item = 0ull;
-    if (area > 0) item = ((unsigned long long)ordered_u32(geo.feat2[g].w) << 32) | (unsigned int)g;
+    if (area > 0) item = ((unsigned long long)ordered_u32(geo.feat2[gv].w) << 32) | (unsigned int)gv;
 
     const WarpTiles wt = warp_tiles_begin(area, r.x, r.y, w > 0 ? w : 1);
     for (int base = 0; base < wt.total; base += 32 * SCATTER_ILP) {
@@ -123,6 +126,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(int P, int gx, GeomView ge
         for (int u = 0; u < SCATTER_ILP; u++) {
             int owner;
             tile[u] = warp_tiles_get(wt, base + 32 * u + lane, gx, owner);
+            if (tile[u] >= 0) tile[u] += tbase;
             it[u] = __shfl_sync(0xffffffffu, item, owner);
             slot[u] = 0u;
             if (tile[u] >= 0) slot[u] = atomicAdd(im.tile_cursor + tile[u], 1u);
@@ -145,7 +149,8 @@ cudaError_t launch_scatter(const DevSettings& s, int P, GeomView g, ImageView im
 {
     if (P <= 0) return cudaSuccess;
     count_launch();
-    return launch_pdl(scatter_kernel, dim3((P + 255) / 256), dim3(256), st, P, s.gx, g, im, b, (unsigned long long)cap);
+    return launch_pdl(scatter_kernel, dim3((P + 255) / 256, s.n_views), dim3(256), st, P, s.gx, s.gx * s.gy, g, im, b,
+                      (unsigned long long)cap);
 }
 
 // ---- per-tile sort of the 64-bit composites -----------------------------------------------------
@@ -303,7 +308,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_tiles_kernel(int T, ImageVi
 
 cudaError_t launch_sort_tiles(const DevSettings& s, ImageView im, BinView b, long long cap, cudaStream_t st)
 {
-    const int T = s.gx * s.gy;
+    const int T = s.gx * s.gy * s.n_views;
     if (T <= 0) return cudaSuccess;
     count_launch();
     return launch_pdl(sort_tiles_kernel, dim3((T + SORT_WARPS - 1) / SORT_WARPS), dim3(SORT_THREADS), st, T, im, b,
@@ -329,7 +334,7 @@ cudaError_t launch_export_keys(const DevSettings& s, ImageView im, BinView b, lo
                                cudaStream_t st)
 {
     (void)R;
-    const int T = s.gx * s.gy;
+    const int T = s.gx * s.gy * s.n_views;   // virtual tiles: keys carry v*Tv + t, point_list v*P + g
     export_keys_kernel<<<T, 128, 0, st>>>(T, im, b, sorted_keys, point_list, ranges);
     count_launch();
     return cudaGetLastError();

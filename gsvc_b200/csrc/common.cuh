@@ -17,15 +17,28 @@ constexpr float ALPHA_MAX = 0.99f;
 constexpr float T_STOP = 0.0001f;
 constexpr float LOWPASS = 0.3f;               // U5
 
+// A batch of views of one Gaussian set (the TSW window: front/back views of one or more frames) is
+// rasterized as ONE virtual problem: virtual Gaussian v*P + g, virtual tile v*Tv + t, virtual pixel
+// v*N + pix.  Every kernel of the chain then runs once for the whole batch.  The drop-in calls are the
+// batch of one view.
+constexpr int MAX_VIEWS = GSVC_RAST_MAX_VIEWS;
+struct ViewTable {
+    const float* V[MAX_VIEWS];           // logical V[r][c] at V[r*vs_r + c*vs_c] (renderer.py:77 passes a permuted view)
+    long long vs_r[MAX_VIEWS], vs_c[MAX_VIEWS];
+    float campos[MAX_VIEWS][3];
+    int out_image[MAX_VIEWS];            // which output image the view is blended into
+    int flip_x[MAX_VIEWS];               // write / read that image mirrored in x (the back view of a frame)
+    float weight[MAX_VIEWS];             // out[out_image] += weight * view  (1 for a plain view, 0.5 for a toast half)
+};
+
 // Settings as the kernels see them (passed by value in the launch parameters).
 struct DevSettings {
     int W, H, gx, gy;
     float x_min, y_min, scale, threshold, scale_modifier;
     const float* bg;
-    const float* V;
-    long long vs_r, vs_c;   // strides of the logical V[r][c] (renderer.py:77 passes a permuted view)
     int sh_degree, sh_M;
-    float campos[3];
+    int n_views, accumulate;   // accumulate: several views share an output image (atomic adds onto a zeroed image)
+    ViewTable vt;
 };
 
 // ---- per-Gaussian state ("geom") -------------------------------------------------------------
@@ -49,6 +62,7 @@ struct ImageHeader {
 };
 struct ImageView {
     ImageHeader* hdr;
+    // T below = n_views * tiles per view, H*W = n_views * pixels per view (virtual tiles / pixels)
     unsigned int* tile_count;   // [T] instances per tile (atomics in preprocess)
     unsigned long long* scan_partials;  // [ceil(T/1024)] per-CTA aggregates of the tile scan (zeroed with tile_count)
     unsigned int* tile_offset;  // [T] exclusive scan of tile_count
@@ -93,11 +107,11 @@ inline size_t geom_bytes(int P, int sh_M)
     if (sh_M > 0) carve<uint8_t>(p, (size_t)P * 3);
     return (size_t)p + 256;
 }
-inline ImageView image_view(void* buf, int W, int H)
+inline ImageView image_view(void* buf, int W, int H, int n_views = 1)
 {
     char* p = static_cast<char*>(buf);
-    size_t T = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
-    size_t N = (size_t)W * H;
+    size_t T = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE) * n_views;
+    size_t N = (size_t)W * H * n_views;
     ImageView v;
     v.hdr = carve<ImageHeader>(p, 1);
     v.tile_count = carve<unsigned int>(p, T);
@@ -109,11 +123,11 @@ inline ImageView image_view(void* buf, int W, int H)
     v.n_contrib = carve<unsigned int>(p, N);
     return v;
 }
-inline size_t image_bytes(int W, int H)
+inline size_t image_bytes(int W, int H, int n_views = 1)
 {
     char* p = nullptr;
-    size_t T = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
-    size_t N = (size_t)W * H;
+    size_t T = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE) * n_views;
+    size_t N = (size_t)W * H * n_views;
     carve<ImageHeader>(p, 1); carve<unsigned int>(p, T); carve<unsigned long long>(p, T / 1024 + 1);
     carve<unsigned int>(p, T); carve<unsigned int>(p, T); carve<uint2>(p, T); carve<float>(p, N); carve<unsigned int>(p, N);
     return (size_t)p + 256;
@@ -246,7 +260,7 @@ cudaError_t launch_render_forward(const DevSettings& s, GeomView g, ImageView im
 cudaError_t launch_render_backward(const DevSettings& s, int P, GeomView g, ImageView im, BinView b,
                                    const float* dL_dout, float4* acc, bool acc_is_zero, cudaStream_t st);
 struct BwdOutputs {
-    float* dL_dmeans3D; float* dL_dmeans2D; float* dL_dcolors; float* dL_dopacities;
+    float* dL_dmeans3D; float* dL_dmeans2D; float* dL_dcolors; float* dL_dopacities;   // dL_dmeans2D is [n_views,P,3]
     float* dL_dscales; float* dL_drotations; float* dL_dcov3D; float* dL_dshs;
     float* packed;  // optional [P,14] (means3D, colours, opacity, scales, rotation) replacing the five dense arrays
 };

@@ -9,7 +9,10 @@
 
 namespace gsvc {
 
-__device__ __forceinline__ float ldV(const DevSettings& s, int r, int c) { return __ldg(s.V + r * s.vs_r + c * s.vs_c); }
+__device__ __forceinline__ float ldV(const DevSettings& s, int v, int r, int c)
+{
+    return __ldg(s.vt.V[v] + r * s.vt.vs_r[v] + c * s.vt.vs_c[v]);
+}
 
 // /root/reference/utils/sh_utils.py:26-43
 __device__ const float SH_C0 = 0.28209479177387814f;
@@ -115,11 +118,14 @@ __global__ void __launch_bounds__(256) preprocess_kernel(DevSettings s, PreInput
     const bool valid = g_raw < in.P;
     if (FILTER && !valid) return;
     const int g = valid ? g_raw : in.P - 1;
+    // view of the batch (grid.y): per-Gaussian state of view v lives at virtual index v*P + g, its tiles at v*Tv + t
+    const int v = FILTER ? 0 : (int)blockIdx.y;
+    const size_t gv = (size_t)v * in.P + g;
     if (!FILTER && acc_to_zero && valid) {
         // the blend backward accumulates into these 9 sums with atomics: zero them here (a store the
         // stream kernel hides) instead of a separate memset launch in the backward
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        acc_to_zero[3 * (size_t)g] = z; acc_to_zero[3 * (size_t)g + 1] = z; acc_to_zero[3 * (size_t)g + 2] = z;
+        acc_to_zero[3 * gv] = z; acc_to_zero[3 * gv + 1] = z; acc_to_zero[3 * gv + 2] = z;
     }
 
     const float p[3] = {__ldg(in.means3D + 3 * g), __ldg(in.means3D + 3 * g + 1), __ldg(in.means3D + 3 * g + 2)};
@@ -131,11 +137,11 @@ __global__ void __launch_bounds__(256) preprocess_kernel(DevSettings s, PreInput
         sc[0] = __ldg(in.scales + 3 * g); sc[1] = __ldg(in.scales + 3 * g + 1); sc[2] = __ldg(in.scales + 3 * g + 2);
         q_pre = __ldg(reinterpret_cast<const float4*>(in.rotations) + g);
     }
-    const float w0[3] = {ldV(s, 0, 0), ldV(s, 0, 1), ldV(s, 0, 2)};
-    const float w1[3] = {ldV(s, 1, 0), ldV(s, 1, 1), ldV(s, 1, 2)};
-    const float vx = w0[0] * p[0] + w0[1] * p[1] + w0[2] * p[2] + ldV(s, 0, 3);
-    const float vy = w1[0] * p[0] + w1[1] * p[1] + w1[2] * p[2] + ldV(s, 1, 3);
-    const float vz = ldV(s, 2, 0) * p[0] + ldV(s, 2, 1) * p[1] + ldV(s, 2, 2) * p[2] + ldV(s, 2, 3);
+    const float w0[3] = {ldV(s, v, 0, 0), ldV(s, v, 0, 1), ldV(s, v, 0, 2)};
+    const float w1[3] = {ldV(s, v, 1, 0), ldV(s, v, 1, 1), ldV(s, v, 1, 2)};
+    const float vx = w0[0] * p[0] + w0[1] * p[1] + w0[2] * p[2] + ldV(s, v, 0, 3);
+    const float vy = w1[0] * p[0] + w1[1] * p[1] + w1[2] * p[2] + ldV(s, v, 1, 3);
+    const float vz = ldV(s, v, 2, 0) * p[0] + ldV(s, v, 2, 1) * p[1] + ldV(s, v, 2, 2) * p[2] + ldV(s, v, 2, 3);
 
     int radius = 0;
     int rminx = 0, rminy = 0, rmaxx = 0, rmaxy = 0;
@@ -168,7 +174,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(DevSettings s, PreInput
         rmaxy = (int)fminf(fgy, fmaxf(0.f, truncf((py + rad_f + (float)(TILE - 1)) / ft)));
         ok = (rmaxx - rminx) * (rmaxy - rminy) > 0;
     }
-    if (valid) radii[g] = ok ? radius : 0;
+    if (valid) radii[gv] = ok ? radius : 0;
     if (FILTER) return;
 
     if (ok) {
@@ -182,10 +188,11 @@ __global__ void __launch_bounds__(256) preprocess_kernel(DevSettings s, PreInput
             rgb[2] = __ldg(in.colors_precomp + 3 * g + 2);
         } else {
             uint8_t cl[3];
-            sh_to_rgb(s.sh_degree, in.shs + (size_t)g * s.sh_M * 3, p, s.campos, rgb, cl);
-            geo.clamped[3 * (size_t)g] = cl[0];
-            geo.clamped[3 * (size_t)g + 1] = cl[1];
-            geo.clamped[3 * (size_t)g + 2] = cl[2];
+            const float campos[3] = {s.vt.campos[v][0], s.vt.campos[v][1], s.vt.campos[v][2]};
+            sh_to_rgb(s.sh_degree, in.shs + (size_t)g * s.sh_M * 3, p, campos, rgb, cl);
+            geo.clamped[3 * gv] = cl[0];
+            geo.clamped[3 * gv + 1] = cl[1];
+            geo.clamped[3 * gv + 2] = cl[2];
         }
         // Half extents of the alpha >= 1/255 ellipse's bounding box (kept for diagnostics; the blend kernels
         // cull with the exact ellipse test): alpha = op*exp(power) >= 1/255  <=>  1/2 d^T Q d <= ln(255 op).
@@ -196,13 +203,13 @@ __global__ void __launch_bounds__(256) preprocess_kernel(DevSettings s, PreInput
             hx = sqrtf(t2 * a) * 1.0001f + 1e-3f;
             hy = sqrtf(t2 * c) * 1.0001f + 1e-3f;
         }
-        geo.feat0[g] = make_float4(px, py, hx, hy);
-        geo.feat1[g] = make_float4(cA, cB, cC, op);
-        geo.feat2[g] = make_float4(rgb[0], rgb[1], rgb[2], vz);
-        geo.rect[g] = make_ushort4((unsigned short)rminx, (unsigned short)rminy, (unsigned short)rmaxx,
-                                   (unsigned short)rmaxy);
+        geo.feat0[gv] = make_float4(px, py, hx, hy);
+        geo.feat1[gv] = make_float4(cA, cB, cC, op);
+        geo.feat2[gv] = make_float4(rgb[0], rgb[1], rgb[2], vz);
+        geo.rect[gv] = make_ushort4((unsigned short)rminx, (unsigned short)rminy, (unsigned short)rmaxx,
+                                    (unsigned short)rmaxy);
     } else if (valid) {
-        geo.rect[g] = make_ushort4(0, 0, 0, 0);
+        geo.rect[gv] = make_ushort4(0, 0, 0, 0);
     }
     // per-tile instance histogram (the counting sort's digit): the warp walks the flattened list of all its
     // (Gaussian, tile) pairs, 32 at a time, so every RED instruction is full width whatever the rectangle sizes
@@ -211,7 +218,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(DevSettings s, PreInput
     for (int base = 0; base < wt.total; base += 32) {
         int owner;
         const int t = warp_tiles_get(wt, base + (threadIdx.x & 31), s.gx, owner);
-        if (t >= 0) atomicAdd(tile_count + t, 1u);
+        if (t >= 0) atomicAdd(tile_count + (size_t)v * (s.gx * s.gy) + t, 1u);
     }
 }
 
@@ -228,14 +235,14 @@ cudaError_t launch_preprocess(const DevSettings& s, const PreInputs& in, int32_t
                               float4* acc_to_zero, cudaStream_t st)
 {
     // one memset clears the per-tile counters and the scan's per-CTA partials that sit right behind them
-    const size_t T = (size_t)s.gx * s.gy;
+    const size_t T = (size_t)s.gx * s.gy * s.n_views;
     const size_t nbytes = reinterpret_cast<char*>(im.scan_partials + (T / 1024 + 1)) - reinterpret_cast<char*>(im.tile_count);
     cudaError_t e = cudaMemsetAsync(im.tile_count, 0, nbytes, st);
     if (e != cudaSuccess) return e;
     if (in.P <= 0) return cudaSuccess;
     count_launch();
-    return launch_pdl(preprocess_kernel<false>, dim3((in.P + 255) / 256), dim3(256), st, s, in, radii, g, im.tile_count,
-                      acc_to_zero);
+    return launch_pdl(preprocess_kernel<false>, dim3((in.P + 255) / 256, s.n_views), dim3(256), st, s, in, radii, g,
+                      im.tile_count, acc_to_zero);
 }
 
 }  // namespace gsvc

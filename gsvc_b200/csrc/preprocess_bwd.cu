@@ -8,7 +8,10 @@
 
 namespace gsvc {
 
-__device__ __forceinline__ float ldVb(const DevSettings& s, int r, int c) { return __ldg(s.V + r * s.vs_r + c * s.vs_c); }
+__device__ __forceinline__ float ldVb(const DevSettings& s, int v, int r, int c)
+{
+    return __ldg(s.vt.V[v] + r * s.vt.vs_r[v] + c * s.vt.vs_c[v]);
+}
 
 __constant__ float B_SH_C0 = 0.28209479177387814f;
 __constant__ float B_SH_C1 = 0.4886025119029199f;
@@ -19,6 +22,7 @@ __constant__ float B_SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.45
                                  -0.5900435899266435f};
 
 // SH backward: basis derivatives of /root/reference/utils/sh_utils.py:57-110 w.r.t. coefficients and direction.
+// ACCUMULATES into dsh (the caller zeroes it): a batch of views sums its views' contributions.
 __device__ void sh_backward(int deg, int M, const float* sh, float* dsh, const float p[3], const float campos[3],
                             const float dL[3], float dmean[3])
 {
@@ -29,21 +33,21 @@ __device__ void sh_backward(int deg, int M, const float* sh, float* dsh, const f
     for (int c = 0; c < 3; c++) {
         const float g = dL[c];
         float rx = 0.f, ry = 0.f, rz = 0.f;
-        dsh[0 * 3 + c] = B_SH_C0 * g;
+        dsh[0 * 3 + c] += B_SH_C0 * g;
         if (deg > 0) {
-            dsh[1 * 3 + c] = -B_SH_C1 * y * g;
-            dsh[2 * 3 + c] = B_SH_C1 * z * g;
-            dsh[3 * 3 + c] = -B_SH_C1 * x * g;
+            dsh[1 * 3 + c] += -B_SH_C1 * y * g;
+            dsh[2 * 3 + c] += B_SH_C1 * z * g;
+            dsh[3 * 3 + c] += -B_SH_C1 * x * g;
             rx = -B_SH_C1 * sh[3 * 3 + c];
             ry = -B_SH_C1 * sh[1 * 3 + c];
             rz = B_SH_C1 * sh[2 * 3 + c];
             if (deg > 1) {
                 const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-                dsh[4 * 3 + c] = B_SH_C2[0] * xy * g;
-                dsh[5 * 3 + c] = B_SH_C2[1] * yz * g;
-                dsh[6 * 3 + c] = B_SH_C2[2] * (2.f * zz - xx - yy) * g;
-                dsh[7 * 3 + c] = B_SH_C2[3] * xz * g;
-                dsh[8 * 3 + c] = B_SH_C2[4] * (xx - yy) * g;
+                dsh[4 * 3 + c] += B_SH_C2[0] * xy * g;
+                dsh[5 * 3 + c] += B_SH_C2[1] * yz * g;
+                dsh[6 * 3 + c] += B_SH_C2[2] * (2.f * zz - xx - yy) * g;
+                dsh[7 * 3 + c] += B_SH_C2[3] * xz * g;
+                dsh[8 * 3 + c] += B_SH_C2[4] * (xx - yy) * g;
                 rx += B_SH_C2[0] * y * sh[4 * 3 + c] + B_SH_C2[2] * 2.f * -x * sh[6 * 3 + c] +
                       B_SH_C2[3] * z * sh[7 * 3 + c] + B_SH_C2[4] * 2.f * x * sh[8 * 3 + c];
                 ry += B_SH_C2[0] * x * sh[4 * 3 + c] + B_SH_C2[1] * z * sh[5 * 3 + c] +
@@ -51,13 +55,13 @@ __device__ void sh_backward(int deg, int M, const float* sh, float* dsh, const f
                 rz += B_SH_C2[1] * y * sh[5 * 3 + c] + B_SH_C2[2] * 4.f * z * sh[6 * 3 + c] +
                       B_SH_C2[3] * x * sh[7 * 3 + c];
                 if (deg > 2) {
-                    dsh[9 * 3 + c] = B_SH_C3[0] * y * (3.f * xx - yy) * g;
-                    dsh[10 * 3 + c] = B_SH_C3[1] * xy * z * g;
-                    dsh[11 * 3 + c] = B_SH_C3[2] * y * (4.f * zz - xx - yy) * g;
-                    dsh[12 * 3 + c] = B_SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy) * g;
-                    dsh[13 * 3 + c] = B_SH_C3[4] * x * (4.f * zz - xx - yy) * g;
-                    dsh[14 * 3 + c] = B_SH_C3[5] * z * (xx - yy) * g;
-                    dsh[15 * 3 + c] = B_SH_C3[6] * x * (xx - 3.f * yy) * g;
+                    dsh[9 * 3 + c] += B_SH_C3[0] * y * (3.f * xx - yy) * g;
+                    dsh[10 * 3 + c] += B_SH_C3[1] * xy * z * g;
+                    dsh[11 * 3 + c] += B_SH_C3[2] * y * (4.f * zz - xx - yy) * g;
+                    dsh[12 * 3 + c] += B_SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy) * g;
+                    dsh[13 * 3 + c] += B_SH_C3[4] * x * (4.f * zz - xx - yy) * g;
+                    dsh[14 * 3 + c] += B_SH_C3[5] * z * (xx - yy) * g;
+                    dsh[15 * 3 + c] += B_SH_C3[6] * x * (xx - 3.f * yy) * g;
                     rx += B_SH_C3[0] * sh[9 * 3 + c] * 6.f * xy + B_SH_C3[1] * sh[10 * 3 + c] * yz +
                           B_SH_C3[2] * sh[11 * 3 + c] * -2.f * xy + B_SH_C3[3] * sh[12 * 3 + c] * -6.f * xz +
                           B_SH_C3[4] * sh[13 * 3 + c] * (-3.f * xx + 4.f * zz - yy) +
@@ -72,7 +76,6 @@ __device__ void sh_backward(int deg, int M, const float* sh, float* dsh, const f
                 }
             }
         }
-        for (int k = (deg + 1) * (deg + 1); k < M; k++) dsh[k * 3 + c] = 0.f;
         ddx += rx * g; ddy += ry * g; ddz += rz * g;
     }
     const float dot = x * ddx + y * ddy + z * ddz;  // through dir = d / |d|
@@ -88,29 +91,39 @@ __global__ void __launch_bounds__(256, 4) preprocess_backward_kernel(DevSettings
     pdl_prologue();
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= in.P) return;
-    const bool vis = radii[g] > 0;
-
-    float dmean[3] = {0.f, 0.f, 0.f}, dm2[2] = {0.f, 0.f}, dcol[3] = {0.f, 0.f, 0.f}, dop = 0.f;
+    float dmean[3] = {0.f, 0.f, 0.f}, dcol[3] = {0.f, 0.f, 0.f}, dop = 0.f;
     float dsc[3] = {0.f, 0.f, 0.f}, drot[4] = {0.f, 0.f, 0.f, 0.f}, dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (in.shs && out.dL_dshs) {
+        float* dsh = out.dL_dshs + (size_t)g * s.sh_M * 3;
+        for (int k = 0; k < s.sh_M * 3; k++) dsh[k] = 0.f;
+    }
 
+    // A batch of views shares the Gaussian parameters: their gradients are summed here, in view order, so the
+    // batch writes ONE dense gradient instead of n_views of them plus the adds.
+    for (int v = 0; v < s.n_views; v++) {
+    const size_t gv = (size_t)v * in.P + g;
+    const bool vis = radii[gv] > 0;
+    float dm2[2] = {0.f, 0.f};
     if (vis) {
         // blend-backward accumulators: raw moments of w = Gs dL/dGs (see render.cu)
         //   a0 = (S w dx, S w dy, S w dx^2, S w dx dy)  a1 = (S w dy^2, dL/dopacity, dL/dr, dL/dg)  a2.x = dL/db
-        const float4 a0 = acc[3 * (size_t)g], a1 = acc[3 * (size_t)g + 1], a2 = acc[3 * (size_t)g + 2];
-        const float4 con = geo.feat1[g];  // conic (A, B, C), opacity
+        const float4 a0 = acc[3 * gv], a1 = acc[3 * gv + 1], a2 = acc[3 * gv + 2];
+        const float4 con = geo.feat1[gv];  // conic (A, B, C), opacity
         const float gpx = -(con.x * a0.x + con.y * a0.y), gpy = -(con.z * a0.y + con.y * a0.x);
         const float gA = -0.5f * a0.z, gB = -a0.w, gC = -0.5f * a1.x;
-        dop = a1.y;
-        dcol[0] = a1.z; dcol[1] = a1.w; dcol[2] = a2.x;
-        const float w0[3] = {ldVb(s, 0, 0), ldVb(s, 0, 1), ldVb(s, 0, 2)};
-        const float w1[3] = {ldVb(s, 1, 0), ldVb(s, 1, 1), ldVb(s, 1, 2)};
+        dop += a1.y;
+        const float dcv[3] = {a1.z, a1.w, a2.x};
+        dcol[0] += dcv[0]; dcol[1] += dcv[1]; dcol[2] += dcv[2];
+        const float w0[3] = {ldVb(s, v, 0, 0), ldVb(s, v, 0, 1), ldVb(s, v, 0, 2)};
+        const float w1[3] = {ldVb(s, v, 1, 0), ldVb(s, v, 1, 1), ldVb(s, v, 1, 2)};
         const float p[3] = {in.means3D[3 * g], in.means3D[3 * g + 1], in.means3D[3 * g + 2]};
 
         if (in.shs && out.dL_dshs) {
-            const uint8_t* cl = geo.clamped + 3 * (size_t)g;
-            const float dL[3] = {cl[0] ? 0.f : dcol[0], cl[1] ? 0.f : dcol[1], cl[2] ? 0.f : dcol[2]};
+            const uint8_t* cl = geo.clamped + 3 * gv;
+            const float dL[3] = {cl[0] ? 0.f : dcv[0], cl[1] ? 0.f : dcv[1], cl[2] ? 0.f : dcv[2]};
+            const float campos[3] = {s.vt.campos[v][0], s.vt.campos[v][1], s.vt.campos[v][2]};
             sh_backward(s.sh_degree, s.sh_M, in.shs + (size_t)g * s.sh_M * 3, out.dL_dshs + (size_t)g * s.sh_M * 3, p,
-                        s.campos, dL, dmean);
+                        campos, dL, dmean);
         }
         // pix = (V[:2,:3] p + V[:2,3] - min) * scale - 0.5
 #pragma unroll
@@ -170,8 +183,8 @@ __global__ void __launch_bounds__(256, 4) preprocess_backward_kernel(DevSettings
 #pragma unroll
             for (int l = 0; l < 3; l++) Gm[3 * k + l] = da * W0[k] * W0[l] + db * W0[k] * W1[l] + dc * W1[k] * W1[l];
         if (in.cov3D_precomp) {
-            dcov[0] = (float)Gm[0]; dcov[1] = (float)(Gm[1] + Gm[3]); dcov[2] = (float)(Gm[2] + Gm[6]);
-            dcov[3] = (float)Gm[4]; dcov[4] = (float)(Gm[5] + Gm[7]); dcov[5] = (float)Gm[8];
+            dcov[0] += (float)Gm[0]; dcov[1] += (float)(Gm[1] + Gm[3]); dcov[2] += (float)(Gm[2] + Gm[6]);
+            dcov[3] += (float)Gm[4]; dcov[4] += (float)(Gm[5] + Gm[7]); dcov[5] += (float)Gm[8];
         } else {
             // Sigma = M M^T, M = R diag(mod*s):  dL/dM = (G + G^T) M
             double dM[9];
@@ -193,22 +206,23 @@ __global__ void __launch_bounds__(256, 4) preprocess_backward_kernel(DevSettings
                     t += dM[3 * i + j] * R[3 * i + j];
                     gR[3 * i + j] = dM[3 * i + j] * sv[j];
                 }
-                dsc[j] = (float)(t * (double)s.scale_modifier);
+                dsc[j] += (float)(t * (double)s.scale_modifier);
             }
             const float4 q = reinterpret_cast<const float4*>(in.rotations)[g];
             const double r = q.x, x = q.y, y = q.z, z = q.w;
-            drot[0] = (float)(2. * (-z * gR[1] + y * gR[2] + z * gR[3] - x * gR[5] - y * gR[6] + x * gR[7]));
-            drot[1] = (float)(2. * (y * gR[1] + z * gR[2] + y * gR[3] - 2. * x * gR[4] - r * gR[5] + z * gR[6] + r * gR[7] -
-                                    2. * x * gR[8]));
-            drot[2] = (float)(2. * (-2. * y * gR[0] + x * gR[1] + r * gR[2] + x * gR[3] + z * gR[5] - r * gR[6] + z * gR[7] -
-                                    2. * y * gR[8]));
-            drot[3] = (float)(2. * (-2. * z * gR[0] - r * gR[1] + x * gR[2] + r * gR[3] - 2. * z * gR[4] + y * gR[5] +
-                                    x * gR[6] + y * gR[7]));
+            drot[0] += (float)(2. * (-z * gR[1] + y * gR[2] + z * gR[3] - x * gR[5] - y * gR[6] + x * gR[7]));
+            drot[1] += (float)(2. * (y * gR[1] + z * gR[2] + y * gR[3] - 2. * x * gR[4] - r * gR[5] + z * gR[6] + r * gR[7] -
+                                     2. * x * gR[8]));
+            drot[2] += (float)(2. * (-2. * y * gR[0] + x * gR[1] + r * gR[2] + x * gR[3] + z * gR[5] - r * gR[6] + z * gR[7] -
+                                     2. * y * gR[8]));
+            drot[3] += (float)(2. * (-2. * z * gR[0] - r * gR[1] + x * gR[2] + r * gR[3] - 2. * z * gR[4] + y * gR[5] +
+                                     x * gR[6] + y * gR[7]));
         }
-    } else if (in.shs && out.dL_dshs) {
-        float* dsh = out.dL_dshs + (size_t)g * s.sh_M * 3;
-        for (int k = 0; k < s.sh_M * 3; k++) dsh[k] = 0.f;
     }
+    if (out.dL_dmeans2D) {
+        out.dL_dmeans2D[3 * gv] = dm2[0]; out.dL_dmeans2D[3 * gv + 1] = dm2[1]; out.dL_dmeans2D[3 * gv + 2] = 0.f;
+    }
+    }   // views
 
     if (out.packed) {
         // [P,14] row = (means3D 3, colours 3, opacity 1, scales 3, rotation 4): the layout the frame-sharded
@@ -218,11 +232,9 @@ __global__ void __launch_bounds__(256, 4) preprocess_backward_kernel(DevSettings
         row[2] = make_float2(dcol[1], dcol[2]);   row[3] = make_float2(dop, dsc[0]);
         row[4] = make_float2(dsc[1], dsc[2]);     row[5] = make_float2(drot[0], drot[1]);
         row[6] = make_float2(drot[2], drot[3]);
-        if (out.dL_dmeans2D) { out.dL_dmeans2D[3 * g] = dm2[0]; out.dL_dmeans2D[3 * g + 1] = dm2[1]; out.dL_dmeans2D[3 * g + 2] = 0.f; }
         return;
     }
     if (out.dL_dmeans3D) { out.dL_dmeans3D[3 * g] = dmean[0]; out.dL_dmeans3D[3 * g + 1] = dmean[1]; out.dL_dmeans3D[3 * g + 2] = dmean[2]; }
-    if (out.dL_dmeans2D) { out.dL_dmeans2D[3 * g] = dm2[0]; out.dL_dmeans2D[3 * g + 1] = dm2[1]; out.dL_dmeans2D[3 * g + 2] = 0.f; }
     if (out.dL_dcolors) { out.dL_dcolors[3 * g] = dcol[0]; out.dL_dcolors[3 * g + 1] = dcol[1]; out.dL_dcolors[3 * g + 2] = dcol[2]; }
     if (out.dL_dopacities) out.dL_dopacities[g] = dop;
     if (out.dL_dscales) { out.dL_dscales[3 * g] = dsc[0]; out.dL_dscales[3 * g + 1] = dsc[1]; out.dL_dscales[3 * g + 2] = dsc[2]; }

@@ -179,13 +179,16 @@ render_forward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, un
     __shared__ float4 s_feat[3 * BATCH];
 
     pdl_prologue();
-    const int tile = blockIdx.x;
+    // virtual tile blockIdx.x = view * Tv + tile (a batch of views is one launch; the drop-in call has one view)
+    const int Tv = s.gx * s.gy;
+    const int view = (int)blockIdx.x / Tv;
+    const int tile = (int)blockIdx.x - view * Tv;
     const int tid = threadIdx.x, lane = tid & 31;
     const BlockGeom bg = block_geom(tile, s.gx, tid);
     const bool inA = bg.px < s.W && bg.py < s.H, inB = bg.px < s.W && bg.py + 4 < s.H;
     const float pxf = (float)bg.px, pyf = (float)bg.py;
 
-    const uint2 rg = im.ranges[tile];
+    const uint2 rg = im.ranges[blockIdx.x];
     if ((unsigned long long)rg.y > cap) return;  // capacity overflow: host re-runs with a larger buffer
     const int n = (int)(rg.y - rg.x);
 
@@ -252,28 +255,41 @@ render_forward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, un
     }
     const size_t N = (size_t)s.W * s.H;
     const float bg0 = __ldg(s.bg + 0), bg1 = __ldg(s.bg + 1), bg2 = __ldg(s.bg + 2);
+    // the view's own per-pixel state (unflipped), and its target: image out_image, optionally mirrored in x,
+    // scaled by weight; views that share an image (toast halves) accumulate with atomics onto a zeroed image
+    float* const fT = im.final_T + (size_t)view * N;
+    unsigned int* const nc = im.n_contrib + (size_t)view * N;
+    float* const out = out_color + (size_t)s.vt.out_image[view] * 3 * N;
+    const float wgt = s.vt.weight[view];
+    const int ox = s.vt.flip_x[view] ? s.W - 1 - bg.px : bg.px;
     if (inA) {
-        const size_t pix = (size_t)bg.py * s.W + bg.px;
-        out_color[pix] = A0 + TA * bg0;
-        out_color[N + pix] = A1 + TA * bg1;
-        out_color[2 * N + pix] = A2 + TA * bg2;
-        im.final_T[pix] = TA;
-        im.n_contrib[pix] = lastA;
+        const size_t pix = (size_t)bg.py * s.W + bg.px, opix = (size_t)bg.py * s.W + ox;
+        const float c0 = wgt * (A0 + TA * bg0), c1 = wgt * (A1 + TA * bg1), c2 = wgt * (A2 + TA * bg2);
+        if (s.accumulate) {
+            atomicAdd(out + opix, c0); atomicAdd(out + N + opix, c1); atomicAdd(out + 2 * N + opix, c2);
+        } else {
+            out[opix] = c0; out[N + opix] = c1; out[2 * N + opix] = c2;
+        }
+        fT[pix] = TA;
+        nc[pix] = lastA;
     }
     if (inB) {
-        const size_t pix = (size_t)(bg.py + 4) * s.W + bg.px;
-        out_color[pix] = B0 + TB * bg0;
-        out_color[N + pix] = B1 + TB * bg1;
-        out_color[2 * N + pix] = B2 + TB * bg2;
-        im.final_T[pix] = TB;
-        im.n_contrib[pix] = lastB;
+        const size_t pix = (size_t)(bg.py + 4) * s.W + bg.px, opix = (size_t)(bg.py + 4) * s.W + ox;
+        const float c0 = wgt * (B0 + TB * bg0), c1 = wgt * (B1 + TB * bg1), c2 = wgt * (B2 + TB * bg2);
+        if (s.accumulate) {
+            atomicAdd(out + opix, c0); atomicAdd(out + N + opix, c1); atomicAdd(out + 2 * N + opix, c2);
+        } else {
+            out[opix] = c0; out[N + opix] = c1; out[2 * N + opix] = c2;
+        }
+        fT[pix] = TB;
+        nc[pix] = lastB;
     }
 }
 
 cudaError_t launch_render_forward(const DevSettings& s, GeomView g, ImageView im, BinView b, long long cap,
                                   float* out_color, cudaStream_t st)
 {
-    const int T = s.gx * s.gy;
+    const int T = s.gx * s.gy * s.n_views;
     if (T <= 0) return cudaSuccess;
     count_launch();
     return launch_pdl(render_forward_kernel, dim3(T), dim3(BLEND_THREADS), st, s, g, im, b, (unsigned long long)cap,
@@ -342,15 +358,24 @@ render_backward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, c
     __shared__ unsigned int s_max[BLEND_WARPS];
 
     pdl_prologue();
-    const int tile = blockIdx.x;
+    const int Tv = s.gx * s.gy;
+    const int view = (int)blockIdx.x / Tv;          // virtual tile = view * Tv + tile
+    const int tile = (int)blockIdx.x - view * Tv;
     const int tid = threadIdx.x, lane = tid & 31;
     const BlockGeom bg = block_geom(tile, s.gx, tid);
     const bool inA = bg.px < s.W && bg.py < s.H, inB = bg.px < s.W && bg.py + 4 < s.H;
     const float pxf = (float)bg.px, pyf = (float)bg.py;
     const size_t N = (size_t)s.W * s.H;
     const size_t pixA = (size_t)bg.py * s.W + bg.px, pixB = (size_t)(bg.py + 4) * s.W + bg.px;
+    // dL/d(view image) = weight * dL/d(output image), read mirrored in x for a flipped view
+    const int ox = s.vt.flip_x[view] ? s.W - 1 - bg.px : bg.px;
+    const size_t opixA = (size_t)bg.py * s.W + ox, opixB = (size_t)(bg.py + 4) * s.W + ox;
+    const float wgt = s.vt.weight[view];
+    const float* const dL = dL_dout + (size_t)s.vt.out_image[view] * 3 * N;
+    const float* const fT = im.final_T + (size_t)view * N;
+    const unsigned int* const nc = im.n_contrib + (size_t)view * N;
 
-    const uint2 rg = im.ranges[tile];
+    const uint2 rg = im.ranges[blockIdx.x];
     const int n = (int)(rg.y - rg.x);
     if (n <= 0) return;
 
@@ -359,13 +384,13 @@ render_backward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, c
     {
         float gA0 = 0.f, gA1 = 0.f, gA2 = 0.f, gB0 = 0.f, gB1 = 0.f, gB2 = 0.f;
         if (inA) {
-            S.TA = im.final_T[pixA]; S.lastA = im.n_contrib[pixA];
-            gA0 = dL_dout[pixA]; gA1 = dL_dout[N + pixA]; gA2 = dL_dout[2 * N + pixA];
+            S.TA = fT[pixA]; S.lastA = nc[pixA];
+            gA0 = wgt * dL[opixA]; gA1 = wgt * dL[N + opixA]; gA2 = wgt * dL[2 * N + opixA];
             S.SgA = S.TA * (bg0 * gA0 + bg1 * gA1 + bg2 * gA2);
         }
         if (inB) {
-            S.TB = im.final_T[pixB]; S.lastB = im.n_contrib[pixB];
-            gB0 = dL_dout[pixB]; gB1 = dL_dout[N + pixB]; gB2 = dL_dout[2 * N + pixB];
+            S.TB = fT[pixB]; S.lastB = nc[pixB];
+            gB0 = wgt * dL[opixB]; gB1 = wgt * dL[N + opixB]; gB2 = wgt * dL[2 * N + opixB];
             S.SgB = S.TB * (bg0 * gB0 + bg1 * gB1 + bg2 * gB2);
         }
         S.g0 = mk2(gA0, gB0); S.g1 = mk2(gA1, gB1); S.g2 = mk2(gA2, gB2);
@@ -470,10 +495,10 @@ cudaError_t launch_render_backward(const DevSettings& s, int P, GeomView g, Imag
                                    const float* dL_dout, float4* acc, bool acc_is_zero, cudaStream_t st)
 {
     if (!acc_is_zero) {
-        cudaError_t e = cudaMemsetAsync(acc, 0, (size_t)P * 48, st);
+        cudaError_t e = cudaMemsetAsync(acc, 0, (size_t)P * s.n_views * 48, st);
         if (e != cudaSuccess) return e;
     }
-    const int T = s.gx * s.gy;
+    const int T = s.gx * s.gy * s.n_views;
     if (T <= 0 || P <= 0) return cudaSuccess;
     count_launch();
     return launch_pdl(render_backward_kernel, dim3(T), dim3(BLEND_THREADS), st, s, g, im, b, dL_dout,

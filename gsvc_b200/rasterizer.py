@@ -398,7 +398,7 @@ class RasterState:
             keys = torch.zeros(max(R, 1), dtype=torch.int64, device=dev)
             pl = torch.zeros(max(R, 1), dtype=torch.int32, device=dev)
             ranges = torch.zeros((T, 2), dtype=torch.int32, device=dev)
-            _lib.check(L.gsvc_rast_export_keys(self.ns.ref, max(R, 1), _ptr(self.image), _ptr(self.binning), _ptr(keys),
+            _lib.check(L.gsvc_rast_export_keys(self.ns.ref, 1, max(R, 1), _ptr(self.image), _ptr(self.binning), _ptr(keys),
                                                _ptr(pl), _ptr(ranges), _stream_ptr(dev)), "gsvc_rast_export_keys")
             torch.cuda.current_stream(dev).synchronize()
         return keys[:R], pl[:R], ranges
@@ -424,7 +424,7 @@ class RasterState:
         with torch.cuda.device(dev):
             fT = torch.zeros((H, W), dtype=torch.float32, device=dev)
             nc = torch.zeros((H, W), dtype=torch.int32, device=dev)
-            _lib.check(L.gsvc_rast_export_image(self.ns.ref, _ptr(self.image), _ptr(fT), _ptr(nc), _stream_ptr(dev)),
+            _lib.check(L.gsvc_rast_export_image(self.ns.ref, 1, _ptr(self.image), _ptr(fT), _ptr(nc), _stream_ptr(dev)),
                        "gsvc_rast_export_image")
             torch.cuda.current_stream(dev).synchronize()
         return fT, nc

@@ -35,8 +35,9 @@ extern "C" {
 #define GSVC_RAST_API
 #endif
 
-#define GSVC_RAST_ABI_VERSION 1
+#define GSVC_RAST_ABI_VERSION 2
 #define GSVC_RAST_TILE 16 /* tile edge in pixels; tile ids are row-major over ceil(W/16) x ceil(H/16) */
+#define GSVC_RAST_MAX_VIEWS 16 /* views per batched call (gsvc_rast_*_views) */
 
 typedef enum gsvc_rast_status {
     GSVC_RAST_OK = 0,
@@ -73,6 +74,7 @@ GSVC_RAST_API const char *gsvc_rast_last_error(void);
  * image: per-tile / per-pixel state; binning: per-instance state for `capacity` tile instances. */
 GSVC_RAST_API size_t gsvc_rast_geom_bytes(int32_t P, int32_t sh_M);
 GSVC_RAST_API size_t gsvc_rast_image_bytes(int32_t image_width, int32_t image_height);
+GSVC_RAST_API size_t gsvc_rast_image_bytes_views(int32_t image_width, int32_t image_height, int32_t n_views);
 GSVC_RAST_API size_t gsvc_rast_binning_bytes(int64_t capacity);
 GSVC_RAST_API size_t gsvc_rast_backward_scratch_bytes(int32_t P); /* per-Gaussian gradient accumulators of the blend backward */
 
@@ -153,17 +155,63 @@ GSVC_RAST_API int gsvc_rast_backward(const gsvc_rast_settings *st, int32_t P, in
                        void *stream);
 
 /*
+ * Batched views ("toast" rendering).  The reference renders every frame twice — front
+ * view, then the x-mirrored back view — flips the second image and averages (pipeline/train.py:353-387,
+ * utils/report_utils.py:303-314), and a training iteration does this for two frames: 4 full rasterizer calls on
+ * the SAME Gaussians.  These entry points rasterize up to GSVC_RAST_MAX_VIEWS views of one Gaussian set in ONE
+ * kernel chain (virtual Gaussian v*P+g, virtual tile v*T+t), blend view v into output image views[v].out_image
+ * (mirrored in x if flip_x, scaled by weight; views sharing an image are summed), and the backward returns the
+ * parameter gradients SUMMED over the views — exactly what autograd accumulates across the reference's calls.
+ * `st` supplies everything the views share (image size, x_min/y_min/scale, threshold, bg, scale_modifier,
+ * sh_degree, debug); its viewmatrix/campos are ignored.  Sizes: geom gsvc_rast_geom_bytes(P*n_views, sh_M),
+ * image gsvc_rast_image_bytes_views(W,H,n_views), scratch gsvc_rast_backward_scratch_bytes(P*n_views).
+ * Outputs: out_color [n_out,3,H,W], radii [n_views,P]; dL_dout [n_out,3,H,W]; dL_dmeans2D [n_views,P,3];
+ * every other gradient as in gsvc_rast_backward.  num_rendered (count slot) is the total over the views.
+ */
+typedef struct gsvc_rast_view {
+    const float *viewmatrix;  /* device 4x4, strides as in gsvc_rast_settings */
+    int64_t vm_stride_r;
+    int64_t vm_stride_c;
+    float campos[3];
+    int32_t out_image;        /* 0..n_out-1 */
+    int32_t flip_x;           /* non-zero: the view lands in (and takes its gradient from) the image mirrored in x */
+    float weight;             /* out[out_image] += weight * view */
+} gsvc_rast_view;
+
+GSVC_RAST_API int gsvc_rast_forward_views_launch(const gsvc_rast_settings *st, int32_t n_views,
+                             const gsvc_rast_view *views_host, int32_t n_out, int32_t P, int32_t sh_M,
+                             const float *means3D, const float *shs, const float *colors_precomp,
+                             const float *opacities, const float *scales, const float *rotations,
+                             const float *cov3D_precomp, void *geom, void *image, void *binning, int64_t capacity,
+                             void *bwd_scratch, float *out_color, int32_t *radii, uint64_t *count_slot_host,
+                             uint32_t ticket, void *stream);
+GSVC_RAST_API int gsvc_rast_forward_views_render(const gsvc_rast_settings *st, int32_t n_views,
+                             const gsvc_rast_view *views_host, int32_t n_out, int32_t P, const void *geom,
+                             void *image, void *binning, int64_t capacity, float *out_color, void *stream);
+GSVC_RAST_API int gsvc_rast_backward_views(const gsvc_rast_settings *st, int32_t n_views, const gsvc_rast_view *views_host,
+                             int32_t n_out, int32_t P, int32_t sh_M, int64_t capacity, const float *means3D,
+                             const float *shs, const float *colors_precomp, const float *scales,
+                             const float *rotations, const float *cov3D_precomp, const int32_t *radii,
+                             const void *geom, const void *image, const void *binning, void *scratch,
+                             int32_t scratch_is_zero, const float *dL_dout, float *dL_dmeans3D, float *dL_dmeans2D,
+                             float *dL_dcolors, float *dL_dopacities, float *dL_dscales, float *dL_drotations,
+                             float *dL_dcov3D, float *dL_dshs, float *dL_packed, void *stream);
+
+/*
  * Stage exports for bit-exact parity tests (not used on the hot path).
  * keys: sorted_keys [R] = (tile << 32) | depth_key, point_list [R], ranges [T,2] (untouched tiles 0,0).
  * geom: depth [P], xy [P,2], conic_opacity [P,4], rgb [P,3], rect [P,4] int32 (minx,miny,maxx,maxy tiles).
  * image: final_T [H,W], n_contrib [H,W].  Any output pointer may be NULL.
+ * For state made by a batched call pass its n_views (keys then carry the virtual tile v*T+t, point_list the
+ * virtual Gaussian v*P+g, ranges is [n_views*T,2], final_T / n_contrib are [n_views,H,W]; export_geom takes
+ * P*n_views); 1 otherwise.
  */
-GSVC_RAST_API int gsvc_rast_export_keys(const gsvc_rast_settings *st, int64_t capacity, const void *image, const void *binning,
-                          uint64_t *sorted_keys, uint32_t *point_list, uint32_t *ranges, void *stream);
+GSVC_RAST_API int gsvc_rast_export_keys(const gsvc_rast_settings *st, int32_t n_views, int64_t capacity, const void *image,
+                          const void *binning, uint64_t *sorted_keys, uint32_t *point_list, uint32_t *ranges, void *stream);
 GSVC_RAST_API int gsvc_rast_export_geom(int32_t P, int32_t sh_M, const void *geom, float *depth, float *xy, float *conic_opacity,
                           float *rgb, int32_t *rect, void *stream);
-GSVC_RAST_API int gsvc_rast_export_image(const gsvc_rast_settings *st, const void *image, float *final_T, uint32_t *n_contrib,
-                           void *stream);
+GSVC_RAST_API int gsvc_rast_export_image(const gsvc_rast_settings *st, int32_t n_views, const void *image, float *final_T,
+                           uint32_t *n_contrib, void *stream);
 
 /*
  * Optional per-stage device timing (tracing aid; used by bench.py for the roofline numbers).

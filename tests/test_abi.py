@@ -44,12 +44,15 @@ def test_no_torch_or_python_dependency_in_the_abi():
 
 
 def test_abi_version_and_sizes(lib):
-    assert lib.gsvc_rast_abi_version() == _lib.ABI_VERSION == 1
+    assert lib.gsvc_rast_abi_version() == _lib.ABI_VERSION == 2
     g1, g2 = lib.gsvc_rast_geom_bytes(1000, 0), lib.gsvc_rast_geom_bytes(2000, 0)
     assert 56 * 1000 <= g1 < g2 <= 2 * g1 + 4096
     assert lib.gsvc_rast_geom_bytes(1000, 16) > g1                       # SH clamp flags
     im = lib.gsvc_rast_image_bytes(1920, 1080)
     assert im >= 8 * 1920 * 1080 + 20 * 8160
+    im4 = lib.gsvc_rast_image_bytes_views(1920, 1080, 4)
+    assert 4 * (8 * 1920 * 1080 + 20 * 8160) <= im4 <= 4 * im
+    assert lib.gsvc_rast_image_bytes_views(1920, 1080, 1) == im
     assert lib.gsvc_rast_binning_bytes(10 ** 6) >= 16 * 10 ** 6
     assert lib.gsvc_rast_backward_scratch_bytes(1000) >= 48 * 1000
     assert lib.gsvc_rast_binning_bytes(0) > 0 and lib.gsvc_rast_geom_bytes(0, 0) > 0
