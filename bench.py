@@ -30,7 +30,7 @@ from gsvc_b200.frames import CONFIGS, CubeGeometry, synthetic_gaussians
 
 WORKLOAD = "UVG-shaped synthetic 1920x1080 frame, 200k Gaussians, forward+backward (BASELINE.json configs[1])"
 METRIC = "train_iters_per_s"
-UNIT = "iters/s (1 iter = rasterizer fwd+bwd of one 1080p view, 200k Gaussians)"
+UNIT = "iters/s (1 iter = rasterizer fwd+bwd of one 1080p view, 200k Gaussians)"   # a step (one frame) is 2 iters
 THRESHOLD = 0.05  # /root/reference/cfgs/cfg_20240919.yaml:13
 
 
@@ -42,17 +42,18 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def algorithmic_bytes(P, V, R, N, T):
+def algorithmic_bytes(P, V, R, N, T, nv=1):
     """Compulsory HBM bytes per launch of each kernel (SURVEY.md §8d stages S1..S5
-    restated for this design's buffers)."""
+    restated for this design's buffers) for a batch of nv views: V = visible (view, Gaussian) pairs and
+    R = instances over all views; P, N, T per view."""
     return {
-        "preprocess": 56 * P + 4 * P + 56 * V,           # inputs, radii, 3 float4 + rect per visible Gaussian
-        "tile_scan": 4 * T + 20 * T,                      # counts in; offsets, cursors, ranges out
+        "preprocess": 56 * P + 4 * P * nv + 56 * V,      # inputs (once), radii, 3 float4 + rect per visible pair
+        "tile_scan": (4 + 20) * T * nv,                   # counts in; offsets, cursors, ranges out
         "scatter": 24 * V + 8 * R,                        # rect + depth in; (depth_key|id) out
         "sort_tiles": 8 * R + 8 * R,                      # composites in; point_list + depth_keys out
-        "render_forward": 8 * T + 40 * R + 20 * N,        # ranges, id + 36 B features per instance, colour+T+n_contrib
-        "render_backward": 8 * T + 40 * R + 20 * N + 36 * V,  # + dL/dC, final_T, n_contrib in; 9 floats per visible out
-        "preprocess_backward": 4 * P + 40 * V + 36 * V + 68 * P,
+        "render_forward": (8 * T + 20 * N) * nv + 40 * R,  # ranges, id + 36 B features per instance, colour+T+n_contrib
+        "render_backward": (8 * T + 20 * N) * nv + 40 * R + 36 * V,  # + dL/dC, final_T, n_contrib in; 9 floats per visible out
+        "preprocess_backward": 4 * P * nv + 76 * V + 56 * P + 12 * P * nv,   # radii, acc+geom+inputs; packed grads, means2D
         "visible_filter": 44 * P,
     }
 
@@ -196,11 +197,17 @@ def run_reference_arm(args, rank, world):
 # --------------------------------------------------------------------------------------------------
 # product arm
 # --------------------------------------------------------------------------------------------------
+VIEWS_PER_STEP = 2   # a step renders one FRAME as the reference composes it: front + back view (train.py:353-375)
+
+
 def run_product_arm(args, rank, local_rank, world):
     import torch.distributed as dist
     from gsvc_b200 import _lib
+    from gsvc_b200.graphed import GraphedStep
+    from gsvc_b200.hostpipe import HostStepPipeline
     from gsvc_b200.rasterizer import GaussianRasterizer
-    from gsvc_b200.sharding import GRAD_LAYOUT, pack_grads, packed_backward
+    from gsvc_b200.sharding import GRAD_LAYOUT, packed_backward
+    from gsvc_b200.views import ViewBatch, rasterize_views
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py product arm needs a CUDA device (no CPU fallback exists)")
@@ -212,12 +219,14 @@ def run_product_arm(args, rank, local_rank, world):
 
     cfg, geom, f0, g = build_scene(world, device)
     frame_id = f0 + rank                     # frame-sharded window: rank r renders frame f0 + r of the shared set
-    rs = settings_for(geom, frame_id, device)
-    rast = GaussianRasterizer(raster_settings=rs)
+    front, back = settings_for(geom, frame_id, device), settings_for(geom, frame_id, device, back=True)
+    toast = ViewBatch.toast(front, back)     # image = (front + flip_x(back)) / 2, both views in ONE kernel chain
+    rast = GaussianRasterizer(raster_settings=front)      # the single-view drop-in call, reported beside
+    NV = VIEWS_PER_STEP
     P, W, H = cfg["P"], cfg["W"], cfg["H"]
     N, T = W * H, ((W + 15) // 16) * ((H + 15) // 16)
-    params = {k: v.clone().requires_grad_(True) for k, v in g.items()}
-    dL = torch.randn((3, H, W), generator=torch.Generator().manual_seed(100 + rank)).to(device)
+    params = {k: v.clone() for k, v in g.items()}         # static tensors: the graphs replay on them
+    dL = torch.randn((1, 3, H, W), generator=torch.Generator().manual_seed(100 + rank)).to(device)
     # frame-sharded steps: the backward writes straight into one of two [P,14] buffers (no pack pass) and the
     # NCCL sum all-reduce of that buffer runs asynchronously, overlapping the next step's forward
     grad_bufs = [torch.empty((P, 14), dtype=torch.float32, device=device) for _ in range(2)]
@@ -225,31 +234,47 @@ def run_product_arm(args, rank, local_rank, world):
     step_no = [0]
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=device)  # 256 MiB > 126 MB L2
 
-    def forward_only(p=params):
-        with torch.no_grad():
-            return rast(means3D=p["means3D"], means2D=p["means3D"], shs=None, colors_precomp=p["colors_precomp"],
-                        opacities=p["opacities"], scales=p["scales"], rotations=p["rotations"], cov3D_precomp=None)
+    def leaves():
+        return {k: params[k].detach().requires_grad_(True) for k, _ in GRAD_LAYOUT}
 
-    def train_step(p=params, packed=None):
+    def toast_eager(backward=True):
+        """The step, launched eagerly (warm-up and the per-stage timing pass)."""
+        if not backward:
+            with torch.no_grad():
+                return rasterize_views(toast, means3D=params["means3D"], opacities=params["opacities"],
+                                       colors_precomp=params["colors_precomp"], scales=params["scales"],
+                                       rotations=params["rotations"])
+        p = leaves()
+        images, radii, n = rasterize_views(toast, means3D=p["means3D"], opacities=p["opacities"],
+                                           colors_precomp=p["colors_precomp"], scales=p["scales"],
+                                           rotations=p["rotations"])
+        b = step_no[0] & 1
+        step_no[0] += 1
+        if pending[b] is not None:
+            pending[b].wait()                  # stream-level wait: the buffer's previous all-reduce has finished
+        with packed_backward(grad_bufs[b]):
+            torch.autograd.grad(images, [p[k] for k, _ in GRAD_LAYOUT], grad_outputs=dL)
+        if world > 1:
+            pending[b] = dist.all_reduce(grad_bufs[b], op=dist.ReduceOp.SUM, async_op=True)
+        return images, radii, n
+
+    def toast_eager_fwd():
+        return toast_eager(False)
+
+    def single_eager():
+        """One view through the reference-shaped drop-in call, eagerly, autograd and all."""
+        p = leaves()
         means2D = torch.zeros_like(p["means3D"], requires_grad=True)
         color, radii, n = rast(means3D=p["means3D"], means2D=means2D, shs=None, colors_precomp=p["colors_precomp"],
                                opacities=p["opacities"], scales=p["scales"], rotations=p["rotations"],
                                cov3D_precomp=None)
-        if world > 1:
-            b = step_no[0] & 1
-            step_no[0] += 1
-            if pending[b] is not None:
-                pending[b].wait()              # stream-level wait: the buffer's previous all-reduce has finished
-            with packed_backward(grad_bufs[b]):
-                grads = torch.autograd.grad(color, [p[k] for k, _ in GRAD_LAYOUT], grad_outputs=dL)
-            pending[b] = dist.all_reduce(grad_bufs[b], op=dist.ReduceOp.SUM, async_op=True)
-            return color, radii, n, grads, b
-        if packed is not None:
-            with packed_backward(packed):
-                grads = torch.autograd.grad(color, [p[k] for k, _ in GRAD_LAYOUT], grad_outputs=dL)
-        else:
-            grads = torch.autograd.grad(color, [p[k] for k, _ in GRAD_LAYOUT], grad_outputs=dL)
-        return color, radii, n, grads, None
+        return torch.autograd.grad(color, [p[k] for k, _ in GRAD_LAYOUT], grad_outputs=dL[0])
+
+    def single_eager_fwd():
+        with torch.no_grad():
+            return rast(means3D=params["means3D"], means2D=params["means3D"], shs=None,
+                        colors_precomp=params["colors_precomp"], opacities=params["opacities"],
+                        scales=params["scales"], rotations=params["rotations"], cov3D_precomp=None)
 
     def sync_all():
         if world > 1:
@@ -282,43 +307,41 @@ def run_product_arm(args, rank, local_rank, world):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), out
 
-    # ---- warm-up (also sets the instance-capacity hint so no step re-sizes its buffers)
+    # ---- warm-up (also sets the instance-capacity hints so no step re-sizes its buffers)
     for _ in range(max(args.warmup, 3)):
         flush.zero_()
-        out = train_step()
+        out = toast_eager()
+        single_eager()
     torch.cuda.synchronize(device)
-    num_rendered = out[2]
-    V = int((out[1] > 0).sum().item())
+    num_rendered = out[2]                                   # instances of both views
+    V = int((out[1] > 0).sum().item())                      # visible (view, Gaussian) pairs
     for w in pending:
         if w is not None:
             w.wait()
 
-    # ---- the timed step: forward + backward replayed from a CUDA graph (gsvc_b200.graphed.GraphedStep), one graph
-    # per gradient buffer.  The eager call must hand num_rendered back as a Python int, i.e. one host wait per
-    # forward, which leaves the SMs idle for ~25 us per step now that the kernels are this short; the eager number
-    # is reported beside it.
-    from gsvc_b200.graphed import GraphedStep
+    # ---- the timed step: forward + backward of the frame replayed from a CUDA graph (gsvc_b200.graphed.GraphedStep),
+    # one graph per gradient buffer.  An eager call must hand num_rendered back as a Python int, i.e. one host wait
+    # per forward, which leaves the SMs idle for ~25 us per call now that the kernels are this short.
     L.gsvc_rast_launch_count(1)
-    graphs = [GraphedStep(rast, params, dL, packed=grad_bufs[b]) for b in range(2)]
+    graphs = [GraphedStep(toast, params, dL, packed=grad_bufs[b]) for b in range(2)]
     kernels_per_step = int(L.gsvc_rast_launch_count(1)) // (2 * (graphs[0].warmup + 1))
-    fwd_graph = GraphedStep(rast, params, None)
+    fwd_graph = GraphedStep(toast, params, None)
+    single_graph = GraphedStep(rast, params, dL[0])
+    single_fwd_graph = GraphedStep(rast, params, None)
 
-    def train_step_graphed():
+    def toast_graphed():
         b = step_no[0] & 1
         step_no[0] += 1
         if pending[b] is not None:
-            pending[b].wait()                  # stream-level wait: the buffer's previous all-reduce has finished
+            pending[b].wait()
         out = graphs[b]()
         if world > 1:
             pending[b] = dist.all_reduce(grad_bufs[b], op=dist.ReduceOp.SUM, async_op=True)
         return out
 
-    def forward_graphed():
-        return fwd_graph()
-
     for _ in range(4):
-        train_step_graphed()
-        forward_graphed()
+        toast_graphed()
+        fwd_graph()
     torch.cuda.synchronize(device)
 
     clocks = ClockSampler(local_rank)
@@ -326,29 +349,37 @@ def run_product_arm(args, rank, local_rank, world):
     # best of REPEATS measurements of exactly K steps each (a shared host occasionally stalls a step for
     # milliseconds; the minimum over repeats is the reproducible figure, as for MEASURED_PEAKS.json)
     REPEATS = 3
-    total_ms = min(timed(train_step_graphed, args.steps)[0] for _ in range(REPEATS))
+    total_ms = min(timed(toast_graphed, args.steps)[0] for _ in range(REPEATS))
     if not graphs[0].capacity_ok():
         raise SystemExit("the captured instance capacity was exceeded (cannot happen with a fixed scene)")
     launches = kernels_per_step * args.steps
-    fwd_ms = min(timed(forward_graphed, args.steps)[0] for _ in range(REPEATS))
-    eager_ms = min(timed(train_step, args.steps)[0] for _ in range(REPEATS))      # the plain drop-in call
-    eager_fwd_ms = min(timed(forward_only, args.steps)[0] for _ in range(REPEATS))
-    # the same K steps again with a CUDA-event pair around every kernel (events between kernels defeat the
-    # programmatic-dependent-launch overlap, so this pass is a little slower: it only feeds the roofline)
+    fwd_ms = min(timed(fwd_graph, args.steps)[0] for _ in range(REPEATS))
+    for w in pending:
+        if w is not None:
+            w.wait()
+    # single-view numbers (one rasterizer call = one view, no all-reduce): graph replay and the eager drop-in call
+    single_ms = min(timed(single_graph, args.steps)[0] for _ in range(REPEATS))
+    single_fwd_ms = min(timed(single_fwd_graph, args.steps)[0] for _ in range(REPEATS))
+    eager_ms = min(timed(single_eager, args.steps)[0] for _ in range(REPEATS))
+    eager_fwd_ms = min(timed(single_eager_fwd, args.steps)[0] for _ in range(REPEATS))
+    # the same K steps again, launched eagerly with a CUDA-event pair around every kernel (events between kernels
+    # defeat the programmatic-dependent-launch overlap, so this pass is slower: it only feeds the roofline)
     _lib.stage_timing(True)
-    staged_ms, _ = timed(train_step, args.steps)
+    staged_ms, _ = timed(toast_eager, args.steps)
     stage_avg = _lib.stage_times()          # mean per stage over the timed steps (last 256)
-    timed(forward_only, args.steps)
+    timed(toast_eager_fwd, args.steps)
     fwd_stage_avg = _lib.stage_times()
     _lib.stage_timing(False)
+    for w in pending:
+        if w is not None:
+            w.wait()
 
     # ---- end to end through the public API with HOST buffers (gsvc_b200.hostpipe.HostStepPipeline): every step
     # copies its inputs (all Gaussian parameters, one [14*P] pinned buffer) from host memory and reads its result
     # (the packed [P,14] parameter gradients a host optimizer consumes) back to pinned host memory, inside the
     # timed region.  Copies run on their own streams, ring-buffered over 2 slots, and the copy of step i+1 is
-    # enqueued before step i's forward blocks the host on num_rendered.  (The rendered image stays on the device,
-    # where the reference computes its loss: pipeline/train.py:407-444.)
-    from gsvc_b200.hostpipe import HostStepPipeline
+    # enqueued before step i runs.  (The rendered image stays on the device, where the reference computes its
+    # loss: pipeline/train.py:407-444.)
     pipe = HostStepPipeline(P, device, slots=2, use_graphs=os.environ.get("GSVC_E2E_GRAPHS", "1") != "0")
     host_flat = torch.empty(14 * P, dtype=torch.float32).pin_memory()
     off = 0
@@ -363,7 +394,7 @@ def run_product_arm(args, rank, local_rank, world):
         for i in range(n):
             if i + 1 < n:
                 pipe.prefetch(host_flat)        # step i+1's copy is in flight while step i computes
-            pipe.step(rast, dL, reduce)
+            pipe.step(toast, dL, reduce)
 
     e2e_steps(6)      # per slot: one eager step (sizes the binning buffer), then the CUDA-graph capture
 
@@ -394,7 +425,7 @@ def run_product_arm(args, rank, local_rank, world):
 
     e2e_ms = min(e2e_run() for _ in range(REPEATS))
     torch.cuda.synchronize(device)
-    if not pipe.capacity_ok(rast):
+    if not pipe.capacity_ok(toast):
         raise SystemExit("e2e: the captured instance capacity was exceeded (cannot happen with a fixed scene)")
     pcie = {"h2d_GBs": round(copy_gbs(pipe.dev_flat[0], host_flat, pipe.s_h2d), 2),
             "d2h_GBs": round(copy_gbs(pipe.host_grads[0].view(-1), pipe.dev_grads[0].view(-1), pipe.s_d2h), 2)}
@@ -421,9 +452,9 @@ def run_product_arm(args, rank, local_rank, world):
 
     if rank == 0:
         ms_per_step = total_ms / args.steps
-        value = world * 1000.0 / ms_per_step
+        value = world * NV * 1000.0 / ms_per_step
         peak, peak_src = load_peaks()
-        alg = algorithmic_bytes(P, V, num_rendered, N, T)
+        alg = algorithmic_bytes(P, V, num_rendered, N, T, NV)
         # per-launch DRAM traffic and issue utilisation of each kernel from the committed ncu --set full capture of
         # this same command (profiles/r1_traffic.json, made by scripts/ncu_traffic.py); None if it is absent
         prof = {}
@@ -435,21 +466,31 @@ def run_product_arm(args, rank, local_rank, world):
         dom = max(stage_avg, key=stage_avg.get)
         achieved = alg[dom] / (stage_avg[dom] * 1e-3) / 1e9
         pairs = 256.0 * num_rendered
+        per_s = lambda ms, units: world * units * 1000.0 * args.steps / ms
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "P": P, "V": V, "R": num_rendered, "N": N, "T": T,
-                       "frames": f"frame {f0}+rank of F=600, front view", "l2": "256 MiB flush between timed steps (outside the per-step events)",
+            "config": {"workload": WORKLOAD, "P": P, "views_per_step": NV, "V": V, "R": num_rendered, "N": N, "T": T,
+                       "frames": f"frame {f0}+rank of F=600, front + back view",
+                       "step": "one frame = its front and back view (the reference's (front + flip(back)) / 2, "
+                               "pipeline/train.py:353-375) forward + backward in ONE batched kernel chain "
+                               "(gsvc_b200.views), replayed from a CUDA graph (gsvc_b200.graphed.GraphedStep); "
+                               "V, R count both views; single-view and eager numbers under `single_view`",
+                       "l2": "256 MiB flush between timed steps (outside the per-step events)",
                        "timing": "best of 3 repeats of exactly K steps; per-step CUDA events summed; max over ranks",
-                       "step": "forward+backward of the view replayed from a CUDA graph (gsvc_b200.graphed.GraphedStep); "
-                               "the eager drop-in call is reported under `eager`",
                        "parallelism": f"frame-sharded x{world}" + (", NCCL fp32 sum all-reduce of [P,14] grads per step" if world > 1 else "")},
-            "fwd_frames_per_s": world * 1000.0 * args.steps / fwd_ms,
-            "fwd_ms_per_view": fwd_ms / args.steps,
-            "eager": {"iters_per_s": world * 1000.0 * args.steps / eager_ms, "ms_per_step": eager_ms / args.steps,
-                      "fwd_frames_per_s": world * 1000.0 * args.steps / eager_fwd_ms,
-                      "note": "GaussianRasterizer called eagerly through autograd (one host wait per forward for num_rendered)"},
+            "fwd_views_per_s": per_s(fwd_ms, NV),
+            "fwd_frames_per_s": per_s(fwd_ms, 1),
+            "fwd_ms_per_frame": fwd_ms / args.steps,
+            "ref_iterations_per_s": per_s(total_ms, 1) / 2.0,
+            "single_view": {
+                "graph": {"iters_per_s": per_s(single_ms, 1), "ms_per_step": single_ms / args.steps,
+                          "fwd_views_per_s": per_s(single_fwd_ms, 1)},
+                "eager": {"iters_per_s": per_s(eager_ms, 1), "ms_per_step": eager_ms / args.steps,
+                          "fwd_views_per_s": per_s(eager_fwd_ms, 1)},
+                "note": "one GaussianRasterizer call = one view (no all-reduce): replayed from a CUDA graph, and "
+                        "called eagerly through autograd (one host wait per forward for num_rendered)"},
             "ms_per_step_with_stage_events": staged_ms / args.steps,
             "stage_ms": {k: round(v, 5) for k, v in stage_avg.items()},
             "fwd_stage_ms": {k: round(v, 5) for k, v in fwd_stage_avg.items()},
@@ -461,10 +502,10 @@ def run_product_arm(args, rank, local_rank, world):
                          "note": "blend kernels are FP32/issue-bound by construction (256 pixel-Gaussian pairs per 40 B "
                                  "instance; ncu: ~84 % issue-active, < 5 % DRAM); the HBM fraction of a stream kernel of "
                                  "this path is reported under visible_filter; see DESIGN.md §4"},
-            "e2e": {"value": world * 1000.0 * args.steps / e2e_ms, "unit": UNIT, "h2d_bytes_per_step": h2d,
+            "e2e": {"value": per_s(e2e_ms, NV), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps, "pcie_alone": pcie,
                     "api": "gsvc_b200.hostpipe.HostStepPipeline (pinned host params in, pinned host [P,14] grads out; "
-                           + ("forward+backward replayed from a CUDA graph per slot)" if pipe.use_graphs else "eager launches)")},
+                           + ("the frame's forward+backward replayed from a CUDA graph per slot)" if pipe.use_graphs else "eager launches)")},
             "visible_filter": dict(vf, frac=vf["achieved_GBs"] / peak),
             "gpu_launches": launches,
             "clocks": clk,
@@ -477,9 +518,9 @@ def run_product_arm(args, rank, local_rank, world):
             total, full, ns, Tt = cpu_sample(geom, f0, g_cpu, tile_stride=stride, threads=cores)
             line["cpu_baseline"] = {
                 "value": 1.0 / full, "unit": UNIT, "cores": cores, "kind": "port",
-                "sample": (f"pure-PyTorch oracle, same scene: preprocess+binning of all {P} Gaussians, blend fwd+bwd on "
-                           f"{ns} of {Tt} tiles (every {stride}th) took {total:.2f} s; blend part scaled x{Tt / ns:.1f} "
-                           f"to a whole view = {full:.1f} s")}
+                "sample": (f"pure-PyTorch oracle, same scene, ONE view: preprocess+binning of all {P} Gaussians, blend "
+                           f"fwd+bwd on {ns} of {Tt} tiles (every {stride}th) took {total:.2f} s; blend part scaled "
+                           f"x{Tt / ns:.1f} to a whole view = {full:.1f} s")}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -25,14 +25,17 @@ import torch
 from . import rasterizer as R
 from .rasterizer import GaussianRasterizer, RasterizerError
 from .sharding import GRAD_LAYOUT, GRAD_WIDTH, packed_backward
+from .views import ViewBatch, rasterize_views
 
 
 class GraphedStep:
-    def __init__(self, rast: GaussianRasterizer, params: Dict[str, torch.Tensor], dL: Optional[torch.Tensor],
+    def __init__(self, rast, params: Dict[str, torch.Tensor], dL: Optional[torch.Tensor],
                  packed: Optional[torch.Tensor] = None, warmup: int = 2):
-        """`dL` None: forward only.  `packed`: optional [P,14] buffer the backward writes (sharding.GRAD_LAYOUT);
-        allocated here if omitted."""
+        """`rast`: a GaussianRasterizer (one view, dL [3,H,W]) or a views.ViewBatch (all its views in one chain,
+        dL [n_out,3,H,W], gradients summed over the views).  `dL` None: forward only.  `packed`: optional [P,14]
+        buffer the backward writes (sharding.GRAD_LAYOUT); allocated here if omitted."""
         self.rast, self.params, self.dL = rast, params, dL
+        self.batch = rast if isinstance(rast, ViewBatch) else None
         m = params["means3D"]
         if not m.is_cuda:
             raise RasterizerError("GraphedStep needs CUDA tensors: gsvc_b200 has no CPU fallback")
@@ -46,19 +49,21 @@ class GraphedStep:
         self.color = self.radii = None
         self.recapture()
 
+    def _call(self, p, means2D):
+        if self.batch is not None:
+            return rasterize_views(self.batch, means3D=p["means3D"], opacities=p["opacities"], means2D=None,
+                                   colors_precomp=p["colors_precomp"], scales=p["scales"], rotations=p["rotations"])
+        return self.rast(means3D=p["means3D"], means2D=means2D, shs=None, colors_precomp=p["colors_precomp"],
+                         opacities=p["opacities"], scales=p["scales"], rotations=p["rotations"], cov3D_precomp=None)
+
     def _run(self):
         p = self.params
         if not self.backward:
             with torch.no_grad():
-                color, radii, n = self.rast(means3D=p["means3D"], means2D=p["means3D"], shs=None,
-                                            colors_precomp=p["colors_precomp"], opacities=p["opacities"],
-                                            scales=p["scales"], rotations=p["rotations"], cov3D_precomp=None)
-            return color, radii, n
+                return self._call(p, p["means3D"])
         leaves = {k: p[k].detach().requires_grad_(True) for k, _ in GRAD_LAYOUT}
-        means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
-        color, radii, n = self.rast(means3D=leaves["means3D"], means2D=means2D, shs=None,
-                                    colors_precomp=leaves["colors_precomp"], opacities=leaves["opacities"],
-                                    scales=leaves["scales"], rotations=leaves["rotations"], cov3D_precomp=None)
+        means2D = None if self.batch is not None else torch.zeros_like(leaves["means3D"], requires_grad=True)
+        color, radii, n = self._call(leaves, means2D)
         with packed_backward(self.packed):
             torch.autograd.grad(color, [leaves[k] for k, _ in GRAD_LAYOUT], grad_outputs=self.dL)
         return color, radii, n
@@ -87,5 +92,6 @@ class GraphedStep:
         return R.last_num_rendered()
 
     def capacity_ok(self) -> bool:
-        rs = self.rast.raster_settings
-        return R.captured_capacity_ok(self.device, self.P, int(rs.image_height), int(rs.image_width))
+        rs = self.batch.settings[0] if self.batch is not None else self.rast.raster_settings
+        return R.captured_capacity_ok(self.device, self.P, int(rs.image_height), int(rs.image_width),
+                                      self.batch.n_views if self.batch is not None else None)

@@ -25,6 +25,7 @@ import torch
 
 from .rasterizer import GaussianRasterizer, RasterizerError
 from .sharding import GRAD_LAYOUT, GRAD_WIDTH, packed_backward
+from .views import ViewBatch, rasterize_views
 
 
 class HostStepPipeline:
@@ -78,11 +79,12 @@ class HostStepPipeline:
             self.in_ready[b] = self.s_h2d.record_event()
         self.ready.append(b)
 
-    def step(self, rast: GaussianRasterizer, dL: torch.Tensor,
-             reduce: Optional[Callable[[torch.Tensor], None]] = None) -> int:
+    def step(self, rast, dL: torch.Tensor, reduce: Optional[Callable[[torch.Tensor], None]] = None) -> int:
         """Forward + backward of the oldest prefetched parameter set on the current stream, then the
-        device→host copy of its packed gradients.  `reduce(buf)` (frame-sharded training) is called on the
-        [P,14] buffer after the backward and must leave the current stream ordered after its collective."""
+        device→host copy of its packed gradients.  `rast`: a GaussianRasterizer (one view, dL [3,H,W]) or a
+        views.ViewBatch (its views in one chain, dL [n_out,3,H,W], gradients summed over the views).
+        `reduce(buf)` (frame-sharded training) is called on the [P,14] buffer after the backward and must leave
+        the current stream ordered after its collective."""
         if not self.ready:
             raise RasterizerError("step() without a prefetched parameter set")
         b = self.ready.popleft()
@@ -99,7 +101,7 @@ class HostStepPipeline:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 self._compute(b, rast, dL)
-            g = self.graphs[b] = (key, graph, rast.raster_settings)
+            g = self.graphs[b] = (key, graph, rast)
         if g is not None:
             g[1].replay()
         else:
@@ -115,22 +117,29 @@ class HostStepPipeline:
         self.n_stepped += 1
         return b
 
-    def _compute(self, b: int, rast: GaussianRasterizer, dL: torch.Tensor) -> int:
+    def _compute(self, b: int, rast, dL: torch.Tensor) -> int:
         p = {k: v.requires_grad_(True) for k, v in self.views(self.dev_flat[b]).items()}
-        means2D = torch.zeros_like(p["means3D"], requires_grad=True)
-        color, radii, n = rast(means3D=p["means3D"], means2D=means2D, shs=None, colors_precomp=p["colors_precomp"],
-                               opacities=p["opacities"], scales=p["scales"], rotations=p["rotations"],
-                               cov3D_precomp=None)
+        if isinstance(rast, ViewBatch):
+            color, radii, n = rasterize_views(rast, means3D=p["means3D"], opacities=p["opacities"],
+                                              colors_precomp=p["colors_precomp"], scales=p["scales"],
+                                              rotations=p["rotations"])
+        else:
+            means2D = torch.zeros_like(p["means3D"], requires_grad=True)
+            color, radii, n = rast(means3D=p["means3D"], means2D=means2D, shs=None,
+                                   colors_precomp=p["colors_precomp"], opacities=p["opacities"], scales=p["scales"],
+                                   rotations=p["rotations"], cov3D_precomp=None)
         with packed_backward(self.dev_grads[b]):
             torch.autograd.grad(color, [p[k] for k, _ in GRAD_LAYOUT], grad_outputs=dL)
         return n
 
-    def capacity_ok(self, rast: GaussianRasterizer) -> bool:
+    def capacity_ok(self, rast) -> bool:
         """After a synchronisation: did the instance capacity of the captured graphs hold the last replayed step?
         (False: call `recapture()`; the gradients of that step are invalid.)"""
         from . import rasterizer as R
-        rs = rast.raster_settings
-        return R.captured_capacity_ok(self.device, self.P, int(rs.image_height), int(rs.image_width))
+        batch = rast if isinstance(rast, ViewBatch) else None
+        rs = batch.settings[0] if batch is not None else rast.raster_settings
+        return R.captured_capacity_ok(self.device, self.P, int(rs.image_height), int(rs.image_width),
+                                      batch.n_views if batch is not None else None)
 
     def recapture(self) -> None:
         self.graphs = [None] * self.slots

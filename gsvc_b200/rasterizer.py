@@ -56,11 +56,12 @@ def last_num_rendered() -> int:
     return int(st.slot[0].item()) & ((1 << 40) - 1) if hasattr(st, "slot") else 0
 
 
-def captured_capacity_ok(device, P: int, H: int, W: int) -> bool:
+def captured_capacity_ok(device, P: int, H: int, W: int, n_views: Optional[int] = None) -> bool:
     """After replaying a CUDA graph that contains the rasterizer (and synchronizing): did the binning capacity
     fixed at capture time hold the instances of the last replay?  If not, the replay's image is invalid and
-    the step must be re-captured (or run eagerly)."""
-    cap = _captured_caps.get((torch.device(device).index, P, H, W))
+    the step must be re-captured (or run eagerly).  `n_views`: for a graph around views.rasterize_views."""
+    key = (torch.device(device).index, P, H, W) + (() if n_views is None else (n_views,))
+    cap = _captured_caps.get(key)
     return cap is None or last_num_rendered() <= cap
 
 
