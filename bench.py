@@ -214,6 +214,7 @@ def run_product_arm(args, rank, local_rank, world):
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=device)
     L = _lib.lib()
 
@@ -387,7 +388,7 @@ def run_product_arm(args, rank, local_rank, world):
         host_flat[off:off + w * P].copy_(g[k].detach().reshape(-1).cpu())
         off += w * P
     h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
-    reduce = (lambda buf: dist.all_reduce(buf, op=dist.ReduceOp.SUM)) if world > 1 else None
+    reduce = (lambda buf: dist.all_reduce(buf, op=dist.ReduceOp.SUM, async_op=True)) if world > 1 else None
 
     def e2e_steps(n):
         pipe.prefetch(host_flat)

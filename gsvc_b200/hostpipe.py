@@ -83,8 +83,10 @@ class HostStepPipeline:
         """Forward + backward of the oldest prefetched parameter set on the current stream, then the
         device→host copy of its packed gradients.  `rast`: a GaussianRasterizer (one view, dL [3,H,W]) or a
         views.ViewBatch (its views in one chain, dL [n_out,3,H,W], gradients summed over the views).
-        `reduce(buf)` (frame-sharded training) is called on the [P,14] buffer after the backward and must leave
-        the current stream ordered after its collective."""
+        `reduce(buf)` (frame-sharded training) is called on the [P,14] buffer after the backward; it either
+        leaves the current stream ordered after its collective (returns None), or returns an asynchronous work
+        handle (`dist.all_reduce(buf, async_op=True)`): then only the device→host copy waits for the collective
+        and the next step's kernels run beside it."""
         if not self.ready:
             raise RasterizerError("step() without a prefetched parameter set")
         b = self.ready.popleft()
@@ -107,11 +109,12 @@ class HostStepPipeline:
         else:
             self.last_num_rendered = self._compute(b, rast, dL)
             self.eager_seen[b] = key
-        if reduce is not None:
-            reduce(self.dev_grads[b])
+        work = reduce(self.dev_grads[b]) if reduce is not None else None
         self.compute_done[b] = main.record_event()
         with torch.cuda.stream(self.s_d2h):
             self.s_d2h.wait_event(self.compute_done[b])
+            if work is not None:
+                work.wait()                                   # stream-level: the copy stream waits for the collective
             self.host_grads[b].copy_(self.dev_grads[b], non_blocking=True)
             self.d2h_done[b] = self.s_d2h.record_event()
         self.n_stepped += 1
