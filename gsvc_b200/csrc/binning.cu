@@ -154,15 +154,19 @@ cudaError_t launch_scatter(const DevSettings& s, int P, GeomView g, ImageView im
 }
 
 // ---- per-tile sort of the 64-bit composites -----------------------------------------------------
-// Normalised bitonic network: every compare-exchange moves the minimum to the lower index, so an
-// arbitrary length n is handled by treating indices >= n as +inf (pairs that touch them are no-ops).
-// Typical buckets hold ~100 instances: one WARP sorts one bucket in shared memory with __syncwarp
-// between stages (no block barriers, 8 buckets per CTA).  Buckets above SORT_WARP_ITEMS are sorted
-// by the whole CTA afterwards (shared memory up to SORT_SMEM_ITEMS, in place in global beyond).
+// Normalised bitonic network (every compare-exchange moves the minimum to the lower index; slots past
+// the bucket's end hold +inf, so any length works).  Typical buckets hold 50..150 instances: one WARP
+// sorts one bucket entirely IN REGISTERS — element e = lane*R + r lives in register r of its lane, a
+// compare-exchange at distance < R is a register pair of the same lane, at distance >= R a 64-bit warp
+// shuffle.  (The earlier shared-memory version of the same network was bound by shared-memory
+// wavefronts — ncu: 390 per bucket, l1tex 53 %, issue 37 % — not by instructions; the shuffle version
+// moves 8 B per element per stage through that pipe instead of up to 32.)  Buckets above
+// SORT_WARP_ITEMS are sorted by the whole CTA afterwards (shared memory up to SORT_SMEM_ITEMS, in place
+// in global memory beyond).
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
-constexpr int SORT_WARP_ITEMS = 512;
-constexpr int SORT_SMEM_ITEMS = SORT_WARPS * SORT_WARP_ITEMS;  // 4096 items = 32 KB
+constexpr int SORT_WARP_ITEMS = 256;   // 8 registers of 64 bits per lane
+constexpr int SORT_SMEM_ITEMS = 2048;  // 16 KB
 
 template <bool BLOCK, typename Ptr>
 __device__ __forceinline__ void bitonic_sort(Ptr a, int n, int tid, int nthreads)
@@ -195,59 +199,73 @@ __device__ __forceinline__ void bitonic_sort(Ptr a, int n, int tid, int nthreads
     }
 }
 
-// Warp-level specialisation: padded size 2^LG known at compile time, so every stage is straight-line code
-// (constant index arithmetic, constant trip counts) — roughly half the instructions of the generic loop.
-template <int LG>
-__device__ __forceinline__ void bitonic_warp(unsigned long long* a, int n, int lane)
+// One step of the network on R = 2^LR registers per lane, BLOCKED layout: element e = lane*R + r.  Element e is
+// compared with element e ^ M and keeps the minimum iff bit DB of e is clear (DB = the highest set bit of M).
+// The low LR bits of M pick the partner's register, the rest its lane: a step with M < R (13 of the 28 steps of
+// a 128-element sort) never leaves the lane, every other one is one 64-bit shuffle per element.
+template <int R, int M, int DB>
+__device__ __forceinline__ void bitonic_step(unsigned long long (&v)[R], int lane)
 {
-    constexpr int HALF = (1 << LG) >> 1;
+    constexpr int LR = R == 1 ? 0 : R == 2 ? 1 : R == 4 ? 2 : 3;
+    constexpr int mr = M & (R - 1), ml = M >> LR;
+    unsigned long long nv[R];
 #pragma unroll
-    for (int p = 1; p <= LG; p++) {
-        const int k = 1 << p, hk = k >> 1;
-#pragma unroll
-        for (int i0 = 0; i0 < HALF; i0 += 32) {
-            const int i = i0 + lane;
-            if (HALF >= 32 || i < HALF) {
-                const int blk = i >> (p - 1), pos = i & (hk - 1);
-                const int lo = blk * k + pos, hi = blk * k + k - 1 - pos;
-                if (hi < n) {
-                    const unsigned long long x = a[lo], y = a[hi];
-                    if (x > y) { a[lo] = y; a[hi] = x; }
-                }
-            }
-        }
-        __syncwarp();
-#pragma unroll
-        for (int q = p - 2; q >= 0; q--) {
-            const int j = 1 << q;
-#pragma unroll
-            for (int i0 = 0; i0 < HALF; i0 += 32) {
-                const int i = i0 + lane;
-                if (HALF >= 32 || i < HALF) {
-                    const int lo = ((i >> q) << (q + 1)) + (i & (j - 1)), hi = lo + j;
-                    if (hi < n) {
-                        const unsigned long long x = a[lo], y = a[hi];
-                        if (x > y) { a[lo] = y; a[hi] = x; }
-                    }
-                }
-            }
-            __syncwarp();
-        }
+    for (int r = 0; r < R; r++) {
+        const unsigned long long o = v[r ^ mr];
+        const unsigned long long pv = ml ? __shfl_xor_sync(0xffffffffu, o, ml) : o;
+        const bool keep_min = DB < LR ? ((r >> (DB < LR ? DB : 0)) & 1) == 0 : ((lane >> (DB >= LR ? DB - LR : 0)) & 1) == 0;
+        nv[r] = ((v[r] < pv) == keep_min) ? v[r] : pv;
     }
+#pragma unroll
+    for (int r = 0; r < R; r++) v[r] = nv[r];
 }
 
-__device__ __forceinline__ void bitonic_warp_dispatch(unsigned long long* a, int n, int lane)
+template <int R, int P, int Q>
+struct BitonicHalfCleaners {   // distances 2^Q, 2^(Q-1), ..., 1
+    static __device__ __forceinline__ void run(unsigned long long (&v)[R], int lane)
+    {
+        bitonic_step<R, (1 << Q), Q>(v, lane);
+        BitonicHalfCleaners<R, P, Q - 1>::run(v, lane);
+    }
+};
+template <int R, int P>
+struct BitonicHalfCleaners<R, P, -1> {
+    static __device__ __forceinline__ void run(unsigned long long (&)[R], int) {}
+};
+template <int R, int P, int LG>
+struct BitonicMerges {          // merge sizes 2^P .. 2^LG
+    static __device__ __forceinline__ void run(unsigned long long (&v)[R], int lane)
+    {
+        bitonic_step<R, (1 << P) - 1, P - 1>(v, lane);          // mirrored compare inside each 2^P block
+        BitonicHalfCleaners<R, P, P - 2>::run(v, lane);
+        BitonicMerges<R, P + 1, LG>::run(v, lane);
+    }
+};
+template <int R, int LG>
+struct BitonicMerges<R, LG + 1, LG> {
+    static __device__ __forceinline__ void run(unsigned long long (&)[R], int) {}
+};
+
+// Sort one bucket of n <= 32*R composites by one warp, registers only; writes the sorted ids / depth keys.
+template <int R, int LG>
+__device__ __forceinline__ void sort_bucket_regs(const unsigned long long* __restrict__ src, int n, int lane,
+                                                 unsigned int* __restrict__ ids, unsigned int* __restrict__ keys)
 {
-    if (n <= 1) return;
-    if (n <= 2) bitonic_warp<1>(a, n, lane);
-    else if (n <= 4) bitonic_warp<2>(a, n, lane);
-    else if (n <= 8) bitonic_warp<3>(a, n, lane);
-    else if (n <= 16) bitonic_warp<4>(a, n, lane);
-    else if (n <= 32) bitonic_warp<5>(a, n, lane);
-    else if (n <= 64) bitonic_warp<6>(a, n, lane);
-    else if (n <= 128) bitonic_warp<7>(a, n, lane);
-    else if (n <= 256) bitonic_warp<8>(a, n, lane);
-    else bitonic_warp<9>(a, n, lane);
+    unsigned long long v[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int e = lane * R + r;
+        v[r] = e < n ? src[e] : ~0ull;
+    }
+    BitonicMerges<R, 1, LG>::run(v, lane);
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int e = lane * R + r;
+        if (e < n) {
+            ids[e] = (unsigned int)v[r];
+            keys[e] = (unsigned int)(v[r] >> 32);
+        }
+    }
 }
 
 __global__ void __launch_bounds__(SORT_THREADS) sort_tiles_kernel(int T, ImageView im, BinView bin,
@@ -267,16 +285,13 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_tiles_kernel(int T, ImageVi
     const bool big = n > SORT_WARP_ITEMS;
     if (lane == 0) s_big[warp] = big ? t : -1;
     if (!big && n > 0) {
-        unsigned long long* mine = s_items + warp * SORT_WARP_ITEMS;
         const unsigned long long* src = bin.inst + rg.x;
-        for (int i = lane; i < n; i += 32) mine[i] = src[i];
-        __syncwarp();
-        bitonic_warp_dispatch(mine, n, lane);
-        for (int i = lane; i < n; i += 32) {
-            const unsigned long long v = mine[i];
-            bin.point_list[rg.x + i] = (unsigned int)v;
-            bin.depth_keys[rg.x + i] = (unsigned int)(v >> 32);
-        }
+        unsigned int* ids = bin.point_list + rg.x;
+        unsigned int* keys = bin.depth_keys + rg.x;
+        if (n <= 32) sort_bucket_regs<1, 5>(src, n, lane, ids, keys);
+        else if (n <= 64) sort_bucket_regs<2, 6>(src, n, lane, ids, keys);
+        else if (n <= 128) sort_bucket_regs<4, 7>(src, n, lane, ids, keys);
+        else sort_bucket_regs<8, 8>(src, n, lane, ids, keys);
     }
     __syncthreads();
     for (int w = 0; w < SORT_WARPS; w++) {
