@@ -42,8 +42,7 @@ struct DevSettings {
 };
 
 // ---- per-Gaussian state ("geom") -------------------------------------------------------------
-//  feat0 = (pix.x, pix.y, hx, hy)  with (hx,hy) the half extents of the alpha >= 1/255 ellipse's
-//          bounding box (exact-culling aid; 0 when the Gaussian can never reach 1/255)
+//  feat0 = (pix.x, pix.y, 0, 0)
 //  feat1 = (conic.A, conic.B, conic.C, opacity)      feat2 = (r, g, b, view depth)
 //  rect  = tile rectangle (minx, miny, maxx, maxy), max exclusive; all-zero when culled
 struct GeomView {

@@ -194,16 +194,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(DevSettings s, PreInput
             geo.clamped[3 * gv + 1] = cl[1];
             geo.clamped[3 * gv + 2] = cl[2];
         }
-        // Half extents of the alpha >= 1/255 ellipse's bounding box (kept for diagnostics; the blend kernels
-        // cull with the exact ellipse test): alpha = op*exp(power) >= 1/255  <=>  1/2 d^T Q d <= ln(255 op).
-        float hx = 0.f, hy = 0.f;
-        const float tau = logf(255.0f * op);
-        if (tau > 0.f) {
-            const float t2 = 2.0f * tau * 1.0001f + 1e-4f;
-            hx = sqrtf(t2 * a) * 1.0001f + 1e-3f;
-            hy = sqrtf(t2 * c) * 1.0001f + 1e-3f;
-        }
-        geo.feat0[gv] = make_float4(px, py, hx, hy);
+        geo.feat0[gv] = make_float4(px, py, 0.f, 0.f);   // .zw: scratch of the blend kernels' staging (B/A, B/C)
         geo.feat1[gv] = make_float4(cA, cB, cC, op);
         geo.feat2[gv] = make_float4(rgb[0], rgb[1], rgb[2], vz);
         geo.rect[gv] = make_ushort4((unsigned short)rminx, (unsigned short)rminy, (unsigned short)rmaxx,
@@ -220,6 +211,12 @@ __global__ void __launch_bounds__(256) preprocess_kernel(DevSettings s, PreInput
         const int t = warp_tiles_get(wt, base + (threadIdx.x & 31), s.gx, owner);
         if (t >= 0) atomicAdd(tile_count + (size_t)v * (s.gx * s.gy) + t, 1u);
     }
+    // Measured and rejected (profiles/r1_notes.md): (a) taking each instance's rank inside its tile from this
+    // atomic's return value and writing (composite, tile, rank) records so that the scatter needs no second atomic
+    // pass; (b) running the tile scan in the last CTA of this kernel (threadfence + counter).  Both made the
+    // 2-view step slower (+15 us): this kernel is instruction-bound, the fire-and-forget RED is free for it while
+    // a returning ATOM or a serial single-CTA scan tail is not.
+
 }
 
 cudaError_t launch_visible_filter(const DevSettings& s, const PreInputs& in, int32_t* radii, cudaStream_t st)
