@@ -381,14 +381,16 @@ def run_product_arm(args, rank, local_rank, world):
     # timed region.  Copies run on their own streams, ring-buffered over 2 slots, and the copy of step i+1 is
     # enqueued before step i runs.  (The rendered image stays on the device, where the reference computes its
     # loss: pipeline/train.py:407-444.)
-    pipe = HostStepPipeline(P, device, slots=2, use_graphs=os.environ.get("GSVC_E2E_GRAPHS", "1") != "0")
+    pipe = HostStepPipeline(P, device, slots=2, use_graphs=os.environ.get("GSVC_E2E_GRAPHS", "1") != "0",
+                            sharded=world > 1 and P % world == 0)
     host_flat = torch.empty(14 * P, dtype=torch.float32).pin_memory()
     off = 0
     for k, w in GRAD_LAYOUT:
         host_flat[off:off + w * P].copy_(g[k].detach().reshape(-1).cpu())
         off += w * P
-    h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
-    reduce = (lambda buf: dist.all_reduce(buf, op=dist.ReduceOp.SUM, async_op=True)) if world > 1 else None
+    h2d, d2h = pipe.h2d_bytes * pipe.world, pipe.d2h_bytes * pipe.world      # all ranks together
+    # replicated host state (P not divisible by the world size): every rank copies everything and all-reduces
+    reduce = (lambda buf: dist.all_reduce(buf, op=dist.ReduceOp.SUM, async_op=True)) if world > 1 and pipe.world == 1 else None
 
     def e2e_steps(n):
         pipe.prefetch(host_flat)
@@ -429,7 +431,8 @@ def run_product_arm(args, rank, local_rank, world):
     if not pipe.capacity_ok(toast):
         raise SystemExit("e2e: the captured instance capacity was exceeded (cannot happen with a fixed scene)")
     pcie = {"h2d_GBs": round(copy_gbs(pipe.dev_flat[0], host_flat, pipe.s_h2d), 2),
-            "d2h_GBs": round(copy_gbs(pipe.host_grads[0].view(-1), pipe.dev_grads[0].view(-1), pipe.s_d2h), 2)}
+            "d2h_GBs": round(copy_gbs(pipe.host_grads[0].view(-1), pipe.dev_grads[0].view(-1), pipe.s_d2h), 2),
+            "note": "one direction alone, one rank"}
     # ---- the second native entry point, visible_filter over 1M anchors (prefilter_voxel, preprocess.py:99-104):
     # a pure stream kernel — the one stage whose HBM roofline fraction is meaningful as such
     vf = None
@@ -505,6 +508,9 @@ def run_product_arm(args, rank, local_rank, world):
                                  "this path is reported under visible_filter; see DESIGN.md §4"},
             "e2e": {"value": per_s(e2e_ms, NV), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps, "pcie_alone": pcie,
+                    "host_state": ("sharded by rows over the ranks: each rank uploads 1/N of the parameters (all-gather over "
+                                   "NVLink fills in the rest) and reads back 1/N of the summed gradients (reduce-scatter); "
+                                   "the byte counts are the N ranks together") if pipe.world > 1 else "one rank, everything",
                     "api": "gsvc_b200.hostpipe.HostStepPipeline (pinned host params in, pinned host [P,14] grads out; "
                            + ("the frame's forward+backward replayed from a CUDA graph per slot)" if pipe.use_graphs else "eager launches)")},
             "visible_filter": dict(vf, frac=vf["achieved_GBs"] / peak),

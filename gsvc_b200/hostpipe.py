@@ -15,6 +15,12 @@ Copies run on their own streams and every buffer is ring-buffered over `slots` e
 different steps at once and the step time is max(copy in, compute, copy out) instead of their sum.
 The forward's only host wait (num_rendered, published by the tile scan) happens after the next
 step's copy is already in flight.
+
+Frame-sharded training on G GPUs (`sharded=True`, torch.distributed initialised): the Gaussians are
+replicated on the devices but the HOST state is sharded by rows — rank r uploads only rows
+[r·P/G, (r+1)·P/G) of each parameter segment and the devices all-gather the rest over NVLink; the
+gradients are reduce-scattered and rank r reads back only its rows.  PCIe then carries 1/G of the bytes
+per rank (the host link, not the GPUs, is what G replicated uploads would saturate).
 """
 from __future__ import annotations
 
@@ -29,7 +35,7 @@ from .views import ViewBatch, rasterize_views
 
 
 class HostStepPipeline:
-    def __init__(self, P: int, device, slots: int = 2, use_graphs: bool = True):
+    def __init__(self, P: int, device, slots: int = 2, use_graphs: bool = True, sharded: bool = False):
         """`use_graphs`: after one eager step per slot (which sizes the binning buffer), the slot's forward +
         backward (8 kernels) is captured in a CUDA graph and replayed, so a step costs the host one graph launch
         instead of ~10 launches and the autograd bookkeeping; `capacity_ok()` reports whether the instance capacity
@@ -54,8 +60,21 @@ class HostStepPipeline:
         self.use_graphs = bool(use_graphs)
         self.graphs = [None] * slots         # per slot: (key, CUDAGraph) once captured
         self.eager_seen = [None] * slots     # per slot: key of the last eager step (capture needs one first)
-        self.h2d_bytes = GRAD_WIDTH * P * 4
-        self.d2h_bytes = GRAD_WIDTH * P * 4
+        # host-side row sharding over the ranks of the default process group
+        self.rank, self.world = 0, 1
+        if sharded:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                self.rank, self.world = dist.get_rank(), dist.get_world_size()
+                if P % self.world:
+                    raise RasterizerError(f"sharded host state needs P ({P}) divisible by the world size ({self.world})")
+        self.rows = P // self.world
+        self.r0, self.r1 = self.rank * self.rows, (self.rank + 1) * self.rows
+        if self.world > 1:
+            self.dev_shard = [[torch.empty(self.rows * w, **f32) for _, w in GRAD_LAYOUT] for _ in range(slots)]
+            self.dev_gshard = [torch.empty((self.rows, GRAD_WIDTH), **f32) for _ in range(slots)]
+        self.h2d_bytes = GRAD_WIDTH * self.rows * 4     # per rank
+        self.d2h_bytes = GRAD_WIDTH * self.rows * 4
 
     def views(self, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
         out, o, P = {}, 0, self.P
@@ -75,7 +94,27 @@ class HostStepPipeline:
         with torch.cuda.stream(self.s_h2d):
             if self.compute_done[b] is not None:
                 self.s_h2d.wait_event(self.compute_done[b])   # the step that read this slot has finished
-            self.dev_flat[b].copy_(host_flat.view(-1), non_blocking=True)
+            if self.world == 1:
+                self.dev_flat[b].copy_(host_flat.view(-1), non_blocking=True)
+            else:
+                # this rank's rows of every segment over PCIe, everybody else's over NVLink
+                import torch.distributed as dist
+                hf, off = host_flat.view(-1), 0
+                for i, (_, w) in enumerate(GRAD_LAYOUT):
+                    self.dev_shard[b][i].copy_(hf[off + self.r0 * w:off + self.r1 * w], non_blocking=True)
+                    off += w * self.P
+                pairs, off = [], 0
+                for i, (_, w) in enumerate(GRAD_LAYOUT):
+                    pairs.append((self.dev_flat[b][off:off + w * self.P], self.dev_shard[b][i]))
+                    off += w * self.P
+                try:     # the five all-gathers as ONE NCCL group (one kernel launch)
+                    from torch.distributed.distributed_c10d import _coalescing_manager
+                    with _coalescing_manager(device=self.device, async_ops=False):
+                        for out, inp in pairs:
+                            dist.all_gather_into_tensor(out, inp)
+                except ImportError:
+                    for out, inp in pairs:
+                        dist.all_gather_into_tensor(out, inp)
             self.in_ready[b] = self.s_h2d.record_event()
         self.ready.append(b)
 
@@ -109,13 +148,21 @@ class HostStepPipeline:
         else:
             self.last_num_rendered = self._compute(b, rast, dL)
             self.eager_seen[b] = key
-        work = reduce(self.dev_grads[b]) if reduce is not None else None
+        work = None
+        if self.world > 1:
+            # sum over ranks, each rank keeps (and reads back) its own rows
+            import torch.distributed as dist
+            work = dist.reduce_scatter_tensor(self.dev_gshard[b], self.dev_grads[b], op=dist.ReduceOp.SUM,
+                                              async_op=True)
+        elif reduce is not None:
+            work = reduce(self.dev_grads[b])
         self.compute_done[b] = main.record_event()
         with torch.cuda.stream(self.s_d2h):
             self.s_d2h.wait_event(self.compute_done[b])
             if work is not None:
                 work.wait()                                   # stream-level: the copy stream waits for the collective
-            self.host_grads[b].copy_(self.dev_grads[b], non_blocking=True)
+            src = self.dev_gshard[b] if self.world > 1 else self.dev_grads[b]
+            self.host_grads[b][self.r0:self.r1].copy_(src, non_blocking=True)
             self.d2h_done[b] = self.s_d2h.record_event()
         self.n_stepped += 1
         return b
@@ -149,7 +196,8 @@ class HostStepPipeline:
         self.eager_seen = [None] * self.slots
 
     def grads(self, slot: int) -> torch.Tensor:
-        """The [P,14] gradients of the step that returned `slot` (pinned host memory); blocks until they landed."""
+        """The [P,14] gradients of the step that returned `slot` (pinned host memory); blocks until they landed.
+        With sharded host state only rows [r0, r1) of this rank are valid (summed over the ranks)."""
         ev = self.d2h_done[slot]
         if ev is None:
             raise RasterizerError(f"slot {slot} has no finished step")
