@@ -175,3 +175,71 @@ def test_config3_window_sharding_is_split_independent(cuda_device):
         # every backward sums its fp32 atomics in a different order: equal to rounding, not bitwise
         assert (total - single).abs().max() <= 5e-5 * single.abs().max()
     assert single.abs().max() > 0
+
+
+def test_config2_toast_equals_two_calls(cuda_device):
+    """BASELINE config 2 as the reference composes a frame — (front + flip(back)) / 2 — in one batched chain:
+    equals the two single-view calls composed in PyTorch (forward within rounding of the final average, gradients
+    up to summation order), and the frame's instance count is the sum of the views'."""
+    from gsvc_b200.rasterizer import GaussianRasterizer
+    from gsvc_b200.views import render_toast
+    cfg, g, rs_f, _ = build(2, cuda_device)
+    _, _, rs_b, _ = build(2, cuda_device, back=True)
+    names = ("means3D", "colors_precomp", "opacities", "scales", "rotations")
+    p = {k: g[k].to(cuda_device).requires_grad_(True) for k in names}
+    image, radii, n = render_toast(rs_f, rs_b, means3D=p["means3D"], opacities=p["opacities"],
+                                   colors_precomp=p["colors_precomp"], scales=p["scales"], rotations=p["rotations"])
+    dL = torch.randn((3, cfg["H"], cfg["W"]), generator=torch.Generator().manual_seed(2)).to(cuda_device)
+    grads = torch.autograd.grad(image, [p[k] for k in names], grad_outputs=dL)
+    outs, total = [], 0
+    for rs in (rs_f, rs_b):
+        m2d = torch.zeros_like(p["means3D"], requires_grad=True)
+        c, r, k = GaussianRasterizer(raster_settings=rs)(
+            means3D=p["means3D"], means2D=m2d, shs=None, colors_precomp=p["colors_precomp"], opacities=p["opacities"],
+            scales=p["scales"], rotations=p["rotations"], cov3D_precomp=None)
+        outs.append((c, r))
+        total += k
+    assert n == total
+    assert torch.equal(radii[0], outs[0][1]) and torch.equal(radii[1], outs[1][1])
+    ref = (outs[0][0] + torch.flip(outs[1][0], dims=(-1,))) / 2          # pipeline/train.py:366-375
+    assert (image - ref).abs().max() <= 2e-7
+    ref_grads = torch.autograd.grad(ref, [p[k] for k in names], grad_outputs=dL)
+    for k, a, b in zip(names, grads, ref_grads):
+        assert (a - b).abs().max() <= 2e-5 * b.abs().max(), k
+
+
+def test_config3_window_in_one_chain(cuda_device):
+    """BASELINE config 3: the 8-frame TSW window (16 views, 500k Gaussians) as ONE batched chain; per-view images
+    bit-identical to single calls for a sample of views, and the gradient of the window equals the frame-sharded
+    sum (ranks = frames) the multi-GPU path computes."""
+    from gsvc_b200.rasterizer import GaussianRasterizer
+    from gsvc_b200.views import ViewBatch, rasterize_views
+    cfg = CONFIGS[3]
+    f0 = cfg["F"] // 2
+    names = ("means3D", "colors_precomp", "opacities", "scales", "rotations")
+    _, g, _, _ = build(3, cuda_device, n_frames=cfg["window"])
+    p = {k: g[k].to(cuda_device).requires_grad_(True) for k in names}
+    settings = []
+    for f in range(f0, f0 + cfg["window"]):
+        settings.append(build(3, cuda_device, frame=f, n_frames=cfg["window"])[2])
+        settings.append(build(3, cuda_device, frame=f, n_frames=cfg["window"], back=True)[2])
+    V = len(settings)
+    images, radii, n = rasterize_views(ViewBatch(settings), means3D=p["means3D"], opacities=p["opacities"],
+                                       colors_precomp=p["colors_precomp"], scales=p["scales"], rotations=p["rotations"])
+    assert images.shape == (V, 3, cfg["H"], cfg["W"]) and radii.shape == (V, cfg["P"])
+    dL = torch.randn((V, 3, cfg["H"], cfg["W"]), generator=torch.Generator().manual_seed(3)).to(cuda_device)
+    grads = torch.autograd.grad(images, [p[k] for k in names], grad_outputs=dL)
+    sums, total = None, 0
+    for v, rs in enumerate(settings):
+        m2d = torch.zeros_like(p["means3D"], requires_grad=True)
+        c, r, k = GaussianRasterizer(raster_settings=rs)(
+            means3D=p["means3D"], means2D=m2d, shs=None, colors_precomp=p["colors_precomp"], opacities=p["opacities"],
+            scales=p["scales"], rotations=p["rotations"], cov3D_precomp=None)
+        total += k
+        if v in (0, 5, 15):
+            assert torch.equal(images[v], c) and torch.equal(radii[v], r)
+        gv = torch.autograd.grad(c, [p[k] for k in names], grad_outputs=dL[v])
+        sums = list(gv) if sums is None else [a + b for a, b in zip(sums, gv)]
+    assert n == total
+    for k, a, b in zip(names, grads, sums):
+        assert (a - b).abs().max() <= 5e-5 * b.abs().max(), k
