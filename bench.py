@@ -449,8 +449,27 @@ def run_product_arm(args, rank, local_rank, world):
             rast.visible_filter(means3D=ga["means3D"], scales=ga["scales"], rotations=ga["rotations"], cov3D_precomp=None)
         torch.cuda.synchronize(device)
         vf_ms = _lib.stage_times()["visible_filter"]
+        # row f2: the same filter fused with the compaction of the visible indices, against what the reference does
+        # next with the mask (radii > 0 -> nonzero, guassian.py:147-153)
+        for _ in range(20):
+            flush.zero_()
+            idx, _r = rast.visible_filter_compact(means3D=ga["means3D"], scales=ga["scales"], rotations=ga["rotations"])
+        torch.cuda.synchronize(device)
+        vfc_ms = _lib.stage_times()["visible_filter"]
         _lib.stage_timing(False)
-        vf = {"P_anchors": Pa, "ms": vf_ms, "algorithmic_bytes": 44 * Pa, "achieved_GBs": 44 * Pa / (vf_ms * 1e-3) / 1e9}
+        radii_a = rast.visible_filter(means3D=ga["means3D"], scales=ga["scales"], rotations=ga["rotations"], cov3D_precomp=None)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(device)
+        e0.record()
+        for _ in range(20):
+            nz = torch.nonzero(radii_a > 0)
+        e1.record()
+        torch.cuda.synchronize(device)
+        vf = {"P_anchors": Pa, "ms": vf_ms, "algorithmic_bytes": 44 * Pa, "achieved_GBs": 44 * Pa / (vf_ms * 1e-3) / 1e9,
+              "fused_compaction_ms": vfc_ms, "visible": int(idx.numel()),
+              "torch_mask_nonzero_ms": e0.elapsed_time(e1) / 20,
+              "note": "fused_compaction_ms = filter + ascending visible indices + count in ONE kernel (visible_filter_compact); "
+                      "torch_mask_nonzero_ms = what the mask costs the reference AFTER the filter (radii > 0, nonzero with its host sync)"}
         del ga
     clk = clocks.stop()
 

@@ -245,6 +245,33 @@ static int forward_launch_core(const gsvc_rast_settings* st, const DevSettings& 
     return 0;
 }
 
+size_t gsvc_rast_compact_scratch_bytes(int32_t P) { return compact_scratch_bytes(P); }
+
+int gsvc_rast_visible_filter_compact(const gsvc_rast_settings* st, int32_t P, const float* means3D, const float* scales,
+                                     const float* rotations, const float* cov3D_precomp, int32_t* radii,
+                                     int32_t* visible_indices, void* scratch, uint64_t* count_slot_host,
+                                     uint32_t ticket, void* stream_)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DevSettings d;
+    int rc = make_settings(st, 0, d);
+    if (rc) return rc;
+    rc = check_inputs(P, 0, 0, means3D, nullptr, nullptr, nullptr, scales, rotations, cov3D_precomp, false);
+    if (rc) return rc;
+    if (!scratch || (P > 0 && !visible_indices))
+        return fail(GSVC_RAST_ERR_INVALID, "visible_indices/scratch must be non-NULL");
+    const bool dbg = st->debug != 0;
+    PreInputs in{P, means3D, nullptr, nullptr, nullptr, scales, rotations, cov3D_precomp};
+    {
+        StageScope t(ST_VISIBLE_FILTER, stream);
+        CK(launch_visible_filter_compact(d, in, radii, visible_indices, scratch,
+                                         reinterpret_cast<unsigned long long*>(count_slot_host), ticket & 0xFFFFFFu,
+                                         stream),
+           "visible_filter_compact");
+    }
+    return 0;
+}
+
 int gsvc_rast_forward_launch(const gsvc_rast_settings* st, int32_t P, int32_t sh_M, const float* means3D,
                              const float* shs, const float* colors_precomp, const float* opacities,
                              const float* scales, const float* rotations, const float* cov3D_precomp, void* geom,

@@ -247,6 +247,11 @@ struct PreInputs {
 };
 
 cudaError_t launch_visible_filter(const DevSettings& s, const PreInputs& in, int32_t* radii, cudaStream_t st);
+// look-back scratch of the fused filter + compaction: [count | ticket counter | one word per 256-anchor CTA]
+inline size_t compact_scratch_bytes(int P) { return align_up(((size_t)(P < 1 ? 1 : P) / 256 + 4) * 8, 256); }
+cudaError_t launch_visible_filter_compact(const DevSettings& s, const PreInputs& in, int32_t* radii, int32_t* indices,
+                                          void* scratch, unsigned long long* host_slot, unsigned int ticket,
+                                          cudaStream_t st);
 cudaError_t launch_preprocess(const DevSettings& s, const PreInputs& in, int32_t* radii, GeomView g, ImageView im,
                               float4* acc_to_zero, cudaStream_t st);
 cudaError_t launch_tile_scan(const DevSettings& s, ImageView im, unsigned long long* host_slot, unsigned int ticket,

@@ -105,18 +105,88 @@ __device__ __forceinline__ void sh_to_rgb(int deg, const float* sh, const float 
     }
 }
 
-// FILTER = true: visible_filter (radii only).  FILTER = false: full preprocess + per-tile instance counting.
-template <bool FILTER>
+// Stable stream compaction of the visible anchors, fused into the filter kernel (what
+// `anchor[radii_pure > 0]` — a nonzero + a host synchronisation — does after prefilter_voxel, preprocess.py:99-108,
+// guassian.py:147-153).  Single pass, decoupled look-back: CTAs take a ticket (so logical order = scheduling
+// order), publish their visible count, and resolve their exclusive prefix from their predecessors' published
+// aggregates / inclusive prefixes.  state word: bits 63:62 = 0 invalid, 1 aggregate, 2 inclusive prefix.
+struct CompactOut {
+    int32_t* indices;                 // [P] ascending indices of the visible anchors (first `count` valid)
+    unsigned long long* state;        // [n_ctas + 1]: [0] = ticket counter, [1 + b] = look-back word of logical CTA b
+    unsigned long long* count_dev;    // device copy of the count (may be NULL)
+    unsigned long long* host_slot;    // pinned host word: ticket << 40 | count (may be NULL)
+    unsigned int ticket;
+};
+constexpr unsigned long long CPT_AGG = 1ull << 62, CPT_PREFIX = 2ull << 62, CPT_MASK = (1ull << 62) - 1;
+
+__device__ __forceinline__ void compact_visible(const CompactOut& co, int cta, int n_ctas, int g, bool vis)
+{
+    __shared__ unsigned int s_wsum[8];
+    __shared__ unsigned long long s_excl;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned int bal = __ballot_sync(0xffffffffu, vis);
+    if (lane == 0) s_wsum[wid] = __popc(bal);
+    __syncthreads();
+    unsigned int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        const unsigned int x = s_wsum[w];
+        if (w < wid) before += x;
+        total += x;
+    }
+    if (wid == 0) {
+        volatile unsigned long long* st = co.state + 1;
+        if (lane == 0) st[cta] = (cta == 0 ? CPT_PREFIX : CPT_AGG) | total;
+        unsigned long long excl = 0ull;
+        int look = cta - 1;
+        while (look >= 0) {                       // warp-wide look-back, 32 predecessors per round
+            const int idx = look - lane;
+            unsigned long long w = CPT_PREFIX;    // lanes before the first CTA: a zero inclusive prefix
+            if (idx >= 0) { do { w = st[idx]; } while ((w >> 62) == 0ull); }
+            const unsigned int has_prefix = __ballot_sync(0xffffffffu, (w >> 62) == 2ull);
+            const int stop = has_prefix ? __ffs(has_prefix) - 1 : 32;   // closest predecessor with an inclusive prefix
+            unsigned long long v = lane <= stop ? (w & CPT_MASK) : 0ull;
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+            excl += v;
+            if (has_prefix) break;
+            look -= 32;
+        }
+        if (lane == 0) {
+            if (cta > 0) st[cta] = CPT_PREFIX | (excl + total);
+            s_excl = excl;
+            if (cta == n_ctas - 1) {
+                const unsigned long long cnt = excl + total;
+                if (co.count_dev) *co.count_dev = cnt;
+                if (co.host_slot) *co.host_slot = ((unsigned long long)co.ticket << 40) | cnt;
+            }
+        }
+    }
+    __syncthreads();
+    if (vis) co.indices[s_excl + before + __popc(bal & ((1u << lane) - 1u))] = g;
+}
+
+// MODE 0: full preprocess + per-tile instance counting.  MODE 1: visible_filter (radii only).
+// MODE 2: visible_filter + stable compaction of the visible indices.
+template <int MODE>
 __global__ void __launch_bounds__(256) preprocess_kernel(DevSettings s, PreInputs in, int32_t* __restrict__ radii,
                                                          GeomView geo, unsigned int* __restrict__ tile_count,
-                                                         float4* __restrict__ acc_to_zero)
+                                                         float4* __restrict__ acc_to_zero, CompactOut co)
 {
+    constexpr bool FILTER = MODE != 0;
     pdl_prologue();
     // Lanes past the end stay in the warp (they redo the last Gaussian with all stores masked) so that the
-    // warp-wide tile walk at the end runs converged.
-    const int g_raw = blockIdx.x * blockDim.x + threadIdx.x;
+    // warp-wide tile walk at the end (and the block-wide compaction) runs converged.
+    __shared__ int s_cta;
+    int cta = blockIdx.x;
+    if (MODE == 2) {                              // logical CTA index = ticket: look-back never waits on a later CTA
+        if (threadIdx.x == 0) s_cta = (int)atomicAdd(co.state, 1ull);
+        __syncthreads();
+        cta = s_cta;
+    }
+    const int g_raw = cta * blockDim.x + threadIdx.x;
     const bool valid = g_raw < in.P;
-    if (FILTER && !valid) return;
+    if (MODE == 1 && !valid) return;
     const int g = valid ? g_raw : in.P - 1;
     // view of the batch (grid.y): per-Gaussian state of view v lives at virtual index v*P + g, its tiles at v*Tv + t
     const int v = FILTER ? 0 : (int)blockIdx.y;
@@ -174,7 +244,8 @@ __global__ void __launch_bounds__(256) preprocess_kernel(DevSettings s, PreInput
         rmaxy = (int)fminf(fgy, fmaxf(0.f, truncf((py + rad_f + (float)(TILE - 1)) / ft)));
         ok = (rmaxx - rminx) * (rmaxy - rminy) > 0;
     }
-    if (valid) radii[gv] = ok ? radius : 0;
+    if (valid && radii) radii[gv] = ok ? radius : 0;
+    if (MODE == 2) compact_visible(co, cta, (int)gridDim.x, g, ok);
     if (FILTER) return;
 
     if (ok) {
@@ -224,8 +295,31 @@ cudaError_t launch_visible_filter(const DevSettings& s, const PreInputs& in, int
     if (in.P <= 0) return cudaSuccess;
     GeomView none{};
     count_launch();
-    return launch_pdl(preprocess_kernel<true>, dim3((in.P + 255) / 256), dim3(256), st, s, in, radii, none,
-                      (unsigned int*)nullptr, (float4*)nullptr);
+    return launch_pdl(preprocess_kernel<1>, dim3((in.P + 255) / 256), dim3(256), st, s, in, radii, none,
+                      (unsigned int*)nullptr, (float4*)nullptr, CompactOut{});
+}
+
+cudaError_t launch_visible_filter_compact(const DevSettings& s, const PreInputs& in, int32_t* radii, int32_t* indices,
+                                          void* scratch, unsigned long long* host_slot, unsigned int ticket,
+                                          cudaStream_t st)
+{
+    const int n_ctas = (in.P + 255) / 256;
+    CompactOut co;
+    co.indices = indices;
+    co.state = static_cast<unsigned long long*>(scratch) + 1;      // [0] of scratch = device copy of the count
+    co.count_dev = static_cast<unsigned long long*>(scratch);
+    co.host_slot = host_slot;
+    co.ticket = ticket;
+    cudaError_t e = cudaMemsetAsync(scratch, 0, compact_scratch_bytes(in.P), st);
+    if (e != cudaSuccess) return e;
+    if (in.P <= 0) {
+        if (host_slot) *host_slot = (unsigned long long)ticket << 40;   // pinned HOST memory: count 0, no launch
+        return cudaSuccess;
+    }
+    GeomView none{};
+    count_launch();
+    return launch_pdl(preprocess_kernel<2>, dim3(n_ctas), dim3(256), st, s, in, radii, none, (unsigned int*)nullptr,
+                      (float4*)nullptr, co);
 }
 
 cudaError_t launch_preprocess(const DevSettings& s, const PreInputs& in, int32_t* radii, GeomView g, ImageView im,
@@ -238,8 +332,8 @@ cudaError_t launch_preprocess(const DevSettings& s, const PreInputs& in, int32_t
     if (e != cudaSuccess) return e;
     if (in.P <= 0) return cudaSuccess;
     count_launch();
-    return launch_pdl(preprocess_kernel<false>, dim3((in.P + 255) / 256, s.n_views), dim3(256), st, s, in, radii, g,
-                      im.tile_count, acc_to_zero);
+    return launch_pdl(preprocess_kernel<0>, dim3((in.P + 255) / 256, s.n_views), dim3(256), st, s, in, radii, g,
+                      im.tile_count, acc_to_zero, CompactOut{});
 }
 
 }  // namespace gsvc

@@ -325,6 +325,38 @@ class GaussianRasterizer(nn.Module):
                                                   _stream_ptr(device)), "gsvc_rast_visible_filter")
         return radii
 
+    def visible_filter_compact(self, means3D, scales=None, rotations=None, cov3D_precomp=None, want_radii=True):
+        """visible_filter fused with the compaction its caller does next.
+
+        prefilter_voxel returns `radii_pure > 0` (preprocess.py:108) and generate_neural_gaussians indexes every
+        per-anchor tensor with that mask (guassian.py:147-153): a nonzero pass and a host synchronisation.  Here
+        the same kernel also writes the ascending indices of the visible anchors and publishes their count to
+        pinned memory, so the caller gets `idx` (int32, == nonzero(radii > 0)) without synchronising the stream and
+        gathers with `anchor.index_select(0, idx)` / `anchor[idx]`.  Returns (idx [count], radii [P] or None)."""
+        rs = self.raster_settings
+        if (scales is None or rotations is None) == (cov3D_precomp is None):
+            raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
+        L = _lib.lib()
+        _require_cuda(means3D, "means3D")
+        device = means3D.device
+        with torch.no_grad(), torch.cuda.device(device):
+            ns = _NativeSettings(rs, device)
+            P = int(means3D.shape[0])
+            m = _dev_f32(means3D, device, "means3D")
+            s = _dev_f32(scales, device, "scales")
+            r = _dev_f32(rotations, device, "rotations")
+            c = _dev_f32(cov3D_precomp, device, "cov3D_precomp")
+            radii = torch.empty((P,), dtype=torch.int32, device=device) if want_radii else None
+            idx = torch.empty((P,), dtype=torch.int32, device=device)
+            scratch = _bytes(L.gsvc_rast_compact_scratch_bytes(P), device)
+            stream = _stream_ptr(device)
+            slot, ticket = _count_slot()
+            _lib.check(L.gsvc_rast_visible_filter_compact(ns.ref, P, _ptr(m), _ptr(s), _ptr(r), _ptr(c), _ptr(radii),
+                                                          _ptr(idx), scratch.data_ptr(), slot, ticket, stream),
+                       "gsvc_rast_visible_filter_compact")
+            count = _lib.check(L.gsvc_rast_wait_count(slot, ticket, stream), "gsvc_rast_wait_count")
+        return idx[:count], radii
+
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
                 cov3D_precomp=None):
         rs = self.raster_settings

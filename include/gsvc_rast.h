@@ -86,6 +86,22 @@ GSVC_RAST_API int gsvc_rast_visible_filter(const gsvc_rast_settings *st, int32_t
                              const float *rotations, const float *cov3D_precomp, int32_t *radii, void *stream);
 
 /*
+ * visible_filter fused with the compaction its caller does next: prefilter_voxel returns
+ * `radii_pure > 0` (preprocess.py:108) and generate_neural_gaussians indexes every per-anchor tensor with that
+ * boolean mask (guassian.py:147-153) — a nonzero pass plus a host synchronisation.  This entry point writes the
+ * ascending indices of the visible anchors (exactly nonzero's order) in the same kernel, single pass, and
+ * publishes their count to `count_slot_host` with the ticket protocol of gsvc_rast_forward_launch (read it with
+ * gsvc_rast_wait_count: no stream synchronisation).  radii may be NULL.  visible_indices [P] int32 (first `count`
+ * entries valid).  scratch: gsvc_rast_compact_scratch_bytes(P) bytes; its first 64-bit word holds the count on
+ * the device afterwards.
+ */
+GSVC_RAST_API size_t gsvc_rast_compact_scratch_bytes(int32_t P);
+GSVC_RAST_API int gsvc_rast_visible_filter_compact(const gsvc_rast_settings *st, int32_t P, const float *means3D,
+                             const float *scales, const float *rotations, const float *cov3D_precomp, int32_t *radii,
+                             int32_t *visible_indices, void *scratch, uint64_t *count_slot_host, uint32_t ticket,
+                             void *stream);
+
+/*
  * Forward, launch form (no host synchronisation): preprocess → tile counting → tile scan →
  * instance scatter → per-tile depth sort → front-to-back blend, all enqueued on `stream`.
  * Exactly one of shs ([P,sh_M,3]) / colors_precomp ([P,3]); exactly one of (scales,rotations) /

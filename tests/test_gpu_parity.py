@@ -473,3 +473,27 @@ def test_graphed_step_matches_eager(cuda_device):
         assert torch.equal(radii_g, radii) and torch.equal(radii_f, radii)
         ref = torch.cat([x.reshape(P, -1) for x in grads], dim=1)
         assert (packed - ref).abs().max() <= 1e-5 * ref.abs().max()
+
+
+@pytest.mark.parametrize("P", [1, 255, 256, 257, 50000, 300001])
+def test_visible_filter_compact_equals_nonzero(cuda_device, P):
+    """the fused filter + compaction returns exactly nonzero(radii > 0) (ascending indices,
+    same radii as visible_filter and the oracle), for sizes around the 256-anchor CTA boundary and many CTAs."""
+    from gsvc_b200.rasterizer import GaussianRasterizer
+    scene = make_scene(P=P, W=320, H=192, F=320, seed=13)
+    g = _to_dev(scene["gaussians"], cuda_device)
+    rast = GaussianRasterizer(raster_settings=product_settings(scene, cuda_device))
+    ref = rast.visible_filter(means3D=g["means3D"], scales=g["scales"], rotations=g["rotations"], cov3D_precomp=None)
+    for _ in range(3):   # repeated calls reuse the pinned slot with a new ticket
+        idx, radii = rast.visible_filter_compact(means3D=g["means3D"], scales=g["scales"], rotations=g["rotations"])
+        assert idx.dtype == torch.int32 and torch.equal(radii, ref)
+        assert torch.equal(idx.long(), torch.nonzero(ref > 0).flatten())
+    idx2, none = rast.visible_filter_compact(means3D=g["means3D"], scales=g["scales"], rotations=g["rotations"],
+                                             want_radii=False)
+    assert none is None and torch.equal(idx2, idx)
+    if P >= 50000:
+        gi = np_inputs(scene["gaussians"])
+        oracle = c_oracle.visible_filter(scene["oracle_settings"], gi["means3D"], gi["scales"], gi["rotations"])
+        np.testing.assert_array_equal(idx.cpu().numpy(), np.nonzero(oracle > 0)[0].astype(np.int32))
+        # the gather the reference does with the boolean mask (guassian.py:147-153)
+        assert torch.equal(g["means3D"][idx.long()], g["means3D"][ref > 0])
