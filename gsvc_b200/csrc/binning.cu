@@ -165,7 +165,8 @@ cudaError_t launch_scatter(const DevSettings& s, int P, GeomView g, ImageView im
 // in global memory beyond).
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
-constexpr int SORT_WARP_ITEMS = 256;   // 8 registers of 64 bits per lane
+constexpr int SORT_WARP_ITEMS = 256;   // 8 registers of 64 bits per lane (the kernel tuned for typical buckets)
+constexpr int SORT_WARP_ITEMS_BIG = 512;  // 16 registers per lane (the kernel tuned for dense scenes: more registers, fewer warps)
 constexpr int SORT_SMEM_ITEMS = 2048;  // 16 KB
 
 template <bool BLOCK, typename Ptr>
@@ -206,7 +207,7 @@ __device__ __forceinline__ void bitonic_sort(Ptr a, int n, int tid, int nthreads
 template <int R, int M, int DB>
 __device__ __forceinline__ void bitonic_step(unsigned long long (&v)[R], int lane)
 {
-    constexpr int LR = R == 1 ? 0 : R == 2 ? 1 : R == 4 ? 2 : 3;
+    constexpr int LR = R == 1 ? 0 : R == 2 ? 1 : R == 4 ? 2 : R == 8 ? 3 : 4;
     constexpr int mr = M & (R - 1), ml = M >> LR;
     unsigned long long nv[R];
 #pragma unroll
@@ -268,9 +269,14 @@ __device__ __forceinline__ void sort_bucket_regs(const unsigned long long* __res
     }
 }
 
+// BIG = false: buckets up to 256 entries in registers (32 registers per thread, 8 CTAs per SM) — the common case.
+// BIG = true: up to 512 (dense scenes, e.g. 1 M Gaussians at 1080p = ~360 per tile); chosen by the launcher from
+// the expected bucket size.  Either kernel sorts any bucket correctly (CTA-wide fallbacks beyond its register path).
+template <bool BIG>
 __global__ void __launch_bounds__(SORT_THREADS) sort_tiles_kernel(int T, ImageView im, BinView bin,
                                                                   unsigned long long cap)
 {
+    constexpr int WARP_ITEMS = BIG ? SORT_WARP_ITEMS_BIG : SORT_WARP_ITEMS;
     __shared__ unsigned long long s_items[SORT_SMEM_ITEMS];
     __shared__ int s_big[SORT_WARPS];
     pdl_prologue();
@@ -282,7 +288,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_tiles_kernel(int T, ImageVi
         rg = im.ranges[t];
         n = (unsigned long long)rg.y > cap ? 0 : (int)(rg.y - rg.x);
     }
-    const bool big = n > SORT_WARP_ITEMS;
+    const bool big = n > WARP_ITEMS;
     if (lane == 0) s_big[warp] = big ? t : -1;
     if (!big && n > 0) {
         const unsigned long long* src = bin.inst + rg.x;
@@ -291,7 +297,8 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_tiles_kernel(int T, ImageVi
         if (n <= 32) sort_bucket_regs<1, 5>(src, n, lane, ids, keys);
         else if (n <= 64) sort_bucket_regs<2, 6>(src, n, lane, ids, keys);
         else if (n <= 128) sort_bucket_regs<4, 7>(src, n, lane, ids, keys);
-        else sort_bucket_regs<8, 8>(src, n, lane, ids, keys);
+        else if (!BIG || n <= 256) sort_bucket_regs<8, 8>(src, n, lane, ids, keys);
+        else sort_bucket_regs<16, 9>(src, n, lane, ids, keys);
     }
     __syncthreads();
     for (int w = 0; w < SORT_WARPS; w++) {
@@ -326,8 +333,10 @@ cudaError_t launch_sort_tiles(const DevSettings& s, ImageView im, BinView b, lon
     const int T = s.gx * s.gy * s.n_views;
     if (T <= 0) return cudaSuccess;
     count_launch();
-    return launch_pdl(sort_tiles_kernel, dim3((T + SORT_WARPS - 1) / SORT_WARPS), dim3(SORT_THREADS), st, T, im, b,
-                      (unsigned long long)cap);
+    // expected bucket size from the instance capacity (1.25 x the last num_rendered seen for this shape)
+    const bool dense = cap / T > 160;
+    return launch_pdl(dense ? sort_tiles_kernel<true> : sort_tiles_kernel<false>, dim3((T + SORT_WARPS - 1) / SORT_WARPS),
+                      dim3(SORT_THREADS), st, T, im, b, (unsigned long long)cap);
 }
 
 // ---- export for the bit-exact stage tests --------------------------------------------------------
