@@ -247,8 +247,12 @@ struct PreInputs {
 };
 
 cudaError_t launch_visible_filter(const DevSettings& s, const PreInputs& in, int32_t* radii, cudaStream_t st);
-// look-back scratch of the fused filter + compaction: [count | ticket counter | one word per 256-anchor CTA]
-inline size_t compact_scratch_bytes(int P) { return align_up(((size_t)(P < 1 ? 1 : P) / 256 + 4) * 8, 256); }
+// scratch of the filter + compaction: [count | visible count per 256-anchor CTA | CTA offsets | one ballot word per warp]
+inline size_t compact_scratch_bytes(int P)
+{
+    const size_t n = ((size_t)(P < 1 ? 1 : P) + 255) / 256;
+    return 256 + 2 * align_up(n * 4, 256) + align_up(n * 32, 256) + 256;
+}
 cudaError_t launch_visible_filter_compact(const DevSettings& s, const PreInputs& in, int32_t* radii, int32_t* indices,
                                           void* scratch, unsigned long long* host_slot, unsigned int ticket,
                                           cudaStream_t st);

@@ -105,65 +105,80 @@ __device__ __forceinline__ void sh_to_rgb(int deg, const float* sh, const float 
     }
 }
 
-// Stable stream compaction of the visible anchors, fused into the filter kernel (what
-// `anchor[radii_pure > 0]` — a nonzero + a host synchronisation — does after prefilter_voxel, preprocess.py:99-108,
-// guassian.py:147-153).  Single pass, decoupled look-back: CTAs take a ticket (so logical order = scheduling
-// order), publish their visible count, and resolve their exclusive prefix from their predecessors' published
-// aggregates / inclusive prefixes.  state word: bits 63:62 = 0 invalid, 1 aggregate, 2 inclusive prefix.
+// Stable stream compaction of the visible anchors (what `anchor[radii_pure > 0]` — a nonzero
+// pass + a host synchronisation — does after prefilter_voxel, preprocess.py:99-108, guassian.py:147-153).
+// Reduce-then-scan, no spinning: the filter kernel (MODE 2) also writes one ballot word per warp and one visible
+// count per 256-anchor CTA; a single-CTA kernel scans the CTA counts and publishes the total; a write kernel turns
+// ballots + CTA offsets into ascending indices.  (A single-pass decoupled look-back was built first and measured
+// 2-3x slower than the filter itself: with one 256-anchor CTA per look-back word, ~1200 concurrently started CTAs
+// spin on each other through L2 — profiles/r1_notes.md.)
 struct CompactOut {
-    int32_t* indices;                 // [P] ascending indices of the visible anchors (first `count` valid)
-    unsigned long long* state;        // [n_ctas + 1]: [0] = ticket counter, [1 + b] = look-back word of logical CTA b
-    unsigned long long* count_dev;    // device copy of the count (may be NULL)
-    unsigned long long* host_slot;    // pinned host word: ticket << 40 | count (may be NULL)
-    unsigned int ticket;
+    unsigned int* ballots;            // [ceil(P/32)] visibility bits, one word per warp
+    unsigned int* cta_count;          // [n_ctas] visible anchors per 256-anchor CTA
 };
-constexpr unsigned long long CPT_AGG = 1ull << 62, CPT_PREFIX = 2ull << 62, CPT_MASK = (1ull << 62) - 1;
 
-__device__ __forceinline__ void compact_visible(const CompactOut& co, int cta, int n_ctas, int g, bool vis)
+__global__ void __launch_bounds__(1024) compact_scan_kernel(int n_ctas, const unsigned int* __restrict__ cta_count,
+                                                            unsigned int* __restrict__ cta_offset,
+                                                            unsigned long long* count_dev,
+                                                            unsigned long long* host_slot, unsigned int ticket)
+{
+    __shared__ unsigned int s_warp[32];
+    __shared__ unsigned int s_carry;
+    pdl_prologue();
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_carry = 0u;
+    __syncthreads();
+    for (int base = 0; base < n_ctas; base += 1024) {
+        const int i = base + tid;
+        const unsigned int c = i < n_ctas ? cta_count[i] : 0u;
+        unsigned int v = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned int o = __shfl_up_sync(0xffffffffu, v, d);
+            if (lane >= d) v += o;
+        }
+        if (lane == 31) s_warp[wid] = v;
+        __syncthreads();
+        if (wid == 0) {
+            unsigned int w = s_warp[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned int o = __shfl_up_sync(0xffffffffu, w, d);
+                if (lane >= d) w += o;
+            }
+            s_warp[lane] = w;   // inclusive over warps
+        }
+        __syncthreads();
+        const unsigned int carry = s_carry;
+        if (i < n_ctas) cta_offset[i] = carry + (wid ? s_warp[wid - 1] : 0u) + v - c;
+        __syncthreads();
+        if (tid == 0) s_carry = carry + s_warp[31];
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const unsigned long long cnt = s_carry;
+        if (count_dev) *count_dev = cnt;
+        if (host_slot) *host_slot = ((unsigned long long)ticket << 40) | cnt;
+    }
+}
+
+__global__ void __launch_bounds__(256) compact_write_kernel(int P, const unsigned int* __restrict__ ballots,
+                                                            const unsigned int* __restrict__ cta_offset,
+                                                            int32_t* __restrict__ indices)
 {
     __shared__ unsigned int s_wsum[8];
-    __shared__ unsigned long long s_excl;
+    pdl_prologue();
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const unsigned int bal = __ballot_sync(0xffffffffu, vis);
+    const int g = blockIdx.x * 256 + tid;
+    const int word = blockIdx.x * 8 + wid;
+    const unsigned int bal = word * 32 < P ? ballots[word] : 0u;
     if (lane == 0) s_wsum[wid] = __popc(bal);
     __syncthreads();
-    unsigned int before = 0, total = 0;
+    unsigned int before = cta_offset[blockIdx.x];
 #pragma unroll
-    for (int w = 0; w < 8; w++) {
-        const unsigned int x = s_wsum[w];
-        if (w < wid) before += x;
-        total += x;
-    }
-    if (wid == 0) {
-        volatile unsigned long long* st = co.state + 1;
-        if (lane == 0) st[cta] = (cta == 0 ? CPT_PREFIX : CPT_AGG) | total;
-        unsigned long long excl = 0ull;
-        int look = cta - 1;
-        while (look >= 0) {                       // warp-wide look-back, 32 predecessors per round
-            const int idx = look - lane;
-            unsigned long long w = CPT_PREFIX;    // lanes before the first CTA: a zero inclusive prefix
-            if (idx >= 0) { do { w = st[idx]; } while ((w >> 62) == 0ull); }
-            const unsigned int has_prefix = __ballot_sync(0xffffffffu, (w >> 62) == 2ull);
-            const int stop = has_prefix ? __ffs(has_prefix) - 1 : 32;   // closest predecessor with an inclusive prefix
-            unsigned long long v = lane <= stop ? (w & CPT_MASK) : 0ull;
-#pragma unroll
-            for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-            excl += v;
-            if (has_prefix) break;
-            look -= 32;
-        }
-        if (lane == 0) {
-            if (cta > 0) st[cta] = CPT_PREFIX | (excl + total);
-            s_excl = excl;
-            if (cta == n_ctas - 1) {
-                const unsigned long long cnt = excl + total;
-                if (co.count_dev) *co.count_dev = cnt;
-                if (co.host_slot) *co.host_slot = ((unsigned long long)co.ticket << 40) | cnt;
-            }
-        }
-    }
-    __syncthreads();
-    if (vis) co.indices[s_excl + before + __popc(bal & ((1u << lane) - 1u))] = g;
+    for (int w = 0; w < 8; w++)
+        if (w < wid) before += s_wsum[w];
+    if ((bal >> lane) & 1u) indices[before + __popc(bal & ((1u << lane) - 1u))] = g;
 }
 
 // MODE 0: full preprocess + per-tile instance counting.  MODE 1: visible_filter (radii only).
@@ -177,16 +192,8 @@ __global__ void __launch_bounds__(256) preprocess_kernel(DevSettings s, PreInput
     pdl_prologue();
     // Lanes past the end stay in the warp (they redo the last Gaussian with all stores masked) so that the
     // warp-wide tile walk at the end (and the block-wide compaction) runs converged.
-    __shared__ int s_cta;
-    int cta = blockIdx.x;
-    if (MODE == 2) {                              // logical CTA index = ticket: look-back never waits on a later CTA
-        if (threadIdx.x == 0) s_cta = (int)atomicAdd(co.state, 1ull);
-        __syncthreads();
-        cta = s_cta;
-    }
-    const int g_raw = cta * blockDim.x + threadIdx.x;
+    const int g_raw = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = g_raw < in.P;
-    if (MODE == 1 && !valid) return;
     const int g = valid ? g_raw : in.P - 1;
     // view of the batch (grid.y): per-Gaussian state of view v lives at virtual index v*P + g, its tiles at v*Tv + t
     const int v = FILTER ? 0 : (int)blockIdx.y;
@@ -207,11 +214,17 @@ __global__ void __launch_bounds__(256) preprocess_kernel(DevSettings s, PreInput
         sc[0] = __ldg(in.scales + 3 * g); sc[1] = __ldg(in.scales + 3 * g + 1); sc[2] = __ldg(in.scales + 3 * g + 2);
         q_pre = __ldg(reinterpret_cast<const float4*>(in.rotations) + g);
     }
-    const float w0[3] = {ldV(s, v, 0, 0), ldV(s, v, 0, 1), ldV(s, v, 0, 2)};
-    const float w1[3] = {ldV(s, v, 1, 0), ldV(s, v, 1, 1), ldV(s, v, 1, 2)};
-    const float vx = w0[0] * p[0] + w0[1] * p[1] + w0[2] * p[2] + ldV(s, v, 0, 3);
-    const float vy = w1[0] * p[0] + w1[1] * p[1] + w1[2] * p[2] + ldV(s, v, 1, 3);
-    const float vz = ldV(s, v, 2, 0) * p[0] + ldV(s, v, 2, 1) * p[1] + ldV(s, v, 2, 2) * p[2] + ldV(s, v, 2, 3);
+    // The CTA's view matrix (strided device tensor: 12 loads + 64-bit stride arithmetic per thread otherwise) is
+    // fetched once by 12 threads and broadcast through shared memory; the Gaussian's own loads above are already
+    // in flight when the barrier is reached.
+    __shared__ float s_V[12];
+    if (threadIdx.x < 12) s_V[threadIdx.x] = ldV(s, v, threadIdx.x >> 2, threadIdx.x & 3);
+    __syncthreads();
+    const float w0[3] = {s_V[0], s_V[1], s_V[2]};
+    const float w1[3] = {s_V[4], s_V[5], s_V[6]};
+    const float vx = w0[0] * p[0] + w0[1] * p[1] + w0[2] * p[2] + s_V[3];
+    const float vy = w1[0] * p[0] + w1[1] * p[1] + w1[2] * p[2] + s_V[7];
+    const float vz = s_V[8] * p[0] + s_V[9] * p[1] + s_V[10] * p[2] + s_V[11];
 
     int radius = 0;
     int rminx = 0, rminy = 0, rmaxx = 0, rmaxy = 0;
@@ -245,7 +258,21 @@ __global__ void __launch_bounds__(256) preprocess_kernel(DevSettings s, PreInput
         ok = (rmaxx - rminx) * (rmaxy - rminy) > 0;
     }
     if (valid && radii) radii[gv] = ok ? radius : 0;
-    if (MODE == 2) compact_visible(co, cta, (int)gridDim.x, g, ok);
+    if (MODE == 2) {
+        __shared__ unsigned int s_vis[8];
+        const unsigned int bal = __ballot_sync(0xffffffffu, ok);
+        if ((threadIdx.x & 31) == 0) {
+            co.ballots[g_raw >> 5] = bal;
+            s_vis[threadIdx.x >> 5] = __popc(bal);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned int tot = 0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) tot += s_vis[w];
+            co.cta_count[blockIdx.x] = tot;
+        }
+    }
     if (FILTER) return;
 
     if (ok) {
@@ -303,23 +330,28 @@ cudaError_t launch_visible_filter_compact(const DevSettings& s, const PreInputs&
                                           void* scratch, unsigned long long* host_slot, unsigned int ticket,
                                           cudaStream_t st)
 {
-    const int n_ctas = (in.P + 255) / 256;
-    CompactOut co;
-    co.indices = indices;
-    co.state = static_cast<unsigned long long*>(scratch) + 1;      // [0] of scratch = device copy of the count
-    co.count_dev = static_cast<unsigned long long*>(scratch);
-    co.host_slot = host_slot;
-    co.ticket = ticket;
-    cudaError_t e = cudaMemsetAsync(scratch, 0, compact_scratch_bytes(in.P), st);
-    if (e != cudaSuccess) return e;
     if (in.P <= 0) {
         if (host_slot) *host_slot = (unsigned long long)ticket << 40;   // pinned HOST memory: count 0, no launch
         return cudaSuccess;
     }
+    // scratch: [count (8 B, 256-aligned) | CTA counts | CTA offsets | ballot words]
+    const int n_ctas = (in.P + 255) / 256;
+    char* p = static_cast<char*>(scratch);
+    unsigned long long* count_dev = carve<unsigned long long>(p, 1);
+    unsigned int* cta_count = carve<unsigned int>(p, n_ctas);
+    unsigned int* cta_offset = carve<unsigned int>(p, n_ctas);
+    unsigned int* ballots = carve<unsigned int>(p, (size_t)n_ctas * 8);
+    CompactOut co{ballots, cta_count};
     GeomView none{};
-    count_launch();
-    return launch_pdl(preprocess_kernel<2>, dim3(n_ctas), dim3(256), st, s, in, radii, none, (unsigned int*)nullptr,
-                      (float4*)nullptr, co);
+    count_launch(3);
+    cudaError_t e = launch_pdl(preprocess_kernel<2>, dim3(n_ctas), dim3(256), st, s, in, radii, none,
+                               (unsigned int*)nullptr, (float4*)nullptr, co);
+    if (e != cudaSuccess) return e;
+    e = launch_pdl(compact_scan_kernel, dim3(1), dim3(1024), st, n_ctas, (const unsigned int*)cta_count, cta_offset,
+                   count_dev, host_slot, ticket);
+    if (e != cudaSuccess) return e;
+    return launch_pdl(compact_write_kernel, dim3(n_ctas), dim3(256), st, in.P, (const unsigned int*)ballots,
+                      (const unsigned int*)cta_offset, indices);
 }
 
 cudaError_t launch_preprocess(const DevSettings& s, const PreInputs& in, int32_t* radii, GeomView g, ImageView im,

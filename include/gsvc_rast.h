@@ -89,7 +89,8 @@ GSVC_RAST_API int gsvc_rast_visible_filter(const gsvc_rast_settings *st, int32_t
  * visible_filter fused with the compaction its caller does next: prefilter_voxel returns
  * `radii_pure > 0` (preprocess.py:108) and generate_neural_gaussians indexes every per-anchor tensor with that
  * boolean mask (guassian.py:147-153) — a nonzero pass plus a host synchronisation.  This entry point writes the
- * ascending indices of the visible anchors (exactly nonzero's order) in the same kernel, single pass, and
+ * ascending indices of the visible anchors (exactly nonzero's order): the filter kernel leaves one ballot word per
+ * warp and one count per CTA, a single-CTA scan and a write kernel finish the job (no spinning, deterministic), and
  * publishes their count to `count_slot_host` with the ticket protocol of gsvc_rast_forward_launch (read it with
  * gsvc_rast_wait_count: no stream synchronisation).  radii may be NULL.  visible_indices [P] int32 (first `count`
  * entries valid).  scratch: gsvc_rast_compact_scratch_bytes(P) bytes; its first 64-bit word holds the count on
