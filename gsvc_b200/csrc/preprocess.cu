@@ -198,13 +198,6 @@ __global__ void __launch_bounds__(256) preprocess_kernel(DevSettings s, PreInput
     // view of the batch (grid.y): per-Gaussian state of view v lives at virtual index v*P + g, its tiles at v*Tv + t
     const int v = FILTER ? 0 : (int)blockIdx.y;
     const size_t gv = (size_t)v * in.P + g;
-    if (!FILTER && acc_to_zero && valid) {
-        // the blend backward accumulates into these 9 sums with atomics: zero them here (a store the
-        // stream kernel hides) instead of a separate memset launch in the backward
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        acc_to_zero[3 * gv] = z; acc_to_zero[3 * gv + 1] = z; acc_to_zero[3 * gv + 2] = z;
-    }
-
     const float p[3] = {__ldg(in.means3D + 3 * g), __ldg(in.means3D + 3 * g + 1), __ldg(in.means3D + 3 * g + 2)};
     // scales / quaternion are fetched together with the position (one memory round trip per Gaussian, at the
     // price of 28 wasted bytes for the third of the Gaussians the slab test culls)
@@ -291,6 +284,12 @@ __global__ void __launch_bounds__(256) preprocess_kernel(DevSettings s, PreInput
             geo.clamped[3 * gv] = cl[0];
             geo.clamped[3 * gv + 1] = cl[1];
             geo.clamped[3 * gv + 2] = cl[2];
+        }
+        if (acc_to_zero) {
+            // the blend backward accumulates into these 9 sums with atomics: zero them here (stores this kernel
+            // hides) instead of a memset launch in the backward — visible Gaussians only, nobody reads the others
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            acc_to_zero[3 * gv] = z; acc_to_zero[3 * gv + 1] = z; acc_to_zero[3 * gv + 2] = z;
         }
         geo.feat0[gv] = make_float4(px, py, 0.f, 0.f);   // .zw: scratch of the blend kernels' staging (B/A, B/C)
         geo.feat1[gv] = make_float4(cA, cB, cC, op);

@@ -115,8 +115,8 @@ GSVC_RAST_API int gsvc_rast_visible_filter_compact(const gsvc_rast_settings *st,
  * The caller MUST check num_rendered <= capacity; if not, out_color is invalid and
  * gsvc_rast_forward_render must be re-run with a larger binning buffer (geom/image stay valid).
  * `bwd_scratch` (optional): gsvc_rast_backward_scratch_bytes(P) bytes that a later gsvc_rast_backward will
- * use; the preprocess kernel zeroes them on the fly, which saves the backward a memset launch
- * (pass scratch_is_zero = 1 there).
+ * use; the preprocess kernel zeroes the entries of the visible Gaussians on the fly (nobody reads the others),
+ * which saves the backward a memset launch (pass scratch_is_zero = 1 there).
  * Outputs: out_color [3,H,W], radii [P].
  * All kernels of the chain are launched with programmatic dependent launch (their launch latency and
  * prologue overlap the predecessor's tail).
