@@ -385,6 +385,23 @@ def run_product_arm(args, rank, local_rank, world):
         if w is not None:
             w.wait()
 
+    # ---- the reference's own FPS convention (utils/report_utils.py:297-319): per frame, synchronize, time.time(),
+    # render front, render back, flip, average, clamp, synchronize — here the two renders are one render_toast call
+    from gsvc_b200.views import render_toast
+    ref_style = []
+    with torch.no_grad():
+        for i in range(args.steps + 5):
+            torch.cuda.synchronize(device)
+            t0 = time.perf_counter()
+            img, _, _ = render_toast(front, back, means3D=params["means3D"], opacities=params["opacities"],
+                                     colors_precomp=params["colors_precomp"], scales=params["scales"],
+                                     rotations=params["rotations"])
+            img = torch.clamp(img, min=0, max=1.0)
+            torch.cuda.synchronize(device)
+            if i >= 5:
+                ref_style.append(time.perf_counter() - t0)
+    ref_style_fps = 1.0 / statistics.median(ref_style)
+
     # ---- end to end through the public API with HOST buffers (gsvc_b200.hostpipe.HostStepPipeline): every step
     # copies its inputs (all Gaussian parameters, one [14*P] pinned buffer) from host memory and reads its result
     # (the packed [P,14] parameter gradients a host optimizer consumes) back to pinned host memory, inside the
@@ -519,6 +536,10 @@ def run_product_arm(args, rank, local_rank, world):
             "fwd_frames_per_s": per_s(fwd_ms, 1),
             "fwd_ms_per_frame": fwd_ms / args.steps,
             "ref_iterations_per_s": per_s(total_ms, 1) / 2.0,
+            "ref_style_eval_fps": {"value": ref_style_fps, "unit": "frames/s per GPU",
+                                   "note": "the reference's evaluate() convention (utils/report_utils.py:297-319): wall "
+                                           "clock around synchronize / 2 views + flip + average + clamp / synchronize, "
+                                           "eager launches, median over K frames"},
             "single_view": {
                 "graph": {"iters_per_s": per_s(single_ms, 1), "ms_per_step": single_ms / args.steps,
                           "fwd_views_per_s": per_s(single_fwd_ms, 1)},
