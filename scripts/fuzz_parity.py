@@ -12,70 +12,78 @@ from tests.scenes import make_scene, np_inputs, product_settings
 from gsvc_b200.rasterizer import GaussianRasterizer, RasterState
 from gsvc_b200.views import ViewBatch, rasterize_views
 
-n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 40
-rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
-dev = torch.device("cuda:0")
 NAMES = ("means3D", "colors_precomp", "opacities", "scales", "rotations")
-worst = dict(fwd=0.0, grad=0.0, frag=0.0)
-t_start = time.time()
-for case in range(n_cases):
-    W = int(rng.choice([7, 16, 33, 64, 100, 160, 250, 320]))
-    H = int(rng.choice([5, 16, 40, 64, 96, 130, 200]))
-    F = int(rng.choice([64, 128, 320]))
-    # density: instances per tile from ~5 to ~3000
-    tiles = ((W + 15) // 16) * ((H + 15) // 16)
-    per_tile = float(rng.choice([4, 20, 50, 100, 200, 400, 900, 3000]))
-    P = int(min(60000, max(1, per_tile * tiles / 3.0)))
-    back = bool(rng.integers(2))
-    bg = tuple(float(x) for x in rng.random(3)) if rng.integers(2) else (0.0, 0.0, 0.0)
-    sm = float(rng.choice([1.0, 0.5, 2.0]))
-    scene = make_scene(P=P, W=W, H=H, F=F, seed=int(rng.integers(1 << 30)), back=back, bg=bg, scale_modifier=sm)
-    gi = np_inputs(scene["gaussians"])
-    fo = c_oracle.forward(scene["oracle_settings"], gi["means3D"], gi["opacities"], gi["scales"], gi["rotations"],
-                          colors_precomp=gi["colors_precomp"])
-    rs = product_settings(scene, dev)
-    g = {k: v.to(dev) for k, v in scene["gaussians"].items()}
-    # stage exports through the allocator-callback form (exact capacity, scatter path)
-    st = RasterState(rs, g["means3D"], g["opacities"], colors_precomp=g["colors_precomp"], scales=g["scales"],
-                     rotations=g["rotations"])
-    keys, pl, ranges = st.export_keys()
-    assert st.num_rendered == fo["num_rendered"], (case, st.num_rendered, fo["num_rendered"])
-    assert np.array_equal(st.radii.cpu().numpy(), fo["radii"]), case
-    assert np.array_equal(keys.cpu().numpy().view(np.uint64), fo["bin"]["keys"]), case
-    assert np.array_equal(pl.cpu().numpy().view(np.uint32), fo["bin"]["point_list"]), case
-    assert np.array_equal(ranges.cpu().numpy().view(np.uint32), fo["bin"]["ranges"]), case
-    # autograd call (capacity-hint path on the second call)
-    dL = torch.randn((3, H, W), generator=torch.Generator().manual_seed(case))
-    go = c_oracle.backward(fo, dL.numpy())
-    for rep in range(2):
-        p = {k: g[k].clone().requires_grad_(True) for k in NAMES}
-        m2d = torch.zeros_like(p["means3D"], requires_grad=True)
-        color, radii, n = GaussianRasterizer(raster_settings=rs)(
-            means3D=p["means3D"], means2D=m2d, shs=None, colors_precomp=p["colors_precomp"], opacities=p["opacities"],
-            scales=p["scales"], rotations=p["rotations"], cov3D_precomp=None)
-        grads = torch.autograd.grad(color, [p[k] for k in NAMES], grad_outputs=dL.to(dev))
-        assert n == fo["num_rendered"]
-        err = np.abs(color.detach().cpu().numpy() - fo["color"])
-        frag = fo["fragile"]
-        e = err[:, ~frag].max(initial=0.0)
-        assert e <= 1e-5, (case, e)
-        worst["fwd"] = max(worst["fwd"], float(e)); worst["frag"] = max(worst["frag"], float(frag.mean()))
-        ok = ~go["touched_fragile"]
-        for k, gr in zip(NAMES, grads):
-            a = gr.cpu().numpy().reshape(P, -1)[ok]; b = go[k].reshape(P, -1)[ok]
-            if b.size == 0:
-                continue
-            rel = np.abs(a - b).max() / (np.abs(b).max() + 1e-30)
-            assert rel <= 1e-4, (case, k, rel)
-            worst["grad"] = max(worst["grad"], float(rel))
-    # the same view twice in one batch (plain) == the single call, bit for bit
-    with torch.no_grad():
-        imgs, rad2, n2 = rasterize_views(ViewBatch([rs, rs]), means3D=g["means3D"], opacities=g["opacities"],
-                                         colors_precomp=g["colors_precomp"], scales=g["scales"], rotations=g["rotations"])
-    assert n2 == 2 * fo["num_rendered"] and torch.equal(imgs[0], color.detach()) and torch.equal(imgs[1], color.detach())
-    assert torch.equal(rad2[0], radii) and torch.equal(rad2[1], radii)
-    mx = int(np.diff(fo["bin"]["ranges"].astype(np.int64), axis=1).max(initial=0))
-    print(f"case {case:3d} ok: {W}x{H} P={P} R={fo['num_rendered']} max_bucket={mx} back={back} sm={sm} "
-          f"fwd_err={e:.1e} fragile={frag.mean():.1e}", flush=True)
-print(f"{n_cases} cases ok in {time.time() - t_start:.0f} s; worst fwd err {worst['fwd']:.2e}, worst grad rel err "
+
+
+def run(n_cases=40, seed=0, verbose=True):
+  rng = np.random.default_rng(seed)
+  dev = torch.device("cuda:0")
+  worst = dict(fwd=0.0, grad=0.0, frag=0.0)
+  t_start = time.time()
+  for case in range(n_cases):
+      W = int(rng.choice([7, 16, 33, 64, 100, 160, 250, 320]))
+      H = int(rng.choice([5, 16, 40, 64, 96, 130, 200]))
+      F = int(rng.choice([64, 128, 320]))
+      # density: instances per tile from ~5 to ~3000
+      tiles = ((W + 15) // 16) * ((H + 15) // 16)
+      per_tile = float(rng.choice([4, 20, 50, 100, 200, 400, 900, 3000]))
+      P = int(min(60000, max(1, per_tile * tiles / 3.0)))
+      back = bool(rng.integers(2))
+      bg = tuple(float(x) for x in rng.random(3)) if rng.integers(2) else (0.0, 0.0, 0.0)
+      sm = float(rng.choice([1.0, 0.5, 2.0]))
+      scene = make_scene(P=P, W=W, H=H, F=F, seed=int(rng.integers(1 << 30)), back=back, bg=bg, scale_modifier=sm)
+      gi = np_inputs(scene["gaussians"])
+      fo = c_oracle.forward(scene["oracle_settings"], gi["means3D"], gi["opacities"], gi["scales"], gi["rotations"],
+                            colors_precomp=gi["colors_precomp"])
+      rs = product_settings(scene, dev)
+      g = {k: v.to(dev) for k, v in scene["gaussians"].items()}
+      # stage exports through the allocator-callback form (exact capacity, scatter path)
+      st = RasterState(rs, g["means3D"], g["opacities"], colors_precomp=g["colors_precomp"], scales=g["scales"],
+                       rotations=g["rotations"])
+      keys, pl, ranges = st.export_keys()
+      assert st.num_rendered == fo["num_rendered"], (case, st.num_rendered, fo["num_rendered"])
+      assert np.array_equal(st.radii.cpu().numpy(), fo["radii"]), case
+      assert np.array_equal(keys.cpu().numpy().view(np.uint64), fo["bin"]["keys"]), case
+      assert np.array_equal(pl.cpu().numpy().view(np.uint32), fo["bin"]["point_list"]), case
+      assert np.array_equal(ranges.cpu().numpy().view(np.uint32), fo["bin"]["ranges"]), case
+      # autograd call (capacity-hint path on the second call)
+      dL = torch.randn((3, H, W), generator=torch.Generator().manual_seed(case))
+      go = c_oracle.backward(fo, dL.numpy())
+      for rep in range(2):
+          p = {k: g[k].clone().requires_grad_(True) for k in NAMES}
+          m2d = torch.zeros_like(p["means3D"], requires_grad=True)
+          color, radii, n = GaussianRasterizer(raster_settings=rs)(
+              means3D=p["means3D"], means2D=m2d, shs=None, colors_precomp=p["colors_precomp"], opacities=p["opacities"],
+              scales=p["scales"], rotations=p["rotations"], cov3D_precomp=None)
+          grads = torch.autograd.grad(color, [p[k] for k in NAMES], grad_outputs=dL.to(dev))
+          assert n == fo["num_rendered"]
+          err = np.abs(color.detach().cpu().numpy() - fo["color"])
+          frag = fo["fragile"]
+          e = err[:, ~frag].max(initial=0.0)
+          assert e <= 1e-5, (case, e)
+          worst["fwd"] = max(worst["fwd"], float(e)); worst["frag"] = max(worst["frag"], float(frag.mean()))
+          ok = ~go["touched_fragile"]
+          for k, gr in zip(NAMES, grads):
+              a = gr.cpu().numpy().reshape(P, -1)[ok]; b = go[k].reshape(P, -1)[ok]
+              if b.size == 0:
+                  continue
+              rel = np.abs(a - b).max() / (np.abs(b).max() + 1e-30)
+              assert rel <= 1e-4, (case, k, rel)
+              worst["grad"] = max(worst["grad"], float(rel))
+      # the same view twice in one batch (plain) == the single call, bit for bit
+      with torch.no_grad():
+          imgs, rad2, n2 = rasterize_views(ViewBatch([rs, rs]), means3D=g["means3D"], opacities=g["opacities"],
+                                           colors_precomp=g["colors_precomp"], scales=g["scales"], rotations=g["rotations"])
+      assert n2 == 2 * fo["num_rendered"] and torch.equal(imgs[0], color.detach()) and torch.equal(imgs[1], color.detach())
+      assert torch.equal(rad2[0], radii) and torch.equal(rad2[1], radii)
+      mx = int(np.diff(fo["bin"]["ranges"].astype(np.int64), axis=1).max(initial=0))
+      if verbose:
+        print(f"case {case:3d} ok: {W}x{H} P={P} R={fo['num_rendered']} max_bucket={mx} back={back} sm={sm} "
+            f"fwd_err={e:.1e} fragile={frag.mean():.1e}", flush=True)
+  print(f"{n_cases} cases ok in {time.time() - t_start:.0f} s; worst fwd err {worst['fwd']:.2e}, worst grad rel err "
       f"{worst['grad']:.2e}, worst fragile fraction {worst['frag']:.1e}")
+  return worst
+
+
+if __name__ == "__main__":
+    run(int(sys.argv[1]) if len(sys.argv) > 1 else 40, int(sys.argv[2]) if len(sys.argv) > 2 else 0)
