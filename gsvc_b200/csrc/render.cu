@@ -130,7 +130,7 @@ __device__ __forceinline__ BlockGeom block_geom(int tile, int gx, int tid)
 //   [0] = (pix.x, pix.y, B/A, B/C)
 //   [1] = (A', B', C', opacity) with A' = -A log2e/2, B' = -B log2e, C' = -C log2e/2, so that
 //         alpha = opacity * 2^q(d),  q(d) = A' dx^2 + B' dx dy + C' dy^2  (q <= 0, concave)
-//   [2] = (r, g, b, thr) with thr = -log2(255 opacity) - margin: alpha >= 1/255  <=>  q >= thr (+margin)
+//   [2] = (r, g, b, Gaussian id as bits)
 constexpr float CULL_MARGIN = 1e-3f;  // in log2 units (7e-4 relative in alpha) >> fp32 rounding of q
 
 __device__ __forceinline__ void stage(float4* s_feat, int slot, const GeomView& geo, unsigned int id)
@@ -140,7 +140,7 @@ __device__ __forceinline__ void stage(float4* s_feat, int slot, const GeomView& 
     float4 f2 = __ldg(geo.feat2 + id);
     f0.z = __fdividef(f1.y, f1.x);
     f0.w = __fdividef(f1.y, f1.z);
-    f2.w = -__log2f(255.0f * f1.w) - CULL_MARGIN;
+    f2.w = __uint_as_float(id);   // rides along with the colour: the backward's atomics need it per hit
     f1.x *= -0.5f * LOG2E;
     f1.y *= -LOG2E;
     f1.z *= -0.5f * LOG2E;
@@ -159,7 +159,7 @@ __device__ __forceinline__ bool block_hit(const BlockGeom& b, const float4* e)
 {
     const float4 f0 = e[0];
     const float4 f1 = e[1];
-    const float thr = e[2].w;
+    const float thr = -__log2f(255.0f * f1.w) - CULL_MARGIN;   // alpha >= 1/255  <=>  q >= thr (+margin)
     const float ex = fminf(fmaxf(f0.x, b.xmin), b.xmax), ey = fminf(fmaxf(f0.y, b.ymin), b.ymax);
     const float dxe = ex - f0.x, dye = ey - f0.y;
     const float dy1 = fminf(fmaxf(fmaf(-f0.w, dxe, f0.y), b.ymin), b.ymax) - f0.y;
@@ -354,7 +354,6 @@ render_backward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, c
                        float* __restrict__ acc /* [P][12] */)
 {
     __shared__ float4 s_feat[3 * BATCH];
-    __shared__ unsigned int s_id[BATCH];
     __shared__ unsigned int s_max[BLEND_WARPS];
 
     pdl_prologue();
@@ -418,7 +417,6 @@ render_backward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, c
             const int kpos = m_len - 1 - (base + slot);  // list position staged in this slot
             if (kpos >= 0) {
                 const unsigned int id = bin.point_list[rg.x + kpos];
-                s_id[slot] = id;
                 stage(s_feat, slot, geo, id);
             }
         }
@@ -485,7 +483,7 @@ render_backward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, c
                 float d_b = lo(cb2) + hi(cb2);
                 const float sum8 = warp_reduce8(v, lane);
                 d_b = warp_sum(d_b);
-                if (red_lane) atomicAdd(acc + (size_t)s_id[c + k] * 12 + red_off, lane == 1 ? d_b : sum8);
+                if (red_lane) atomicAdd(acc + (size_t)__float_as_uint(f2v.w) * 12 + red_off, lane == 1 ? d_b : sum8);
             }
         }
     }
