@@ -558,6 +558,14 @@ def run_product_arm(args, rank, local_rank, world):
                          "note": "blend kernels are FP32/issue-bound by construction (256 pixel-Gaussian pairs per 40 B "
                                  "instance; ncu: ~84 % issue-active, < 5 % DRAM); the HBM fraction of a stream kernel of "
                                  "this path is reported under visible_filter; see DESIGN.md §4"},
+            # what actually bounds the dominant kernel: issued warp-instructions per second against the SMs' issue rate
+            # (4 schedulers x 1 instruction per clock per SM); instruction count per launch from the committed ncu capture
+            "issue_roofline": (lambda inst: None if not inst else {
+                "kernel": dom, "warp_instructions_per_launch": inst, "source": "profiles/r1_traffic.json (ncu smsp__inst_executed.sum)",
+                "achieved_Ginstr_per_s": inst / (stage_avg[dom] * 1e-3) / 1e9,
+                "peak_Ginstr_per_s": 148 * 4 * (clk.get("sm_mhz") or 1965.0) * 1e6 / 1e9,
+                "frac": inst / (stage_avg[dom] * 1e-3) / (148 * 4 * (clk.get("sm_mhz") or 1965.0) * 1e6)})(
+                    prof.get(dom, {}).get("inst_executed")),
             "e2e": {"value": per_s(e2e_ms, NV), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps, "pcie_alone": pcie,
                     "host_state": ("sharded by rows over the ranks: each rank uploads 1/N of the parameters (all-gather over "
