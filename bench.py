@@ -487,6 +487,8 @@ def run_product_arm(args, rank, local_rank, world):
         _lib.stage_timing(False)
         radii_a = rast.visible_filter(means3D=ga["means3D"], scales=ga["scales"], rotations=ga["rotations"], cov3D_precomp=None)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(5):
+            nz = torch.nonzero(radii_a > 0)
         torch.cuda.synchronize(device)
         e0.record()
         for _ in range(20):
