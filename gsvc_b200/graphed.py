@@ -23,7 +23,7 @@ from typing import Dict, Optional
 import torch
 
 from . import rasterizer as R
-from .rasterizer import GaussianRasterizer, RasterizerError
+from .rasterizer import RasterizerError
 from .sharding import GRAD_LAYOUT, GRAD_WIDTH, packed_backward
 from .views import ViewBatch, rasterize_views
 

@@ -29,7 +29,7 @@ from typing import Callable, Dict, Optional
 
 import torch
 
-from .rasterizer import GaussianRasterizer, RasterizerError
+from .rasterizer import RasterizerError
 from .sharding import GRAD_LAYOUT, GRAD_WIDTH, packed_backward
 from .views import ViewBatch, rasterize_views
 

@@ -2,7 +2,6 @@
 x (front + back) in one batched chain, L1 loss, Adam — must actually fit target frames, i.e. the gradients of the
 whole chain point downhill."""
 import pytest
-import torch
 
 pytestmark = pytest.mark.gpu
 
