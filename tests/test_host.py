@@ -167,3 +167,67 @@ def test_frame_sharded_allreduce_equals_single_rank(tmp_path):
     assert torch.equal(r0, r1)
     assert single.abs().max() > 0
     assert (r0 - single).abs().max() <= 1e-6 * single.abs().max() + 1e-12
+
+
+def _cpu_settings(W=64, H=48, F=64, back=False):
+    from gsvc_b200.frames import CubeGeometry
+    from gsvc_b200.rasterizer import GaussianRasterizationSettings
+    fr = CubeGeometry(W, H, F).frame(F // 2)
+    vm = fr.view_matrix_s if back else fr.view_matrix
+    return GaussianRasterizationSettings(
+        image_height=H, image_width=W, x_min=fr.x_min, y_min=fr.y_min, scale=fr.scale, threshold=0.05,
+        bg=torch.zeros(3), scale_modifier=1.0, viewmatrix=vm.permute(1, 0), sh_degree=0, campos=fr.cam_pos,
+        prefiltered=False, debug=False)
+
+
+def test_view_batch_layout_and_validation():
+    """gsvc_b200.views.ViewBatch (host logic only): default one image per view, the toast mapping of the reference's
+    (front + flip(back)) / 2 (pipeline/train.py:353-375), and the checks on what the views of a batch must share."""
+    from gsvc_b200.rasterizer import RasterizerError
+    from gsvc_b200.views import ViewBatch
+    f, b = _cpu_settings(), _cpu_settings(back=True)
+    plain = ViewBatch([f, b])
+    assert (plain.n_views, plain.n_out, plain.out_image, plain.flip_x, plain.weight) == (2, 2, [0, 1], [False, False], [1.0, 1.0])
+    toast = ViewBatch.toast(f, b)
+    assert (toast.n_views, toast.n_out, toast.out_image, toast.flip_x, toast.weight) == (2, 1, [0, 0], [False, True], [0.5, 0.5])
+    win = ViewBatch.toasts([(f, b)] * 3)
+    assert (win.n_views, win.n_out, win.out_image) == (6, 3, [0, 0, 1, 1, 2, 2])
+    with pytest.raises(RasterizerError):
+        ViewBatch([f, _cpu_settings(W=80)])                       # image sizes differ
+    with pytest.raises(RasterizerError):
+        ViewBatch([f, f._replace(threshold=0.1)])                 # TSW slab differs
+    with pytest.raises(RasterizerError):
+        ViewBatch([f, f._replace(bg=torch.ones(3))])              # background differs
+    with pytest.raises(RasterizerError):
+        ViewBatch([f] * 17)                                       # GSVC_RAST_MAX_VIEWS
+    with pytest.raises(RasterizerError):
+        ViewBatch([f, b], out_image=[0, 2])                       # gap in the output images
+    with pytest.raises(RasterizerError):
+        ViewBatch([f, b], flip_x=[True])                          # one entry per view
+
+
+def test_batched_and_host_paths_have_no_cpu_fallback():
+    from gsvc_b200.graphed import GraphedStep
+    from gsvc_b200.hostpipe import HostStepPipeline
+    from gsvc_b200.rasterizer import GaussianRasterizer, RasterizerError
+    from gsvc_b200.views import rasterize_views
+    from gsvc_b200.frames import CubeGeometry, synthetic_gaussians
+    g = synthetic_gaussians(50, CubeGeometry(64, 48, 64), 32)
+    f = _cpu_settings()
+    with pytest.raises(RasterizerError):
+        rasterize_views([f, f], means3D=g["means3D"], opacities=g["opacities"], colors_precomp=g["colors_precomp"],
+                        scales=g["scales"], rotations=g["rotations"])
+    with pytest.raises(Exception):
+        rasterize_views([f, f], means3D=g["means3D"], opacities=g["opacities"])          # neither SHs nor colours
+    with pytest.raises(RasterizerError):
+        rasterize_views([f, f], means3D=g["means3D"], opacities=g["opacities"], colors_precomp=g["colors_precomp"],
+                        scales=g["scales"], rotations=g["rotations"], means2D=torch.zeros(1, 50, 3))   # [n_views,P,3]
+    with pytest.raises(RasterizerError):
+        HostStepPipeline(50, "cpu")
+    with pytest.raises(ValueError):
+        HostStepPipeline(50, "cuda", slots=1)
+    with pytest.raises(RasterizerError):
+        GraphedStep(GaussianRasterizer(raster_settings=f), g, None)
+    with pytest.raises(RasterizerError):
+        GaussianRasterizer(raster_settings=f).visible_filter_compact(means3D=g["means3D"], scales=g["scales"],
+                                                                     rotations=g["rotations"])
