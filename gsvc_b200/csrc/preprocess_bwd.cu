@@ -84,7 +84,7 @@ __device__ void sh_backward(int deg, int M, const float* sh, float* dsh, const f
     dmean[2] += (ddz - z * dot) / len;
 }
 
-__global__ void __launch_bounds__(256, 4) preprocess_backward_kernel(DevSettings s, PreInputs in,
+__global__ void __launch_bounds__(256, 3) preprocess_backward_kernel(DevSettings s, PreInputs in,
                                                                   const int32_t* __restrict__ radii, GeomView geo,
                                                                   const float4* __restrict__ acc, BwdOutputs out)
 {
