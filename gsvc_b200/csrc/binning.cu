@@ -273,7 +273,7 @@ __device__ __forceinline__ void sort_bucket_regs(const unsigned long long* __res
 // BIG = true: up to 512 (dense scenes, e.g. 1 M Gaussians at 1080p = ~360 per tile); chosen by the launcher from
 // the expected bucket size.  Either kernel sorts any bucket correctly (CTA-wide fallbacks beyond its register path).
 template <bool BIG>
-__global__ void __launch_bounds__(SORT_THREADS) sort_tiles_kernel(int T, ImageView im, BinView bin,
+__global__ void __launch_bounds__(SORT_THREADS, 4) sort_tiles_kernel(int T, ImageView im, BinView bin,
                                                                   unsigned long long cap)
 {
     constexpr int WARP_ITEMS = BIG ? SORT_WARP_ITEMS_BIG : SORT_WARP_ITEMS;
