@@ -500,6 +500,30 @@ def run_product_arm(args, rank, local_rank, world):
               "note": "fused_compaction_ms = filter + ascending visible indices + count in ONE kernel (visible_filter_compact); "
                       "torch_mask_nonzero_ms = what the mask costs the reference AFTER the filter (radii > 0, nonzero with its host sync)"}
         del ga
+        # row f4: reference-scale anchors (1M over the WHOLE cube depth, as init_anchor_num x n_offsets gives), kept
+        # z-sorted the way the stream codec stores them; the slab's index range comes from its interval table
+        from gsvc_b200.frames import slab_index_range, z_interval_table
+        gz = synthetic_gaussians(Pa, geom, 0, cfg["F"] - 1, threshold=THRESHOLD, seed=5, device=device)
+        order = torch.argsort(gz["means3D"][:, 2], stable=True)
+        gz = {k: v[order].contiguous() for k, v in gz.items() if k in ("means3D", "scales", "rotations")}
+        table = z_interval_table(gz["means3D"][:, 2])
+        rng_idx = slab_index_range(table, geom.z_of(frame_id), THRESHOLD)
+        slab = {}
+        for name, kw in (("full_scan_ms", {}), ("index_range_ms", {"index_range": rng_idx})):
+            _lib.stage_timing(True)
+            for _ in range(20):
+                flush.zero_()
+                rz = rast.visible_filter(means3D=gz["means3D"], scales=gz["scales"], rotations=gz["rotations"],
+                                         cov3D_precomp=None, **kw)
+            torch.cuda.synchronize(device)
+            slab[name] = _lib.stage_times()["visible_filter"]
+            _lib.stage_timing(False)
+            slab["visible"] = int((rz > 0).sum().item())
+        slab.update(P_anchors=Pa, index_range=list(rng_idx),
+                    note="anchors over the whole cube depth, z-sorted; index_range = the codec-style interval table's "
+                         "range for this frame's slab (the filter reads only those anchors)")
+        vf["slab_ordered"] = slab
+        del gz
     clk = clocks.stop()
 
     if rank == 0:

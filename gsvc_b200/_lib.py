@@ -53,9 +53,10 @@ SIGNATURES = {
     "gsvc_rast_image_bytes_views": (_sz, [_i32, _i32, _i32]),
     "gsvc_rast_binning_bytes": (_sz, [_i64]),
     "gsvc_rast_backward_scratch_bytes": (_sz, [_i32]),
-    "gsvc_rast_visible_filter": (C.c_int, [_SP, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gsvc_rast_visible_filter": (C.c_int, [_SP, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
     "gsvc_rast_compact_scratch_bytes": (_sz, [_i32]),
-    "gsvc_rast_visible_filter_compact": (C.c_int, [_SP, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_uint32, _vp]),
+    "gsvc_rast_visible_filter_compact": (C.c_int, [_SP, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_uint32,
+                                                  _i32, _i32, _vp]),
     "gsvc_rast_forward_launch": (C.c_int, [_SP, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64,
                                            _vp, _vp, _vp, _vp, C.c_uint32, _vp]),
     "gsvc_rast_wait_count": (_i64, [_vp, C.c_uint32, _vp]),

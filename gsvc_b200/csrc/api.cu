@@ -195,8 +195,16 @@ int gsvc_rast_stage_times(float* ms_host)
     return ST_COUNT;
 }
 
+static int check_range(int32_t P, int32_t& lo, int32_t& hi)
+{
+    if (lo == 0 && hi == 0) hi = P;    // (0, 0) = no range given: everything
+    if (lo < 0 || hi > P || lo > hi) return fail(GSVC_RAST_ERR_INVALID, "index range [%d, %d) is not inside [0, %d)", lo, hi, P);
+    return 0;
+}
+
 int gsvc_rast_visible_filter(const gsvc_rast_settings* st, int32_t P, const float* means3D, const float* scales,
-                             const float* rotations, const float* cov3D_precomp, int32_t* radii, void* stream_)
+                             const float* rotations, const float* cov3D_precomp, int32_t* radii, int32_t range_lo,
+                             int32_t range_hi, void* stream_)
 {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DevSettings d;
@@ -205,8 +213,10 @@ int gsvc_rast_visible_filter(const gsvc_rast_settings* st, int32_t P, const floa
     rc = check_inputs(P, 0, 0, means3D, nullptr, nullptr, nullptr, scales, rotations, cov3D_precomp, false);
     if (rc) return rc;
     if (P > 0 && !radii) return fail(GSVC_RAST_ERR_INVALID, "radii is NULL");
+    rc = check_range(P, range_lo, range_hi);
+    if (rc) return rc;
     const bool dbg = st->debug != 0;
-    PreInputs in{P, means3D, nullptr, nullptr, nullptr, scales, rotations, cov3D_precomp};
+    PreInputs in{P, means3D, nullptr, nullptr, nullptr, scales, rotations, cov3D_precomp, range_lo, range_hi};
     { StageScope t(ST_VISIBLE_FILTER, stream); CK(launch_visible_filter(d, in, radii, stream), "visible_filter"); }
     return 0;
 }
@@ -229,7 +239,7 @@ static int forward_launch_core(const gsvc_rast_settings* st, const DevSettings& 
     const int PV = (P < 1 ? 1 : P) * d.n_views;
     GeomView g = geom_view(geom, PV, d.sh_M);
     ImageView im = image_view(image, d.W, d.H, d.n_views);
-    PreInputs in{P, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp};
+    PreInputs in{P, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, 0, P};
     if (d.accumulate)   // views that share an output image add into it
         CK(cudaMemsetAsync(out_color, 0, (size_t)n_out * 3 * d.W * d.H * sizeof(float), stream), "zero out_color");
     { StageScope t(ST_PREPROCESS, stream); CK(launch_preprocess(d, in, radii, g, im, static_cast<float4*>(bwd_scratch), stream), "preprocess"); }
@@ -250,7 +260,7 @@ size_t gsvc_rast_compact_scratch_bytes(int32_t P) { return compact_scratch_bytes
 int gsvc_rast_visible_filter_compact(const gsvc_rast_settings* st, int32_t P, const float* means3D, const float* scales,
                                      const float* rotations, const float* cov3D_precomp, int32_t* radii,
                                      int32_t* visible_indices, void* scratch, uint64_t* count_slot_host,
-                                     uint32_t ticket, void* stream_)
+                                     uint32_t ticket, int32_t range_lo, int32_t range_hi, void* stream_)
 {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DevSettings d;
@@ -260,8 +270,10 @@ int gsvc_rast_visible_filter_compact(const gsvc_rast_settings* st, int32_t P, co
     if (rc) return rc;
     if (!scratch || (P > 0 && !visible_indices))
         return fail(GSVC_RAST_ERR_INVALID, "visible_indices/scratch must be non-NULL");
+    rc = check_range(P, range_lo, range_hi);
+    if (rc) return rc;
     const bool dbg = st->debug != 0;
-    PreInputs in{P, means3D, nullptr, nullptr, nullptr, scales, rotations, cov3D_precomp};
+    PreInputs in{P, means3D, nullptr, nullptr, nullptr, scales, rotations, cov3D_precomp, range_lo, range_hi};
     {
         StageScope t(ST_VISIBLE_FILTER, stream);
         CK(launch_visible_filter_compact(d, in, radii, visible_indices, scratch,
@@ -409,7 +421,7 @@ static int backward_core(const gsvc_rast_settings* st, const DevSettings& d, int
     ImageView im = image_view(const_cast<void*>(image), d.W, d.H, d.n_views);
     BinView b = bin_view(const_cast<void*>(binning), capacity);
     float4* acc = static_cast<float4*>(scratch);
-    PreInputs in{P, means3D, shs, colors_precomp, nullptr, scales, rotations, cov3D_precomp};
+    PreInputs in{P, means3D, shs, colors_precomp, nullptr, scales, rotations, cov3D_precomp, 0, P};
     { StageScope t(ST_RENDER_BWD, stream); CK(launch_render_backward(d, P, g, im, b, dL_dout, acc, scratch_is_zero != 0, stream), "render_backward"); }
     { StageScope t(ST_PREPROCESS_BWD, stream); CK(launch_preprocess_backward(d, in, radii, g, acc, out, stream), "preprocess_backward"); }
     return 0;

@@ -244,6 +244,9 @@ struct PreInputs {
     const float* scales;
     const float* rotations;
     const float* cov3D_precomp;
+    // visible_filter only: anchors outside [range_lo, range_hi) are declared culled WITHOUT being read
+    // (slab-ordered anchors: the caller knows which index range can intersect the TSW slab); 0, P = everything
+    int range_lo, range_hi;
 };
 
 cudaError_t launch_visible_filter(const DevSettings& s, const PreInputs& in, int32_t* radii, cudaStream_t st);

@@ -193,8 +193,24 @@ __global__ void __launch_bounds__(256) preprocess_kernel(DevSettings s, PreInput
     // Lanes past the end stay in the warp (they redo the last Gaussian with all stores masked) so that the
     // warp-wide tile walk at the end (and the block-wide compaction) runs converged.
     const int g_raw = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = g_raw < in.P;
-    const int g = valid ? g_raw : in.P - 1;
+    bool valid = g_raw < in.P;
+    if (FILTER) {
+        // Slab-ordered anchors (the reference's stream codec keeps them z-sorted in 0.01
+        // intervals, utils/encodings.py:827-862): only indices in [range_lo, range_hi) can be inside the TSW slab.
+        // A CTA wholly outside writes its zeros and leaves before touching the inputs: the filter costs
+        // O(slab) reads + 4 bytes per anchor.
+        const int cta_lo = blockIdx.x * blockDim.x, cta_hi = cta_lo + blockDim.x;
+        if (cta_hi <= in.range_lo || cta_lo >= in.range_hi) {
+            if (valid && radii) radii[g_raw] = 0;
+            if (MODE == 2) {
+                if ((threadIdx.x & 31) == 0) co.ballots[g_raw >> 5] = 0u;
+                if (threadIdx.x == 0) co.cta_count[blockIdx.x] = 0u;
+            }
+            return;
+        }
+    }
+    const bool in_range = !FILTER || (g_raw >= in.range_lo && g_raw < in.range_hi);
+    const int g = valid ? (in_range ? g_raw : min(max(g_raw, in.range_lo), in.range_hi - 1)) : in.P - 1;
     // view of the batch (grid.y): per-Gaussian state of view v lives at virtual index v*P + g, its tiles at v*Tv + t
     const int v = FILTER ? 0 : (int)blockIdx.y;
     const size_t gv = (size_t)v * in.P + g;
@@ -223,7 +239,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(DevSettings s, PreInput
     int rminx = 0, rminy = 0, rmaxx = 0, rmaxy = 0;
     float a = 0.f, b = 0.f, c = 0.f, det = 0.f, px = 0.f, py = 0.f;
     // U6: TSW slab — keep |z_view| <= threshold (preprocess.py:109-116)
-    bool ok = valid && !(fabsf(vz) > s.threshold);
+    bool ok = valid && in_range && !(fabsf(vz) > s.threshold);
     if (ok) {
         float cov[6];
         if (in.cov3D_precomp) {
@@ -250,7 +266,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(DevSettings s, PreInput
         rmaxy = (int)fminf(fgy, fmaxf(0.f, truncf((py + rad_f + (float)(TILE - 1)) / ft)));
         ok = (rmaxx - rminx) * (rmaxy - rminy) > 0;
     }
-    if (valid && radii) radii[gv] = ok ? radius : 0;
+    if (valid && radii) radii[FILTER ? (size_t)g_raw : gv] = ok ? radius : 0;
     if (MODE == 2) {
         __shared__ unsigned int s_vis[8];
         const unsigned int bal = __ballot_sync(0xffffffffu, ok);

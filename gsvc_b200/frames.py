@@ -120,3 +120,31 @@ def synthetic_gaussians(P: int, geom: CubeGeometry, frame_lo: int, frame_hi: Opt
     colors = torch.rand(P, 3, generator=g)
     out = dict(means3D=means3D, scales=scales, rotations=rotations, opacities=opacities, colors_precomp=colors)
     return {k: v.to(device=device, dtype=torch.float32).contiguous() for k, v in out.items()}
+
+
+def z_interval_table(z_sorted: torch.Tensor, interval: float = 0.01):
+    """The stream codec's slab table for anchors sorted by z (utils/encodings.py:827-862 `reorder_and_split`):
+    z intervals of width `interval` starting at the rounded minimum, each with its [start, end) index range.
+    Returns (z_lo: float, interval: float, starts: LongTensor[n_intervals + 1]) — interval k covers
+    z in [z_lo + k*interval, z_lo + (k+1)*interval) = indices [starts[k], starts[k+1])."""
+    z = z_sorted.detach().double().cpu()
+    if z.numel() and not bool((z[1:] >= z[:-1]).all()):
+        raise ValueError("anchors are not sorted by z")
+    z_min = float(z.min()) if z.numel() else 0.0
+    z_max = float(z.max()) if z.numel() else 0.0
+    z_lo = math.floor(z_min / interval) * interval
+    n = max(1, int(math.ceil((z_max - z_lo) / interval + 1e-9)) + 1)
+    edges = z_lo + interval * torch.arange(n + 1, dtype=torch.float64)
+    starts = torch.searchsorted(z, edges, right=False)
+    return z_lo, interval, starts
+
+
+def slab_index_range(table, z_frame: float, threshold: float):
+    """Index range [lo, hi) of the z-sorted anchors whose interval can intersect the TSW slab |z - z_frame| <= threshold
+    (front and back view share it): whole intervals, one interval of margin on both sides for rounding."""
+    z_lo, interval, starts = table
+    n = starts.numel() - 1
+    k0 = int(math.floor((z_frame - threshold - z_lo) / interval)) - 1
+    k1 = int(math.floor((z_frame + threshold - z_lo) / interval)) + 2
+    k0, k1 = min(max(k0, 0), n), min(max(k1, 0), n)
+    return int(starts[k0]), int(starts[k1])

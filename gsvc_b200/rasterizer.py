@@ -305,8 +305,12 @@ class GaussianRasterizer(nn.Module):
         super().__init__()
         self.raster_settings = raster_settings
 
-    def visible_filter(self, means3D, scales=None, rotations=None, cov3D_precomp=None):
-        """preprocess.py:99-104 — radii[P] int32 (> 0 where the anchor survives the TSW slab and image culls)."""
+    def visible_filter(self, means3D, scales=None, rotations=None, cov3D_precomp=None, index_range=None):
+        """preprocess.py:99-104 — radii[P] int32 (> 0 where the anchor survives the TSW slab and image culls).
+
+        `index_range=(lo, hi)` (slab-ordered anchors): the caller promises that anchors outside
+        [lo, hi) are outside the TSW slab (frames.slab_index_range computes it from a z-interval table like the
+        stream codec's, utils/encodings.py:827-862); they get radius 0 without being read."""
         rs = self.raster_settings
         if (scales is None or rotations is None) == (cov3D_precomp is None):
             raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
@@ -321,11 +325,15 @@ class GaussianRasterizer(nn.Module):
             r = _dev_f32(rotations, device, "rotations")
             c = _dev_f32(cov3D_precomp, device, "cov3D_precomp")
             radii = torch.empty((P,), dtype=torch.int32, device=device)
-            _lib.check(L.gsvc_rast_visible_filter(ns.ref, P, _ptr(m), _ptr(s), _ptr(r), _ptr(c), _ptr(radii),
+            lo, hi = (0, 0) if index_range is None else (int(index_range[0]), int(index_range[1]))
+            if index_range is not None and lo == hi:
+                return radii.zero_()
+            _lib.check(L.gsvc_rast_visible_filter(ns.ref, P, _ptr(m), _ptr(s), _ptr(r), _ptr(c), _ptr(radii), lo, hi,
                                                   _stream_ptr(device)), "gsvc_rast_visible_filter")
         return radii
 
-    def visible_filter_compact(self, means3D, scales=None, rotations=None, cov3D_precomp=None, want_radii=True):
+    def visible_filter_compact(self, means3D, scales=None, rotations=None, cov3D_precomp=None, want_radii=True,
+                               index_range=None):
         """visible_filter fused with the compaction its caller does next.
 
         prefilter_voxel returns `radii_pure > 0` (preprocess.py:108) and generate_neural_gaussians indexes every
@@ -351,8 +359,11 @@ class GaussianRasterizer(nn.Module):
             scratch = _bytes(L.gsvc_rast_compact_scratch_bytes(P), device)
             stream = _stream_ptr(device)
             slot, ticket = _count_slot()
+            lo, hi = (0, 0) if index_range is None else (int(index_range[0]), int(index_range[1]))
+            if index_range is not None and lo == hi:
+                return idx[:0], (radii.zero_() if radii is not None else None)
             _lib.check(L.gsvc_rast_visible_filter_compact(ns.ref, P, _ptr(m), _ptr(s), _ptr(r), _ptr(c), _ptr(radii),
-                                                          _ptr(idx), scratch.data_ptr(), slot, ticket, stream),
+                                                          _ptr(idx), scratch.data_ptr(), slot, ticket, lo, hi, stream),
                        "gsvc_rast_visible_filter_compact")
             count = _lib.check(L.gsvc_rast_wait_count(slot, ticket, stream), "gsvc_rast_wait_count")
         return idx[:count], radii

@@ -81,9 +81,14 @@ GSVC_RAST_API size_t gsvc_rast_backward_scratch_bytes(int32_t P); /* per-Gaussia
 /*
  * visible_filter (preprocess.py:99-104): radii[P] int32, 0 = culled (slab / degenerate / off-image).
  * Exactly one of (scales, rotations) or cov3D_precomp ([P,6] xx,xy,xz,yy,yz,zz) must be non-NULL.
+ * [range_lo, range_hi) (slab-ordered anchors): the caller promises that anchors outside this
+ * index range are outside the TSW slab — e.g. anchors kept z-sorted in intervals as the reference's stream codec
+ * stores them (utils/encodings.py:827-862) — and the kernel gives them radius 0 without reading them, so the filter
+ * costs O(slab) reads.  Anchors inside the range get the exact test.  (0, 0) = no range: every anchor is read.
  */
 GSVC_RAST_API int gsvc_rast_visible_filter(const gsvc_rast_settings *st, int32_t P, const float *means3D, const float *scales,
-                             const float *rotations, const float *cov3D_precomp, int32_t *radii, void *stream);
+                             const float *rotations, const float *cov3D_precomp, int32_t *radii, int32_t range_lo,
+                             int32_t range_hi, void *stream);
 
 /*
  * visible_filter fused with the compaction its caller does next: prefilter_voxel returns
@@ -100,7 +105,7 @@ GSVC_RAST_API size_t gsvc_rast_compact_scratch_bytes(int32_t P);
 GSVC_RAST_API int gsvc_rast_visible_filter_compact(const gsvc_rast_settings *st, int32_t P, const float *means3D,
                              const float *scales, const float *rotations, const float *cov3D_precomp, int32_t *radii,
                              int32_t *visible_indices, void *scratch, uint64_t *count_slot_host, uint32_t ticket,
-                             void *stream);
+                             int32_t range_lo, int32_t range_hi, void *stream);
 
 /*
  * Forward, launch form (no host synchronisation): preprocess → tile counting → tile scan →

@@ -59,18 +59,18 @@ def test_abi_version_and_sizes(lib):
 
 
 def test_argument_errors_do_not_need_a_gpu(lib):
-    assert lib.gsvc_rast_visible_filter(None, 10, None, None, None, None, None, None) == _lib.ERR_INVALID
+    assert lib.gsvc_rast_visible_filter(None, 10, None, None, None, None, None, 0, 0, None) == _lib.ERR_INVALID
     assert b"settings" in lib.gsvc_rast_last_error()
     s = _lib.Settings()
     s.image_height, s.image_width = 64, 64
-    assert lib.gsvc_rast_visible_filter(C.byref(s), 10, None, None, None, None, None, None) == _lib.ERR_INVALID
+    assert lib.gsvc_rast_visible_filter(C.byref(s), 10, None, None, None, None, None, 0, 0, None) == _lib.ERR_INVALID
     assert b"viewmatrix" in lib.gsvc_rast_last_error()
     s.viewmatrix = 0x1000   # never dereferenced: argument validation fails first
     s.image_width = 0
-    assert lib.gsvc_rast_visible_filter(C.byref(s), 10, 0x1000, None, None, None, 0x1000, None) == _lib.ERR_INVALID
+    assert lib.gsvc_rast_visible_filter(C.byref(s), 10, 0x1000, None, None, None, 0x1000, 0, 0, None) == _lib.ERR_INVALID
     s.image_width = 64
     # neither (scales, rotations) nor cov3D_precomp
-    assert lib.gsvc_rast_visible_filter(C.byref(s), 10, 0x1000, None, None, None, 0x1000, None) == _lib.ERR_INVALID
+    assert lib.gsvc_rast_visible_filter(C.byref(s), 10, 0x1000, None, None, None, 0x1000, 0, 0, None) == _lib.ERR_INVALID
     assert b"exactly one" in lib.gsvc_rast_last_error()
     # both colour sources / none
     rc = lib.gsvc_rast_forward_launch(C.byref(s), 10, 0, 0x1000, None, None, 0x1000, 0x1000, 0x1000, None,

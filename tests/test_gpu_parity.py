@@ -497,3 +497,44 @@ def test_visible_filter_compact_equals_nonzero(cuda_device, P):
         np.testing.assert_array_equal(idx.cpu().numpy(), np.nonzero(oracle > 0)[0].astype(np.int32))
         # the gather the reference does with the boolean mask (guassian.py:147-153)
         assert torch.equal(g["means3D"][idx.long()], g["means3D"][ref > 0])
+
+
+def test_visible_filter_slab_index_range(cuda_device):
+    """with z-sorted anchors and the codec-style interval table, the filter restricted to the
+    slab's index range returns exactly the radii (and compacted indices) of the full scan, for several frames, both
+    views, and reads nothing outside the range (poisoned with NaN here)."""
+    from gsvc_b200.frames import CubeGeometry, slab_index_range, synthetic_gaussians, z_interval_table
+    from gsvc_b200.rasterizer import GaussianRasterizationSettings, GaussianRasterizer
+    W, H, F, P, thr = 320, 192, 600, 120000, 0.05
+    geom = CubeGeometry(W, H, F)
+    g = synthetic_gaussians(P, geom, 0, F - 1, threshold=thr, seed=17)        # anchors over the whole cube depth
+    order = torch.argsort(g["means3D"][:, 2], stable=True)
+    g = {k: v[order].contiguous().to(cuda_device) for k, v in g.items()}
+    table = z_interval_table(g["means3D"][:, 2])
+    for frame_id, back in ((5, False), (300, False), (300, True), (597, True)):
+        fr = geom.frame(frame_id)
+        vm = fr.view_matrix_s if back else fr.view_matrix
+        rs = GaussianRasterizationSettings(
+            image_height=H, image_width=W, x_min=fr.x_min, y_min=fr.y_min, scale=fr.scale, threshold=thr,
+            bg=torch.zeros(3, device=cuda_device), scale_modifier=1.0, viewmatrix=vm.permute(1, 0).to(cuda_device),
+            sh_degree=0, campos=fr.cam_pos, prefiltered=False, debug=False)
+        rast = GaussianRasterizer(raster_settings=rs)
+        full = rast.visible_filter(means3D=g["means3D"], scales=g["scales"], rotations=g["rotations"], cov3D_precomp=None)
+        lo, hi = slab_index_range(table, fr.z, thr)
+        assert 0 <= lo < hi <= P and (hi - lo) < 0.35 * P                   # the slab is a fraction of the cube
+        poisoned = {k: v.clone() for k, v in g.items()}
+        for k in ("means3D", "scales", "rotations"):
+            poisoned[k][:lo] = float("nan")
+            poisoned[k][hi:] = float("nan")
+        part = rast.visible_filter(means3D=poisoned["means3D"], scales=poisoned["scales"], rotations=poisoned["rotations"],
+                                   cov3D_precomp=None, index_range=(lo, hi))
+        assert torch.equal(part, full) and int((full > 0).sum()) > 0
+        idx, radii = rast.visible_filter_compact(means3D=poisoned["means3D"], scales=poisoned["scales"],
+                                                 rotations=poisoned["rotations"], index_range=(lo, hi))
+        assert torch.equal(radii, full) and torch.equal(idx.long(), torch.nonzero(full > 0).flatten())
+    none = rast.visible_filter(means3D=g["means3D"], scales=g["scales"], rotations=g["rotations"], cov3D_precomp=None,
+                               index_range=(7, 7))
+    assert int(none.abs().sum()) == 0
+    with pytest.raises(Exception):
+        rast.visible_filter(means3D=g["means3D"], scales=g["scales"], rotations=g["rotations"], cov3D_precomp=None,
+                            index_range=(10, P + 1))
