@@ -32,6 +32,25 @@ _F32 = torch.float32
 _SHARED_FIELDS = ("image_height", "image_width", "x_min", "y_min", "scale", "threshold", "scale_modifier", "sh_degree")
 
 
+_bg_checked: dict = {}
+
+
+def _same_bg(a, b) -> bool:
+    """Background colours of two settings are equal.  Distinct CUDA tensors are compared once per pair of storages
+    (a device→host read); the reference keeps ONE background tensor for all its views (pipeline/train.py:328)."""
+    if a is b:
+        return True
+    ta, tb = torch.as_tensor(a), torch.as_tensor(b)
+    if ta.is_cuda or tb.is_cuda:
+        key = (ta.data_ptr(), tb.data_ptr(), ta._version, tb._version)
+        if key not in _bg_checked:
+            if len(_bg_checked) > 256:
+                _bg_checked.clear()
+            _bg_checked[key] = ta.detach().cpu().reshape(-1).tolist() == tb.detach().cpu().reshape(-1).tolist()
+        return _bg_checked[key]
+    return torch.equal(ta.float(), tb.float())
+
+
 class ViewBatch:
     """The views of one batched call: their settings plus where each view's image goes.
 
@@ -51,7 +70,7 @@ class ViewBatch:
                 if getattr(rs, f) != getattr(first, f):
                     raise RasterizerError(f"views of a batch must share `{f}`: view 0 has {getattr(first, f)!r}, "
                                           f"view {i} has {getattr(rs, f)!r}")
-            if rs.bg is not first.bg and not torch.equal(torch.as_tensor(rs.bg).cpu(), torch.as_tensor(first.bg).cpu()):
+            if not _same_bg(rs.bg, first.bg):
                 raise RasterizerError("views of a batch must share the background colour")
         self.settings = list(settings)
         self.out_image = list(range(V)) if out_image is None else [int(o) for o in out_image]
