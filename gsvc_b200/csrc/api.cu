@@ -70,6 +70,8 @@ static int make_settings_views(const gsvc_rast_settings* st, int n_views, const 
     d.gx = (d.W + TILE - 1) / TILE; d.gy = (d.H + TILE - 1) / TILE;
     if (d.gx > 65535 || d.gy > 65535) return fail(GSVC_RAST_ERR_INVALID, "image too large for 16-bit tile coordinates");
     if ((long long)d.gx * d.gy * n_views > 0x7fffffffll) return fail(GSVC_RAST_ERR_INVALID, "too many tiles");
+    if ((long long)d.gx * d.gy > (1ll << 24))   // warp_tiles_get divides tile counts in fp32 (exact below 2^24)
+        return fail(GSVC_RAST_ERR_INVALID, "image has more than 2^24 tiles");
     d.x_min = st->x_min; d.y_min = st->y_min; d.scale = st->scale; d.threshold = st->threshold;
     d.scale_modifier = st->scale_modifier;
     d.bg = st->bg;

@@ -230,8 +230,13 @@ __device__ __forceinline__ int warp_tiles_get(const WarpTiles& w, int idx, int g
     const int rx = __shfl_sync(0xffffffffu, w.rx, o), ry = __shfl_sync(0xffffffffu, w.ry, o);
     owner = o;
     if (idx >= w.total) return -1;
-    const int row = local / rw;
-    return (ry + row) * gx + rx + (local - row * rw);
+    // row = local / rw without the ~30-instruction signed integer division: approximate quotient in fp32
+    // (local < 2^24, rw < 2^16 for any image this library accepts), then one exact correction step
+    int row = __float2int_rz(__fdividef(__int2float_rz(local), __int2float_rz(rw)));
+    int rem = local - row * rw;
+    if (rem < 0) { row--; rem += rw; }
+    else if (rem >= rw) { row++; rem -= rw; }
+    return (ry + row) * gx + rx + rem;
 }
 
 // ---- launch stages implemented in the .cu files ------------------------------------------------
