@@ -165,24 +165,33 @@ class _RasterizeViews(torch.autograd.Function):
             radii = torch.empty((V, P), dtype=torch.int32, device=device)
             stream = _stream_ptr(device)
             slot, ticket = _count_slot()
-            _lib.check(L.gsvc_rast_forward_views_launch(
-                nv.ref, V, nv.views, n_out, P, sh_M, _ptr(means3D_c), _ptr(sh_c), _ptr(col_c), _ptr(op_c), _ptr(sc_c),
-                _ptr(rot_c), _ptr(cov_c), geom_p, image_p, bin_p, cap, acc_p, color.data_ptr(), radii.data_ptr(), slot,
-                ticket, stream), "gsvc_rast_forward_views_launch")
-            if capturing:
-                num_rendered = hint
-            else:
-                num_rendered = _lib.check(L.gsvc_rast_wait_count(slot, ticket, stream), "gsvc_rast_wait_count")
-            if num_rendered > 0xFFFFFFFF:
-                raise RasterizerError(f"num_rendered {num_rendered} exceeds 32-bit tile ranges")
-            if num_rendered > cap or cap == 0:
-                cap = max(num_rendered, 1)
-                binning = _bytes(L.gsvc_rast_binning_bytes(cap), device)
-                bin_p = binning.data_ptr()
-                _lib.check(L.gsvc_rast_forward_views_render(nv.ref, V, nv.views, n_out, P, geom_p, image_p, bin_p, cap,
-                                                            color.data_ptr(), stream), "gsvc_rast_forward_views_render")
-            if not capturing:
-                R._capacity_hint[hint_key] = num_rendered
+            try:
+                _lib.check(L.gsvc_rast_forward_views_launch(
+                    nv.ref, V, nv.views, n_out, P, sh_M, _ptr(means3D_c), _ptr(sh_c), _ptr(col_c), _ptr(op_c), _ptr(sc_c),
+                    _ptr(rot_c), _ptr(cov_c), geom_p, image_p, bin_p, cap, acc_p, color.data_ptr(), radii.data_ptr(), slot,
+                    ticket, stream), "gsvc_rast_forward_views_launch")
+                if capturing:
+                    num_rendered = hint
+                else:
+                    num_rendered = _lib.check(L.gsvc_rast_wait_count(slot, ticket, stream), "gsvc_rast_wait_count")
+                if num_rendered > 0xFFFFFFFF:
+                    raise RasterizerError(f"num_rendered {num_rendered} exceeds 32-bit tile ranges")
+                if num_rendered > cap or cap == 0:
+                    cap = max(num_rendered, 1)
+                    binning = _bytes(L.gsvc_rast_binning_bytes(cap), device)
+                    bin_p = binning.data_ptr()
+                    _lib.check(L.gsvc_rast_forward_views_render(nv.ref, V, nv.views, n_out, P, geom_p, image_p, bin_p, cap,
+                                                                color.data_ptr(), stream), "gsvc_rast_forward_views_render")
+                if not capturing:
+                    R._capacity_hint[hint_key] = num_rendered
+
+            except Exception:
+                if rs.debug:   # upstream behaviour of the single-view call (snapshot for debugging)
+                    torch.save((means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                                [tuple(x) for x in batch.settings], batch.out_image, batch.flip_x, batch.weight),
+                               "snapshot_fw.dump")
+                    print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+                raise
 
         ctx.batch, ctx.nv = batch, nv
         ctx.num_rendered, ctx.sh_M, ctx.capacity = num_rendered, sh_M, cap
