@@ -2,7 +2,7 @@
 size and images smaller than a tile), Gaussian counts, densities (bucket sizes across every sort path: <=32, 64,
 128, 256, 512 per warp, CTA-wide shared, in-place global), views, backgrounds, scale modifiers; single calls through
 the records of the stage exports (bit-exact), images (1e-5 off fragile pixels), gradients (1e-4 relative), and the
-same scenes through the batched-view path.  Usage: python scripts/fuzz_parity.py [n_cases=40] [seed=0]"""
+same scenes through the batched-view path.  Usage: python tests/fuzz_parity.py [n_cases=40] [seed=0]"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np

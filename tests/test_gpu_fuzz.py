@@ -1,4 +1,4 @@
-"""A slice of the randomised parity sweep (scripts/fuzz_parity.py; 640 cases recorded in profiles/r2_fuzz_parity.txt)
+"""A slice of the randomised parity sweep (tests/fuzz_parity.py; 640 cases recorded in profiles/r2_fuzz_parity.txt)
 as a regular GPU test: random sizes / densities / views against the C oracle, integer stages bit-exact."""
 import pytest
 
@@ -6,6 +6,6 @@ pytestmark = pytest.mark.gpu
 
 
 def test_fuzz_slice(cuda_device):
-    from scripts.fuzz_parity import run
+    from tests.fuzz_parity import run
     worst = run(n_cases=30, seed=7, verbose=False)
     assert worst["fwd"] <= 1e-5 and worst["grad"] <= 1e-4
