@@ -386,16 +386,15 @@ def run_product_arm(args, rank, local_rank, world):
 
     # ---- the reference's own FPS convention (utils/report_utils.py:297-319): per frame, synchronize, time.time(),
     # render front, render back, flip, average, clamp, synchronize — here the two renders are one render_toast call
-    from gsvc_b200.views import render_toast
     ref_style = []
     with torch.no_grad():
         for i in range(args.steps + 5):
             torch.cuda.synchronize(device)
             t0 = time.perf_counter()
-            img, _, _ = render_toast(front, back, means3D=params["means3D"], opacities=params["opacities"],
-                                     colors_precomp=params["colors_precomp"], scales=params["scales"],
-                                     rotations=params["rotations"])
-            img = torch.clamp(img, min=0, max=1.0)
+            img, _, _ = rasterize_views(toast, means3D=params["means3D"], opacities=params["opacities"],
+                                        colors_precomp=params["colors_precomp"], scales=params["scales"],
+                                        rotations=params["rotations"])
+            img = torch.clamp(img[0], min=0, max=1.0)
             torch.cuda.synchronize(device)
             if i >= 5:
                 ref_style.append(time.perf_counter() - t0)

@@ -82,6 +82,15 @@ class ViewBatch:
         self.n_out = max(self.out_image) + 1
         if sorted(set(self.out_image)) != list(range(self.n_out)):
             raise RasterizerError("out_image must cover 0..n_out-1 without gaps")
+        self._native = {}
+
+    def native(self, device) -> "_NativeViews":
+        """The C structs of this batch on `device` (built once; a ViewBatch is immutable after construction and the
+        view-matrix / background tensors it points into are kept alive by it)."""
+        nv = self._native.get(device)
+        if nv is None:
+            nv = self._native[device] = _NativeViews(self, device)
+        return nv
 
     @classmethod
     def toast(cls, front: GaussianRasterizationSettings, back: GaussianRasterizationSettings) -> "ViewBatch":
@@ -128,7 +137,7 @@ class _RasterizeViews(torch.autograd.Function):
         rs = batch.settings[0]
         V, n_out = batch.n_views, batch.n_out
         with torch.cuda.device(device):
-            nv = _NativeViews(batch, device)
+            nv = batch.native(device)
             P = means3D.shape[0]
             means3D_c = _dev_f32(means3D, device, "means3D")
             sh_c = _dev_f32(sh, device, "shs") if sh.numel() else None
