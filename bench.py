@@ -190,7 +190,7 @@ def run_reference_arm(args, rank, world):
             "config": {"workload": WORKLOAD, "sampled_ms_per_step": ms},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -612,12 +612,31 @@ def run_product_arm(args, rank, local_rank, world):
                 "sample": (f"pure-PyTorch oracle, same scene, ONE view: preprocess+binning of all {P} Gaussians, blend "
                            f"fwd+bwd on {ns} of {Tt} tiles (every {stride}th) took {total:.2f} s; blend part scaled "
                            f"x{Tt / ns:.1f} to a whole view = {full:.1f} s")}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE line, the JSON: everything else that writes to file descriptor 1 (NCCL's version
+    banner, library chatter) is sent to stderr, and the JSON line goes to a private duplicate of the original fd."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
