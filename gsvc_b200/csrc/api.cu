@@ -160,6 +160,14 @@ int64_t gsvc_rast_launch_count(int32_t reset)
     return reset ? g_launches.exchange(0) : g_launches.load();
 }
 
+int64_t gsvc_rast_overflow_events(int32_t reset, void* stream_)
+{
+    unsigned int v = 0u;
+    cudaError_t e = read_overflow_events(&v, reset != 0, static_cast<cudaStream_t>(stream_));
+    if (e != cudaSuccess) return fail(GSVC_RAST_ERR_CUDA, "overflow_events: %s", cudaGetErrorString(e));
+    return (int64_t)v;
+}
+
 int gsvc_rast_stage_timing(int32_t enable)
 {
     if (enable && !g_ev_made) {

@@ -101,6 +101,24 @@ cudaError_t launch_tile_scan(const DevSettings& s, ImageView im, unsigned long l
 // before it consumes the first result: a warp needs ~(pairs / 128) round trips, whatever the rectangle sizes.
 constexpr int SCATTER_ILP = 4;
 
+// Sticky, process-wide count of scatter launches that ran out of instance capacity (their frames are invalid: the
+// sort and blend kernels skip overflowed tiles).  The eager call notices an overflow from num_rendered and re-runs
+// with a larger buffer; a CUDA-graph replay has nobody to do that, so its owner polls this counter after a
+// synchronisation (gsvc_rast_overflow_events).
+__device__ unsigned int g_overflow_events = 0u;
+
+cudaError_t read_overflow_events(unsigned int* host_value, bool reset, cudaStream_t st)
+{
+    cudaError_t e = cudaMemcpyFromSymbolAsync(host_value, g_overflow_events, sizeof(unsigned int), 0,
+                                              cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && reset) {
+        static const unsigned int zero = 0u;
+        e = cudaMemcpyToSymbolAsync(g_overflow_events, &zero, sizeof(unsigned int), 0, cudaMemcpyHostToDevice, st);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    return e;
+}
+
 __global__ void __launch_bounds__(256) scatter_kernel(int P, int gx, int Tv, GeomView geo, ImageView im, BinView bin,
                                                       unsigned long long cap)
 {
@@ -135,10 +153,11 @@ __global__ void __launch_bounds__(256) scatter_kernel(int P, int gx, int Tv, Geo
         for (int u = 0; u < SCATTER_ILP; u++) {
             if (tile[u] >= 0) {
                 const unsigned long long sl = (unsigned long long)im.tile_offset[tile[u]] + slot[u];
-                if (sl < cap)
+                if (sl < cap) {
                     bin.inst[sl] = it[u];
-                else
-                    im.hdr->overflow = 1u;
+                } else if (atomicExch(&im.hdr->overflow, 1u) == 0u) {
+                    atomicAdd(&g_overflow_events, 1u);     // once per overflowed launch
+                }
             }
         }
     }

@@ -288,6 +288,8 @@ cudaError_t launch_export_keys(const DevSettings& s, ImageView im, BinView b, lo
 cudaError_t launch_export_geom(int P, GeomView g, float* depth, float* xy, float* conic_opacity, float* rgb,
                                int32_t* rect, cudaStream_t st);
 
+cudaError_t read_overflow_events(unsigned int* host_value, bool reset, cudaStream_t st);
+
 void count_launch(int n = 1);
 
 }  // namespace gsvc

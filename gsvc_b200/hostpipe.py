@@ -186,6 +186,8 @@ class HostStepPipeline:
         """After a synchronisation: did the instance capacity of the captured graphs hold the last replayed step?
         (False: call `recapture()`; the gradients of that step are invalid.)"""
         from . import rasterizer as R
+        if R.overflow_events(self.device) > 0:
+            return False
         batch = rast if isinstance(rast, ViewBatch) else None
         rs = batch.settings[0] if batch is not None else rast.raster_settings
         return R.captured_capacity_ok(self.device, self.P, int(rs.image_height), int(rs.image_width),

@@ -65,6 +65,15 @@ def captured_capacity_ok(device, P: int, H: int, W: int, n_views: Optional[int] 
     return cap is None or last_num_rendered() <= cap
 
 
+def overflow_events(device=None, reset: bool = True) -> int:
+    """How many rasterizer launches on `device` ran out of instance capacity since the last reset (synchronises the
+    current stream).  Only CUDA-graph replays can be affected: the eager call re-runs by itself."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    with torch.cuda.device(device):
+        return _lib.check(_lib.lib().gsvc_rast_overflow_events(1 if reset else 0, _stream_ptr(device)),
+                          "gsvc_rast_overflow_events")
+
+
 class _PackedTarget:
     buf = None  # process-wide on purpose: autograd runs backward on its own thread
 

@@ -249,6 +249,11 @@ GSVC_RAST_API int gsvc_rast_export_image(const gsvc_rast_settings *st, int32_t n
 GSVC_RAST_API int gsvc_rast_stage_timing(int32_t enable);
 GSVC_RAST_API int gsvc_rast_stage_times(float *ms_host);
 
+/* Launches (all threads, current device) whose instance capacity was exceeded since the last reset: their output
+ * is invalid.  The eager forward detects this from num_rendered and re-runs; the owner of a CUDA-graph replay polls
+ * this instead.  Synchronises `stream`. */
+GSVC_RAST_API int64_t gsvc_rast_overflow_events(int32_t reset, void *stream);
+
 /* Number of kernel launches issued by this library (all threads) since the last reset
  * (bench.py reports it as gpu_launches). */
 GSVC_RAST_API int64_t gsvc_rast_launch_count(int32_t reset);

@@ -538,3 +538,35 @@ def test_visible_filter_slab_index_range(cuda_device):
     with pytest.raises(Exception):
         rast.visible_filter(means3D=g["means3D"], scales=g["scales"], rotations=g["rotations"], cov3D_precomp=None,
                             index_range=(10, P + 1))
+
+
+def test_graph_replay_detects_capacity_overflow(cuda_device):
+    """A replayed graph has a fixed instance capacity; when in-place parameter updates make the frame need more, the
+    sticky device-side overflow counter reports it (capacity_ok() False) and a re-capture makes the step valid again."""
+    from gsvc_b200 import rasterizer
+    from gsvc_b200.graphed import GraphedStep
+    from gsvc_b200.rasterizer import GaussianRasterizer
+    scene = make_scene(P=20000, W=256, H=160, F=256, seed=61)
+    rast = GaussianRasterizer(raster_settings=product_settings(scene, cuda_device))
+    params = {k: v.to(cuda_device).clone() for k, v in scene["gaussians"].items()}
+    rasterizer.overflow_events(cuda_device)                       # clear whatever earlier tests left
+    step = GraphedStep(rast, params, None)
+    step()
+    torch.cuda.synchronize()
+    assert step.capacity_ok()
+    n0 = step.num_rendered()
+    with torch.no_grad():
+        params["scales"].mul_(8.0)                                # every splat now covers ~64x the tiles
+    step()
+    torch.cuda.synchronize()
+    assert step.num_rendered() > 1.5 * n0 + 65536
+    assert not step.capacity_ok()                                 # ... and the counter is reset by the check
+    step.recapture()
+    color, radii, _ = step()
+    torch.cuda.synchronize()
+    assert step.capacity_ok()
+    with torch.no_grad():
+        ref, ref_radii, n = rast(means3D=params["means3D"], means2D=params["means3D"], shs=None,
+                                 colors_precomp=params["colors_precomp"], opacities=params["opacities"],
+                                 scales=params["scales"], rotations=params["rotations"], cov3D_precomp=None)
+    assert n == step.num_rendered() and torch.equal(color, ref) and torch.equal(radii, ref_radii)
