@@ -42,13 +42,16 @@ struct DevSettings {
 };
 
 // ---- per-Gaussian state ("geom") -------------------------------------------------------------
-//  feat0 = (pix.x, pix.y, 0, 0)
+//  feat0 = (pix.x, pix.y, B/A, B/C)   (the ratios steer the blend kernels' exact sub-tile culling)
 //  feat1 = (conic.A, conic.B, conic.C, opacity)      feat2 = (r, g, b, view depth)
+//  feat3 = (l11, l21, l22, opacity): Cholesky factor of the conic times log2(e)/2 — what the blend kernels evaluate:
+//          alpha = opacity * 2^-((l11 dx + l21 dy)^2 + (l22 dy)^2)
 //  rect  = tile rectangle (minx, miny, maxx, maxy), max exclusive; all-zero when culled
 struct GeomView {
     float4* feat0;
     float4* feat1;
     float4* feat2;
+    float4* feat3;
     ushort4* rect;
     uint8_t* clamped;  // [P,3], SH clamp flags (only when shs are given)
 };
@@ -95,6 +98,7 @@ inline GeomView geom_view(void* buf, int P, int sh_M)
     g.feat0 = carve<float4>(p, P);
     g.feat1 = carve<float4>(p, P);
     g.feat2 = carve<float4>(p, P);
+    g.feat3 = carve<float4>(p, P);
     g.rect = carve<ushort4>(p, P);
     g.clamped = sh_M > 0 ? carve<uint8_t>(p, (size_t)P * 3) : nullptr;
     return g;
@@ -102,7 +106,7 @@ inline GeomView geom_view(void* buf, int P, int sh_M)
 inline size_t geom_bytes(int P, int sh_M)
 {
     char* p = nullptr;
-    carve<float4>(p, P); carve<float4>(p, P); carve<float4>(p, P); carve<ushort4>(p, P);
+    carve<float4>(p, P); carve<float4>(p, P); carve<float4>(p, P); carve<float4>(p, P); carve<ushort4>(p, P);
     if (sh_M > 0) carve<uint8_t>(p, (size_t)P * 3);
     return (size_t)p + 256;
 }

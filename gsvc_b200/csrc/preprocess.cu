@@ -307,7 +307,20 @@ __global__ void __launch_bounds__(256) preprocess_kernel(DevSettings s, PreInput
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
             acc_to_zero[3 * gv] = z; acc_to_zero[3 * gv + 1] = z; acc_to_zero[3 * gv + 2] = z;
         }
-        geo.feat0[gv] = make_float4(px, py, 0.f, 0.f);   // .zw: scratch of the blend kernels' staging (B/A, B/C)
+        // What the blend kernels evaluate: the Cholesky factor L of the STORED conic (A, B; B, C) times log2(e)/2,
+        //   alpha = op * 2^-((l11 dx + l21 dy)^2 + (l22 dy)^2),
+        // a sum of squares where A dx^2 + B dx dy + C dy^2 cancels.  The Schur complement C - B^2/A itself cancels
+        // for an elongated, rotated Gaussian (B^2 ~ A C): it comes from A C - B^2 with the products' rounding errors
+        // recovered by FMAs (two-product), so L represents the quadratic form of exactly these three fp32 numbers to
+        // fp32 relative accuracy — which is what the reference evaluates.
+        const float kL = 0.5f * 1.4426950408889634f;
+        const float pac = cA * cC, pbb = cB * cB;
+        const float det_c = (pac - pbb) + (fmaf(cA, cC, -pac) - fmaf(cB, cB, -pbb));
+        const float aL = cA * kL;
+        const float r11 = rsqrtf(aL);                          // A > 0: cov2D is positive definite (+0.3 on the diagonal)
+        const float d22 = fmaxf(__fdividef(det_c, cA) * kL, 1e-30f);
+        geo.feat0[gv] = make_float4(px, py, __fdividef(cB, cA), __fdividef(cB, cC));   // culling aids: approximate is fine
+        geo.feat3[gv] = make_float4(aL * r11, (cB * kL) * r11, d22 * rsqrtf(d22), op);
         geo.feat1[gv] = make_float4(cA, cB, cC, op);
         geo.feat2[gv] = make_float4(rgb[0], rgb[1], rgb[2], vz);
         geo.rect[gv] = make_ushort4((unsigned short)rminx, (unsigned short)rminy, (unsigned short)rmaxx,

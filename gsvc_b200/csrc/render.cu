@@ -100,12 +100,17 @@ __device__ __forceinline__ f2 sub2(f2 a, f2 b)
 }
 __device__ __forceinline__ f2 neg2(f2 a) { return mk2(-lo(a), -hi(a)); }
 
-// log2 of the falloff of one staged Gaussian at this lane's two pixels:
-//   q = A' dx^2 + B' dx dy + C' dy^2 = (A' dx) dx + dy (B' dx + C' dy)      (dx is shared: same column)
-__device__ __forceinline__ f2 falloff_log2(const float4 f1, float dx, f2 dy2)
+// MINUS the log2 of the falloff of one staged Gaussian at this lane's two pixels, as a sum of squares:
+//   -q = (l11 dx + l21 dy)^2 + (l22 dy)^2,   L = Cholesky factor of the conic scaled by log2(e)/2
+// (dx is shared: same column).  Unlike A dx^2 + B dx dy + C dy^2 nothing cancels — for a needle-like Gaussian far
+// from its centre those three terms are ~1e2 each and sum to ~1, which costs ~1e-5 of absolute accuracy in fp32 —
+// and -q >= 0 holds by construction, so the reference's `power > 0 -> continue` (only ever taken through rounding)
+// needs no test.
+__device__ __forceinline__ f2 neg_falloff_log2(const float4 f1, float dx, f2 dy2)
 {
-    const float t = f1.x * dx;
-    return fma2(dy2, fma2(bc2(f1.z), dy2, bc2(f1.y * dx)), bc2(t * dx));
+    const f2 u2 = fma2(bc2(f1.y), dy2, bc2(f1.x * dx));
+    const f2 v2 = mul2(bc2(f1.z), dy2);
+    return fma2(u2, u2, mul2(v2, v2));
 }
 
 struct BlockGeom {
@@ -128,22 +133,18 @@ __device__ __forceinline__ BlockGeom block_geom(int tile, int gx, int tid)
 
 // Staged record k = s_feat[3k .. 3k+2]:
 //   [0] = (pix.x, pix.y, B/A, B/C)
-//   [1] = (A', B', C', opacity) with A' = -A log2e/2, B' = -B log2e, C' = -C log2e/2, so that
-//         alpha = opacity * 2^q(d),  q(d) = A' dx^2 + B' dx dy + C' dy^2  (q <= 0, concave)
+//   [1] = (l11, l21, l22, opacity): Cholesky factor of (A, B; B, C) * log2(e)/2, so that
+//         alpha = opacity * 2^q(d),  -q(d) = (l11 dx + l21 dy)^2 + (l22 dy)^2
 //   [2] = (r, g, b, Gaussian id as bits)
 constexpr float CULL_MARGIN = 1e-3f;  // in log2 units (7e-4 relative in alpha) >> fp32 rounding of q
 
 __device__ __forceinline__ void stage(float4* s_feat, int slot, const GeomView& geo, unsigned int id)
 {
-    float4 f0 = __ldg(geo.feat0 + id);
-    float4 f1 = __ldg(geo.feat1 + id);
+    // everything was prepared per Gaussian by the preprocess kernel: three 16-byte gathers, no arithmetic
+    const float4 f0 = __ldg(geo.feat0 + id);
+    const float4 f1 = __ldg(geo.feat3 + id);
     float4 f2 = __ldg(geo.feat2 + id);
-    f0.z = __fdividef(f1.y, f1.x);
-    f0.w = __fdividef(f1.y, f1.z);
     f2.w = __uint_as_float(id);   // rides along with the colour: the backward's atomics need it per hit
-    f1.x *= -0.5f * LOG2E;
-    f1.y *= -LOG2E;
-    f1.z *= -0.5f * LOG2E;
     s_feat[3 * slot] = f0;
     s_feat[3 * slot + 1] = f1;
     s_feat[3 * slot + 2] = f2;
@@ -164,9 +165,10 @@ __device__ __forceinline__ bool block_hit(const BlockGeom& b, const float4* e)
     const float dxe = ex - f0.x, dye = ey - f0.y;
     const float dy1 = fminf(fmaxf(fmaf(-f0.w, dxe, f0.y), b.ymin), b.ymax) - f0.y;
     const float dx2 = fminf(fmaxf(fmaf(-f0.z, dye, f0.x), b.xmin), b.xmax) - f0.x;
-    const float q1 = fmaf(fmaf(f1.x, dxe, f1.y * dy1), dxe, (f1.z * dy1) * dy1);
-    const float q2 = fmaf(fmaf(f1.x, dx2, f1.y * dye), dx2, (f1.z * dye) * dye);
-    return fmaxf(q1, q2) >= thr;
+    const float u1 = fmaf(f1.x, dxe, f1.y * dy1), v1 = f1.z * dy1;
+    const float u2 = fmaf(f1.x, dx2, f1.y * dye), v2 = f1.z * dye;
+    const float nq1 = fmaf(u1, u1, v1 * v1), nq2 = fmaf(u2, u2, v2 * v2);   // -q at the two candidates
+    return -fminf(nq1, nq2) >= thr;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -228,13 +230,13 @@ render_forward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, un
                 const float4 f0 = e[0];
                 const float4 f1 = e[1];
                 const float4 f2v = e[2];
-                const f2 q2 = falloff_log2(f1, f0.x - pxf, add2(bc2(f0.y), npy2));
-                const float qA = lo(q2), qB = hi(q2);
-                const f2 a2 = mul2(bc2(f1.w), mk2(ex2_approx(qA), ex2_approx(qB)));
+                const f2 nq2 = neg_falloff_log2(f1, f0.x - pxf, add2(bc2(f0.y), npy2));
+                const f2 a2 = mul2(bc2(f1.w), mk2(ex2_approx(-lo(nq2)), ex2_approx(-hi(nq2))));
                 const float aA = fminf(ALPHA_MAX, lo(a2)), aB = fminf(ALPHA_MAX, hi(a2));
-                // the reference `continue`s on power > 0 and on alpha < 1/255 (and never gets here once done)
-                const bool okA = !(qA > 0.f) && !(aA < minA);
-                const bool okB = !(qB > 0.f) && !(aB < minB);
+                // the reference `continue`s on alpha < 1/255 (power > 0 cannot happen here; a finished pixel's
+                // floor is unreachable)
+                const bool okA = !(aA < minA);
+                const bool okB = !(aB < minB);
                 const unsigned int pos = pos1 + (unsigned int)k;
                 const f2 ac = mk2(aA, aB), T2 = mk2(TA, TB);
                 const f2 tT2 = mul2(T2, sub2(bc2(1.f), ac));
@@ -439,14 +441,13 @@ render_backward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, c
                 const float4 f2v = e[2];
                 const float dx = f0.x - pxf;
                 const f2 dy2 = add2(bc2(f0.y), npy2);
-                const f2 q2 = falloff_log2(f1, dx, dy2);
-                const float qA = lo(q2), qB = hi(q2);
-                const f2 Gs2 = mk2(ex2_approx(qA), ex2_approx(qB));
+                const f2 nq2 = neg_falloff_log2(f1, dx, dy2);
+                const f2 Gs2 = mk2(ex2_approx(-lo(nq2)), ex2_approx(-hi(nq2)));
                 const f2 a2 = mul2(bc2(f1.w), Gs2);
                 const float aA = fminf(ALPHA_MAX, lo(a2)), aB = fminf(ALPHA_MAX, hi(a2));
                 const unsigned int pos = (unsigned int)(pos0 - k);
-                const bool useA = (pos < S.lastA) && !(qA > 0.f) && !(aA < ALPHA_MIN);
-                const bool useB = (pos < S.lastB) && !(qB > 0.f) && !(aB < ALPHA_MIN);
+                const bool useA = (pos < S.lastA) && !(aA < ALPHA_MIN);
+                const bool useB = (pos < S.lastB) && !(aB < ALPHA_MIN);
                 // (no warp vote here: after the exact culling above 99.9 % of the evaluations that reach this point
                 //  contribute to at least one pixel — ncu source counters — and a pair that does not adds zeros)
 

@@ -311,7 +311,12 @@ void orc_tile_ranges(int64_t R, const uint64_t *sorted_keys, int n_tiles, uint32
 
 /*
  * A.3 forward blend.  out_color [3,H,W]; final_T, n_contrib [H,W].
- * fragile[H*W] (optional): set to 1 for pixels where a discontinuous decision
+ * fragile[H*W] (optional): set to 1 for pixels where this arithmetic is itself ambiguous at the
+ * 1e-5 level: (i) the exponent is ill-conditioned — `power` is a sum of three terms that can be
+ * ~1e2..1e4 each and cancel to ~1 for a needle-like Gaussian far from its centre, so ANY fp32
+ * evaluation order (this one, the reference's FMA-contracted CUDA, a sum-of-squares form) carries
+ * eps * sum|terms| of rounding noise; the flag is set when the first-order bound
+ * eps * sum_k alpha_k T_k S_k (S_k = sum of |terms| of power_k) exceeds 2.5e-6; (ii) a discontinuous decision
  * (alpha floor, T stop, power>0) was within `frag_eps` relative of flipping —
  * two correct fp32 implementations may legitimately disagree there.
  */
@@ -329,6 +334,7 @@ void orc_render_forward(const orc_settings *st, const uint32_t *ranges, const ui
             float T = 1.f, C[3] = {0.f, 0.f, 0.f};
             uint32_t last = 0, n = 0;
             uint8_t frag = 0;
+            double cond = 0.0;   /* sum_k alpha_k T_k S_k: sensitivity of the pixel to rounding in the exponents */
             float pxf = (float)i, pyf = (float)j;
             for (uint32_t k = s; k < e; k++) {
                 n++;
@@ -344,10 +350,13 @@ void orc_render_forward(const orc_settings *st, const uint32_t *ranges, const ui
                 float test_T = T * (1.f - alpha);
                 if (fabsf(test_T - T_STOP) <= frag_eps * T_STOP) frag = 1;
                 if (test_T < T_STOP) break;
+                cond += (double)(alpha * T) * (0.5 * (fabs((double)co[0] * dx * dx) + fabs((double)co[2] * dy * dy)) +
+                                               fabs((double)co[1] * dx * dy));
                 for (int c = 0; c < 3; c++) C[c] += rgb[3 * g + c] * alpha * T;
                 T = test_T;
                 last = n;
             }
+            if (cond * 1.1920929e-7 > 2.5e-6) frag = 1;
             size_t pix = (size_t)j * W + i;
             for (int c = 0; c < 3; c++) out_color[(size_t)c * H * W + pix] = C[c] + T * st->bg[c];
             final_T[pix] = T;
@@ -361,8 +370,10 @@ void orc_render_forward(const orc_settings *st, const uint32_t *ranges, const ui
  * A.4 backward blend: dL/dout [3,H,W] → per-Gaussian dL/dpix (2), dL/dconic (3:
  * A, B, Cc with the full -Gs*dx*dy*dL/dGs for B), dL/dopacity, dL/drgb (3).
  * Accumulators are double so the oracle value does not depend on pixel order.
- * touched[g] (optional) is set when g contributes to a pixel flagged in
- * `fragile` (so tests can exclude Gaussians affected by decision flips).
+ * touched[g] (optional) is set for EVERY Gaussian in the tile list of a pixel flagged in
+ * `fragile` (so tests can exclude Gaussians affected by decision flips): the Gaussian whose
+ * decision is fragile may be one this replay skips (alpha a hair below 1/255, or behind a
+ * fragile stop), and everything behind it sees a different T if the decision flips.
  */
 void orc_render_backward(const orc_settings *st, const uint32_t *ranges, const uint32_t *point_list,
                          const float *xy, const float *conic_opacity, const float *rgb, const float *final_T,
@@ -387,6 +398,13 @@ void orc_render_backward(const orc_settings *st, const uint32_t *ranges, const u
             float bg_dot = st->bg[0] * Gd[0] + st->bg[1] * Gd[1] + st->bg[2] * Gd[2];
             float pxf = (float)i, pyf = (float)j;
             int frag = fragile ? fragile[pix] : 0;
+            if (frag && touched) {
+                uint32_t e = ranges[2 * t + 1];
+                for (uint32_t k = s; k < e; k++) {
+#pragma omp atomic write
+                    touched[point_list[k]] = 1;
+                }
+            }
             for (int64_t k = (int64_t)last - 1; k >= 0; k--) {
                 uint32_t g = point_list[s + k];
                 float dx = xy[2 * g] - pxf, dy = xy[2 * g + 1] - pyf;
@@ -433,7 +451,6 @@ void orc_render_backward(const orc_settings *st, const uint32_t *ranges, const u
                 dL_dconic[3 * g + 2] += cC;
 #pragma omp atomic
                 dL_dopacity[g] += vo;
-                if (frag && touched) touched[g] = 1;
             }
         }
     }
