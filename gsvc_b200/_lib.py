@@ -73,6 +73,7 @@ SIGNATURES = {
     "gsvc_rast_export_keys": (C.c_int, [_SP, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsvc_rast_export_geom": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsvc_rast_export_image": (C.c_int, [_SP, _i32, _vp, _vp, _vp, _vp]),
+    "gsvc_rast_count_overflows": (C.c_int, [_i32]),
     "gsvc_rast_overflow_events": (_i64, [_i32, _vp]),
     "gsvc_rast_launch_count": (_i64, [_i32]),
     "gsvc_rast_stage_timing": (C.c_int, [_i32]),

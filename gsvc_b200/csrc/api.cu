@@ -13,6 +13,9 @@ namespace gsvc {
 static thread_local char g_err[512] = "";
 // process-wide (the backward runs on PyTorch's autograd thread, not on the caller's)
 static std::atomic<long long> g_launches{0};
+// set by the caller around launches it is capturing into a CUDA graph: only those feed the sticky overflow counter
+// (an eager launch that outgrows its capacity is re-run by its caller and must not look like a lost frame)
+static thread_local bool g_count_overflows = false;
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
@@ -133,7 +136,7 @@ static int render_stages(const DevSettings& d, int P, GeomView g, ImageView im, 
                          float* out_color, cudaStream_t stream, bool dbg)
 {
     BinView b = bin_view(binning, cap);
-    { StageScope t(ST_SCATTER, stream); CK(launch_scatter(d, P, g, im, b, cap, stream), "scatter"); }
+    { StageScope t(ST_SCATTER, stream); CK(launch_scatter(d, P, g, im, b, cap, g_count_overflows, stream), "scatter"); }
     { StageScope t(ST_SORT, stream); CK(launch_sort_tiles(d, im, b, cap, stream), "sort_tiles"); }
     { StageScope t(ST_RENDER_FWD, stream); CK(launch_render_forward(d, g, im, b, cap, out_color, stream), "render_forward"); }
     return 0;
@@ -158,6 +161,12 @@ size_t gsvc_rast_backward_scratch_bytes(int32_t P) { return bwd_scratch_bytes(P 
 int64_t gsvc_rast_launch_count(int32_t reset)
 {
     return reset ? g_launches.exchange(0) : g_launches.load();
+}
+
+int gsvc_rast_count_overflows(int32_t enable)
+{
+    g_count_overflows = enable != 0;
+    return 0;
 }
 
 int64_t gsvc_rast_overflow_events(int32_t reset, void* stream_)

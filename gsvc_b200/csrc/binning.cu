@@ -120,7 +120,7 @@ cudaError_t read_overflow_events(unsigned int* host_value, bool reset, cudaStrea
 }
 
 __global__ void __launch_bounds__(256) scatter_kernel(int P, int gx, int Tv, GeomView geo, ImageView im, BinView bin,
-                                                      unsigned long long cap)
+                                                      unsigned long long cap, int count_events)
 {
     pdl_prologue();
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(int P, int gx, int Tv, Geo
                 const unsigned long long sl = (unsigned long long)im.tile_offset[tile[u]] + slot[u];
                 if (sl < cap) {
                     bin.inst[sl] = it[u];
-                } else if (atomicExch(&im.hdr->overflow, 1u) == 0u) {
+                } else if (atomicExch(&im.hdr->overflow, 1u) == 0u && count_events) {
                     atomicAdd(&g_overflow_events, 1u);     // once per overflowed launch
                 }
             }
@@ -164,12 +164,12 @@ __global__ void __launch_bounds__(256) scatter_kernel(int P, int gx, int Tv, Geo
 }
 
 cudaError_t launch_scatter(const DevSettings& s, int P, GeomView g, ImageView im, BinView b, long long cap,
-                           cudaStream_t st)
+                           bool count_overflow_events, cudaStream_t st)
 {
     if (P <= 0) return cudaSuccess;
     count_launch();
     return launch_pdl(scatter_kernel, dim3((P + 255) / 256, s.n_views), dim3(256), st, P, s.gx, s.gx * s.gy, g, im, b,
-                      (unsigned long long)cap);
+                      (unsigned long long)cap, count_overflow_events ? 1 : 0);
 }
 
 // ---- per-tile sort of the 64-bit composites -----------------------------------------------------

@@ -273,7 +273,7 @@ cudaError_t launch_preprocess(const DevSettings& s, const PreInputs& in, int32_t
 cudaError_t launch_tile_scan(const DevSettings& s, ImageView im, unsigned long long* host_slot, unsigned int ticket,
                              cudaStream_t st);
 cudaError_t launch_scatter(const DevSettings& s, int P, GeomView g, ImageView im, BinView b, long long cap,
-                           cudaStream_t st);
+                           bool count_overflow_events, cudaStream_t st);
 cudaError_t launch_sort_tiles(const DevSettings& s, ImageView im, BinView b, long long cap, cudaStream_t st);
 cudaError_t launch_render_forward(const DevSettings& s, GeomView g, ImageView im, BinView b, long long cap,
                                   float* out_color, cudaStream_t st);

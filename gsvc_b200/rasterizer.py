@@ -208,6 +208,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             stream = _stream_ptr(device)
             slot, ticket = _count_slot()
             try:
+                L.gsvc_rast_count_overflows(1 if capturing else 0)   # a replay has nobody to re-run it; eager does
                 _lib.check(L.gsvc_rast_forward_launch(
                     ns.ref, P, sh_M, _ptr(means3D_c), _ptr(sh_c), _ptr(col_c), _ptr(op_c), _ptr(sc_c), _ptr(rot_c),
                     _ptr(cov_c), geom_p, image_p, bin_p, cap, acc_p, color.data_ptr(), radii.data_ptr(), slot, ticket,

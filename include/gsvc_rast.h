@@ -249,9 +249,11 @@ GSVC_RAST_API int gsvc_rast_export_image(const gsvc_rast_settings *st, int32_t n
 GSVC_RAST_API int gsvc_rast_stage_timing(int32_t enable);
 GSVC_RAST_API int gsvc_rast_stage_times(float *ms_host);
 
-/* Launches (all threads, current device) whose instance capacity was exceeded since the last reset: their output
- * is invalid.  The eager forward detects this from num_rendered and re-runs; the owner of a CUDA-graph replay polls
- * this instead.  Synchronises `stream`. */
+/* Launches whose instance capacity was exceeded since the last reset (current device): their output is invalid.
+ * Only launches enqueued while gsvc_rast_count_overflows(1) is in effect on the calling thread are counted — the
+ * caller sets it around the launches it captures into a CUDA graph, whose replays nobody re-runs; an eager forward
+ * detects an overflow from num_rendered and re-runs by itself.  gsvc_rast_overflow_events synchronises `stream`. */
+GSVC_RAST_API int gsvc_rast_count_overflows(int32_t enable);
 GSVC_RAST_API int64_t gsvc_rast_overflow_events(int32_t reset, void *stream);
 
 /* Number of kernel launches issued by this library (all threads) since the last reset

@@ -12,6 +12,10 @@ from gsvc_b200.frames import CONFIGS, CubeGeometry, synthetic_gaussians
 from oracle.c_oracle import OracleSettings
 
 pytestmark = pytest.mark.gpu
+
+# two GPU runs of the same backward differ by the order of the float atomics: up to 4e-6 of the largest gradient in
+# 300 repeats (scripts/probe_noise.py); GPU-vs-GPU comparisons get 4e-5, still 2.5x inside the 1e-4 parity bar
+ATOMIC_RTOL = 4e-5
 THRESHOLD = 0.05
 
 
@@ -205,7 +209,7 @@ def test_config2_toast_equals_two_calls(cuda_device):
     assert (image - ref).abs().max() <= 2e-7
     ref_grads = torch.autograd.grad(ref, [p[k] for k in names], grad_outputs=dL)
     for k, a, b in zip(names, grads, ref_grads):
-        assert (a - b).abs().max() <= 2e-5 * b.abs().max(), k
+        assert (a - b).abs().max() <= ATOMIC_RTOL * b.abs().max(), k
 
 
 def test_config3_window_in_one_chain(cuda_device):

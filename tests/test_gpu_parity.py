@@ -15,6 +15,10 @@ from tests.scenes import make_scene, np_inputs, product_settings
 
 pytestmark = pytest.mark.gpu
 
+# two GPU runs of the same backward differ by the order of the float atomics: up to 4e-6 of the largest gradient in
+# 300 repeats (scripts/probe_noise.py); GPU-vs-GPU comparisons get 4e-5, still 2.5x inside the 1e-4 parity bar
+ATOMIC_RTOL = 4e-5
+
 FWD_ATOL = 1e-5
 GRAD_RTOL = 1e-4
 
@@ -290,7 +294,7 @@ def test_packed_backward_writes_the_allreduce_buffer(cuda_device):
     ref = sharding.pack_grads({k: d for k, d in zip(names, dense)})
     # two backward passes differ in the order of the fp32 atomics, so compare to rounding, not bitwise
     assert not torch.isnan(buf).any()
-    assert (buf - ref).abs().max() <= 1e-5 * ref.abs().max()
+    assert (buf - ref).abs().max() <= ATOMIC_RTOL * ref.abs().max()
     unpacked = sharding.unpack_grads(buf)
     for k, v, d in zip(names, views, dense):
         assert v.shape == d.shape and torch.equal(v, unpacked[k].reshape(d.shape))   # views of the buffer itself
@@ -347,8 +351,8 @@ def test_retain_graph_double_backward_is_consistent(cuda_device):
     b = torch.autograd.grad(color, ins, grad_outputs=dL, retain_graph=True)
     c = torch.autograd.grad(color, ins, grad_outputs=2 * dL)
     for x, y, z in zip(a, b, c):
-        assert (x - y).abs().max() <= 1e-5 * x.abs().max()
-        assert (z - 2 * x).abs().max() <= 1e-5 * z.abs().max()
+        assert (x - y).abs().max() <= ATOMIC_RTOL * x.abs().max()
+        assert (z - 2 * x).abs().max() <= ATOMIC_RTOL * z.abs().max()
 
 
 def test_cuda_graph_capture_and_replay(cuda_device):
@@ -390,7 +394,7 @@ def test_cuda_graph_capture_and_replay(cuda_device):
     assert torch.equal(radii_g, radii_e)
     assert torch.equal(color_g, color_e)               # the forward is deterministic
     for a, b in zip(grads_g, grads_e):
-        assert (a - b).abs().max() <= 1e-5 * b.abs().max()
+        assert (a - b).abs().max() <= ATOMIC_RTOL * b.abs().max()
     assert rasterizer.last_num_rendered() > 0
 
 
@@ -438,7 +442,7 @@ def test_host_step_pipeline_matches_direct_call(cuda_device):
         grads = torch.autograd.grad(color, [p[k] for k, _ in GRAD_LAYOUT], grad_outputs=dL)
         ref = torch.cat([x.reshape(P, -1) for x in grads], dim=1).cpu()
         assert ref.abs().max() > 0
-        assert (packed - ref).abs().max() <= 1e-5 * ref.abs().max()   # atomics order only
+        assert (packed - ref).abs().max() <= ATOMIC_RTOL * ref.abs().max()   # atomics order only
 
 
 def test_graphed_step_matches_eager(cuda_device):
@@ -472,7 +476,7 @@ def test_graphed_step_matches_eager(cuda_device):
         assert torch.equal(color_g, color) and torch.equal(color_f, color)
         assert torch.equal(radii_g, radii) and torch.equal(radii_f, radii)
         ref = torch.cat([x.reshape(P, -1) for x in grads], dim=1)
-        assert (packed - ref).abs().max() <= 1e-5 * ref.abs().max()
+        assert (packed - ref).abs().max() <= ATOMIC_RTOL * ref.abs().max()
 
 
 @pytest.mark.parametrize("P", [1, 255, 256, 257, 50000, 300001])

@@ -11,6 +11,10 @@ from tests.scenes import make_scene, np_inputs, product_settings
 
 pytestmark = pytest.mark.gpu
 
+# two GPU runs of the same backward differ by the order of the float atomics: up to 4e-6 of the largest gradient in
+# 300 repeats (scripts/probe_noise.py); GPU-vs-GPU comparisons get 4e-5, still 2.5x inside the 1e-4 parity bar
+ATOMIC_RTOL = 4e-5
+
 NAMES = ("means3D", "colors_precomp", "opacities", "scales", "rotations")
 
 
@@ -67,11 +71,11 @@ def test_batched_views_equal_single_calls(cuda_device, W, H):
         total += n1
         assert torch.equal(images[v], c1), f"view {v}"
         assert torch.equal(radii[v], r1)
-        assert (grads[-1][v] - g1[-1]).abs().max() <= 1e-5 * g1[-1].abs().max()
+        assert (grads[-1][v] - g1[-1]).abs().max() <= ATOMIC_RTOL * g1[-1].abs().max()
         sums = list(g1[:-1]) if sums is None else [a + b for a, b in zip(sums, g1[:-1])]
     assert n == total
     for k, a, b in zip(NAMES, grads[:-1], sums):
-        assert (a - b).abs().max() <= 2e-5 * b.abs().max(), k
+        assert (a - b).abs().max() <= ATOMIC_RTOL * b.abs().max(), k
 
 
 @pytest.mark.parametrize("W,H", [(160, 96), (150, 90)])
