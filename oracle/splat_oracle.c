@@ -317,8 +317,8 @@ void orc_tile_ranges(int64_t R, const uint64_t *sorted_keys, int n_tiles, uint32
  * evaluation order (this one, the reference's FMA-contracted CUDA, a sum-of-squares form) carries
  * eps * sum|terms| of rounding noise; the flag is set when the first-order bound
  * eps * sum_k alpha_k T_k S_k (S_k = sum of |terms| of power_k) exceeds 2.5e-6; (ii) a discontinuous decision
- * (alpha floor, T stop, power>0) was within `frag_eps` relative of flipping —
- * two correct fp32 implementations may legitimately disagree there.
+ * (alpha floor, T stop, power>0) was within `frag_eps` + the exponent's own rounding bound eps*S_k (relative)
+ * of flipping — two correct fp32 implementations may legitimately disagree there.
  */
 void orc_render_forward(const orc_settings *st, const uint32_t *ranges, const uint32_t *point_list,
                         const float *xy, const float *conic_opacity, const float *rgb, float *out_color,
@@ -335,6 +335,7 @@ void orc_render_forward(const orc_settings *st, const uint32_t *ranges, const ui
             uint32_t last = 0, n = 0;
             uint8_t frag = 0;
             double cond = 0.0;   /* sum_k alpha_k T_k S_k: sensitivity of the pixel to rounding in the exponents */
+            double tamb = 0.0;   /* relative ambiguity of T accumulated from the exponents of the blended Gaussians */
             float pxf = (float)i, pyf = (float)j;
             for (uint32_t k = s; k < e; k++) {
                 n++;
@@ -342,16 +343,24 @@ void orc_render_forward(const orc_settings *st, const uint32_t *ranges, const ui
                 float dx = xy[2 * g] - pxf, dy = xy[2 * g + 1] - pyf;
                 const float *co = conic_opacity + 4 * g;
                 float power = -0.5f * (co[0] * dx * dx + co[2] * dy * dy) - co[1] * dx * dy;
-                if (fabsf(power) < 1e-6f) frag = 1;
+                /* S = sum of |terms| of power: ANY fp32 evaluation of the exponent carries ~eps*S of absolute
+                 * error, i.e. eps*S RELATIVE error in alpha, so every decision below is ambiguous within
+                 * frag_eps + eps*S (needle-like Gaussians far from their centre: S ~ 1e3, eps*S ~ 1e-4) */
+                double S = 0.5 * (fabs((double)co[0] * dx * dx) + fabs((double)co[2] * dy * dy)) +
+                           fabs((double)co[1] * dx * dy);
+                double amb = (double)frag_eps + 1.1920929e-7 * S;
+                if (fabs((double)power) <= 1e-6 + 1.1920929e-7 * S) frag = 1;
                 if (power > 0.f) continue;
                 float alpha = fminf(ALPHA_MAX, co[3] * expf(power));
-                if (fabsf(alpha - ALPHA_MIN) <= frag_eps * ALPHA_MIN) frag = 1;
+                if (fabs((double)alpha - ALPHA_MIN) <= amb * ALPHA_MIN) frag = 1;
                 if (alpha < ALPHA_MIN) continue;
                 float test_T = T * (1.f - alpha);
-                if (fabsf(test_T - T_STOP) <= frag_eps * T_STOP) frag = 1;
+                /* T carries the alphas before it: d(log T) = -sum alpha_k/(1-alpha_k) * d(log alpha_k) */
+                double tamb_k = (alpha < ALPHA_MAX ? (double)alpha / (1.0 - (double)alpha) : 0.0) * 1.1920929e-7 * S;
+                if (fabs((double)test_T - T_STOP) <= ((double)frag_eps + tamb + tamb_k) * T_STOP) frag = 1;
                 if (test_T < T_STOP) break;
-                cond += (double)(alpha * T) * (0.5 * (fabs((double)co[0] * dx * dx) + fabs((double)co[2] * dy * dy)) +
-                                               fabs((double)co[1] * dx * dy));
+                tamb += tamb_k;
+                cond += (double)(alpha * T) * S;
                 for (int c = 0; c < 3; c++) C[c] += rgb[3 * g + c] * alpha * T;
                 T = test_T;
                 last = n;

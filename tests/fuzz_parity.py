@@ -14,6 +14,42 @@ from gsvc_b200.views import ViewBatch, rasterize_views
 
 NAMES = ("means3D", "colors_precomp", "opacities", "scales", "rotations")
 
+def diag_pixel(fo, got, W, bg, note=""):
+    """Print the worst non-fragile pixel of `got` against the oracle forward `fo`, with the same pixel replayed in
+    float64 from the oracle's per-Gaussian state and tile list (who is off, and how well-conditioned it is)."""
+    err = np.abs(got - fo["color"])
+    em = np.where(fo["fragile"][None], 0, err)
+    c_, j_, i_ = np.unravel_index(em.argmax(), em.shape)
+    t_ = (j_ // 16) * ((W + 15) // 16) + i_ // 16
+    rg_ = fo["bin"]["ranges"][t_]
+    pre_, pl_ = fo["pre"], fo["bin"]["point_list"]
+    T64, C64, big = 1.0, np.zeros(3), []
+    for k_ in range(int(rg_[0]), int(rg_[1])):
+        g_ = int(pl_[k_])
+        dx_, dy_ = float(pre_["xy"][g_, 0]) - i_, float(pre_["xy"][g_, 1]) - j_
+        A_, B_, C2_, o_ = [float(v) for v in pre_["conic_opacity"][g_]]
+        terms = (-0.5 * A_ * dx_ * dx_, -0.5 * C2_ * dy_ * dy_, -B_ * dx_ * dy_)
+        pw = sum(terms)
+        if pw > 0:
+            print(f"   skipped (power {pw:.3e} > 0): g {g_} terms {terms} det(conic) {A_ * C2_ - B_ * B_:.3e} opacity {o_:.4f}")
+            continue
+        al = min(0.99, o_ * np.exp(pw))
+        if al < 1 / 255:
+            continue
+        if T64 * (1 - al) < 1e-4:
+            break
+        C64 += pre_["rgb"][g_].astype(np.float64) * al * T64
+        big.append((al * T64 * sum(abs(t) for t in terms), g_, al, T64, pw, terms, A_ * C2_ - B_ * B_))
+        T64 *= 1 - al
+    C64 += T64 * np.asarray(bg)
+    print(f"  float64 replay: {C64[c_]:.8f}  (gpu - f64 {got[c_, j_, i_] - C64[c_]:+.2e}, "
+          f"oracle - f64 {fo['color'][c_, j_, i_] - C64[c_]:+.2e}); cond sum {sum(b[0] for b in big):.3e}")
+    for b_ in sorted(big, reverse=True)[:3]:
+        print("   worst-conditioned contributor: alpha*T*S %.3e g %d alpha %.4f T %.4f power %.4f terms %s det(conic) %.3e" % b_)
+    print(f"DIAG fwd: err {em.max():.3e} at pixel ({i_},{j_}) ch {c_}: got {got[c_, j_, i_]:.8f} "
+          f"ref {fo['color'][c_, j_, i_]:.8f}; tile list {int(rg_[1]) - int(rg_[0])} n_contrib {fo['n_contrib'][j_, i_]} "
+          f"final_T {fo['final_T'][j_, i_]:.3e}; R={fo['num_rendered']} bg={bg} {note}")
+
 
 def run(n_cases=40, seed=0, verbose=True, only_case=None):
   rng = np.random.default_rng(seed)
@@ -64,37 +100,7 @@ def run(n_cases=40, seed=0, verbose=True, only_case=None):
           frag = fo["fragile"]
           e = err[:, ~frag].max(initial=0.0)
           if e > 1e-5 and only_case is not None:
-              em = np.where(frag[None], 0, err)
-              c_, j_, i_ = np.unravel_index(em.argmax(), em.shape)
-              t_ = (j_ // 16) * ((W + 15) // 16) + i_ // 16
-              rg_ = fo["bin"]["ranges"][t_]
-              # the same pixel in float64 from the oracle's per-Gaussian state and list (who is off?)
-              pre_, pl_ = fo["pre"], fo["bin"]["point_list"]
-              T64, C64, big = 1.0, np.zeros(3), []
-              for k_ in range(int(rg_[0]), int(rg_[1])):
-                  g_ = int(pl_[k_])
-                  dx_, dy_ = float(pre_["xy"][g_, 0]) - i_, float(pre_["xy"][g_, 1]) - j_
-                  A_, B_, C2_, o_ = [float(v) for v in pre_["conic_opacity"][g_]]
-                  terms = (-0.5 * A_ * dx_ * dx_, -0.5 * C2_ * dy_ * dy_, -B_ * dx_ * dy_)
-                  pw = sum(terms)
-                  if pw > 0:
-                      continue
-                  al = min(0.99, o_ * np.exp(pw))
-                  if al < 1 / 255:
-                      continue
-                  if T64 * (1 - al) < 1e-4:
-                      break
-                  C64 += pre_["rgb"][g_].astype(np.float64) * al * T64
-                  big.append((al * T64 * sum(abs(t) for t in terms), g_, al, T64, pw, terms, A_ * C2_ - B_ * B_))
-                  T64 *= 1 - al
-              C64 += T64 * np.asarray(bg)
-              print(f"  float64 replay: {C64[c_]:.8f}  (gpu - f64 {color.detach().cpu().numpy()[c_, j_, i_] - C64[c_]:+.2e}, "
-                    f"oracle - f64 {fo['color'][c_, j_, i_] - C64[c_]:+.2e}); cond sum {sum(b[0] for b in big):.3e}")
-              for b_ in sorted(big, reverse=True)[:3]:
-                  print("   worst-conditioned contributor: alpha*T*S %.3e g %d alpha %.4f T %.4f power %.4f terms %s det(conic) %.3e" % b_)
-              print(f"DIAG fwd: err {e:.3e} at pixel ({i_},{j_}) ch {c_}: got {color.detach().cpu().numpy()[c_, j_, i_]:.8f} "
-                    f"ref {fo['color'][c_, j_, i_]:.8f}; tile list {int(rg_[1]) - int(rg_[0])} n_contrib {fo['n_contrib'][j_, i_]} "
-                    f"final_T {fo['final_T'][j_, i_]:.3e}; W={W} H={H} P={P} R={fo['num_rendered']} back={back} sm={sm} bg={bg}")
+              diag_pixel(fo, color.detach().cpu().numpy(), W, bg, f"W={W} H={H} P={P} back={back} sm={sm}")
               continue
           assert e <= 1e-5, (case, e)
           worst["fwd"] = max(worst["fwd"], float(e)); worst["frag"] = max(worst["frag"], float(frag.mean()))
