@@ -247,6 +247,45 @@ def test_edge_cases(cuda_device):
              opacities=gg["opacities"], scales=None, rotations=None, cov3D_precomp=None)
 
 
+def test_nonfinite_rows_are_contained(cuda_device):
+    """NaN / Inf in a Gaussian's position, scales or quaternion (a diverged optimiser step): the row is culled —
+    radii 0, no instances — and the frame equals, bit for bit, the frame rendered without those rows; gradients of
+    the clean rows are finite and equal too.  Non-finite opacity / colour reach the pixels they cover (as in any
+    3DGS rasterizer) but never leave their tiles' lists; nothing reads or writes out of bounds (run under
+    compute-sanitizer in profiles/r2_compute_sanitizer.txt)."""
+    P = 3000
+    scene = make_scene(P=P, W=100, H=70, F=96, seed=23)
+    gs = scene["gaussians"]
+    bad = torch.zeros(P, dtype=torch.bool)
+    nan, inf = float("nan"), float("inf")
+    gs["means3D"][10:20] = nan; gs["means3D"][30:40, 0] = inf; gs["means3D"][50:60, 2] = -inf
+    gs["scales"][70:80, 1] = nan
+    gs["rotations"][90:100] = nan
+    for lo in (10, 30, 50, 70, 90):
+        bad[lo:lo + 10] = True
+    g, m2d, color, radii, n = _run_product(scene, cuda_device)
+    assert (radii[bad.to(cuda_device)] == 0).all() and torch.isfinite(color).all()
+    dL = torch.randn(color.shape, generator=torch.Generator().manual_seed(1)).to(cuda_device)
+    color.backward(dL)
+    clean = make_scene(P=P, W=100, H=70, F=96, seed=23)
+    clean["gaussians"] = {k: v[~bad].clone() for k, v in gs.items()}
+    g2, _, color2, radii2, n2 = _run_product(clean, cuda_device)
+    color2.backward(dL)
+    assert n == n2 and torch.equal(color, color2) and torch.equal(radii[~bad.to(cuda_device)], radii2)
+    for k in ("means3D", "opacities", "scales", "rotations", "colors_precomp"):
+        a, b = g[k].grad[~bad.to(cuda_device)], g2[k].grad
+        assert torch.isfinite(a).all() and (a - b).abs().max() <= ATOMIC_RTOL * b.abs().max(), k
+        assert (g[k].grad[bad.to(cuda_device)] == 0).all(), k
+    # non-finite opacity / colour, overflowing scales: must complete (forward and backward) without a fault
+    for key, val in (("opacities", nan), ("colors_precomp", inf), ("scales", 1e30), ("scales", 0.0), ("rotations", 0.0)):
+        sc = make_scene(P=P, W=100, H=70, F=96, seed=23)
+        sc["gaussians"][key][::97] = val
+        g3, _, c3, r3, n3 = _run_product(sc, cuda_device)
+        c3.backward(dL)
+        torch.cuda.synchronize()
+        assert 0 <= n3 <= P * 35 and c3.shape == color.shape
+
+
 def test_heavy_tile_uses_global_sort_fallback(cuda_device):
     """> 4096 instances on one tile: the per-tile sort leaves shared memory; order must stay exact."""
     from gsvc_b200.rasterizer import RasterState
