@@ -134,56 +134,62 @@ def settings_for(geom, frame_id, device, back=False):
 
 
 # --------------------------------------------------------------------------------------------------
-# CPU arm: the pure-PyTorch oracle (there is no reference CPU implementation: renderer.py:37 is CUDA-only,
-# and the reference's CUDA rasterizer source is not in /root/reference)
+# CPU arm: the C oracle (oracle/splat_oracle.c, OpenMP over pixel rows / Gaussians) — there is no reference CPU
+# implementation to run: renderer.py:37 is CUDA-only and the reference's CUDA rasterizer source is not in
+# /root/reference.  The C port is the faster of the repo's two CPU restatements (the pure-PyTorch one does
+# 0.4-0.6 view-iters/s on 16 cores), so it is the stronger baseline.
 # --------------------------------------------------------------------------------------------------
-def cpu_sample(geom, f0, g_cpu, tile_stride=16, threads=None):
-    """One bounded sample of the config-2 step on the host: preprocess + binning of all 200k Gaussians,
-    blend forward+backward (autograd) on every `tile_stride`-th tile; returns (seconds, extrapolated seconds)."""
-    from oracle import torch_oracle
-    from oracle.c_oracle import OracleSettings
-    if threads:
-        torch.set_num_threads(threads)
+def cpu_step(geom, f0, g_np, rows_div=1):
+    """One view-iteration of the config-2 scene on the host cores: preprocess + binning + blend forward + blend
+    backward + per-Gaussian backward, all Gaussians.  rows_div > 1 bounds the sample: only the top 1/rows_div of
+    the image rows is rendered (the per-Gaussian stages still see every Gaussian) and the per-tile part of the time
+    is scaled back by the row ratio.  Returns (seconds measured, seconds for the whole view, rows rendered)."""
+    from oracle import c_oracle
     fr = geom.frame(f0)
-    st = OracleSettings(image_height=fr.image_height, image_width=fr.image_width, x_min=fr.x_min, y_min=fr.y_min,
-                        scale=fr.scale, threshold=THRESHOLD, bg=np.zeros(3, np.float32),
-                        viewmatrix=fr.view_matrix.permute(1, 0).numpy().copy(), campos=fr.cam_pos.numpy())
-    T = ((fr.image_width + 15) // 16) * ((fr.image_height + 15) // 16)
-    subset = np.arange(0, T, tile_stride)
+    H = int(fr.image_height)
+    h = H if rows_div == 1 else max(16, (H // rows_div) // 16 * 16)
+    st = c_oracle.OracleSettings(image_height=h, image_width=int(fr.image_width), x_min=fr.x_min, y_min=fr.y_min,
+                                 scale=fr.scale, threshold=THRESHOLD, bg=np.zeros(3, np.float32),
+                                 viewmatrix=fr.view_matrix.permute(1, 0).numpy().copy(), campos=fr.cam_pos.numpy())
+    dL = np.ones((3, h, int(fr.image_width)), np.float32)
     t0 = time.perf_counter()
-    fwd = torch_oracle.forward(st, g_cpu["means3D"], g_cpu["opacities"], g_cpu["scales"], g_cpu["rotations"],
-                               colors_precomp=g_cpu["colors_precomp"], requires_grad=True, tile_subset=subset)
+    pre = c_oracle.preprocess(st, g_np["means3D"], g_np["scales"], g_np["rotations"], None, g_np["opacities"],
+                              g_np["colors_precomp"])
     t1 = time.perf_counter()
-    dL = torch.ones_like(fwd["color"])
-    torch_oracle.backward(fwd, dL)
+    fwd = c_oracle.forward(st, g_np["means3D"], g_np["opacities"], g_np["scales"], g_np["rotations"],
+                           colors_precomp=g_np["colors_precomp"])
+    c_oracle.backward(fwd, dL)
     t2 = time.perf_counter()
-    # split: per-Gaussian + binning work is done in full; only the per-tile blend work scales with the tile count
-    total = t2 - t0
-    full = fwd["t_pre"] + (total - fwd["t_pre"]) * (T / len(subset))
-    return total, full, len(subset), T
+    t_pre = t1 - t0                       # timed apart only to know the share that does not scale with the rows
+    total = t2 - t1
+    return total, t_pre + (total - t_pre) * (H / h), h
 
 
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    from oracle import c_oracle
+    c_oracle.build()
     cfg, geom, f0, g = build_scene(1, "cpu")
-    stride = 16
-    times = []
-    fulls = []
+    g_np = {k: v.numpy() for k, v in g.items()}
+    H = int(geom.frame(f0).image_height)
+    t_full, _, _ = cpu_step(geom, f0, g_np)                       # untimed: page in, size the sample
+    budget = 170.0                                                # seconds for the whole --steps + --warmup run
+    rows_div = max(1, int(np.ceil(t_full * (args.steps + args.warmup) / budget)))
+    times, fulls = [], []
     for i in range(args.warmup + args.steps):
-        total, full, ns, T = cpu_sample(geom, f0, g, tile_stride=stride, threads=cores)
+        total, full, h = cpu_step(geom, f0, g_np, rows_div)
         if i >= args.warmup:
             times.append(total)
             fulls.append(full)
     ms = 1000.0 * sum(times) / len(times)
-    # a full step blends all T tiles: the per-tile part of the sample is scaled by T/ns, the per-Gaussian
-    # part (done in full inside the sample) is not
     full_ms = 1000.0 * sum(fulls) / len(fulls)
     value = 1000.0 / full_ms
-    sample = (f"config 2 scene on the host: preprocess+binning of all {cfg['P']} Gaussians, blend fwd+bwd (autograd) on "
-              f"{ns} of {T} tiles (every {stride}th); blend time scaled x{T / ns:.1f} to a whole view")
+    sample = (f"C oracle (OpenMP, {cores} host threads) on the config 2 scene, one view forward+backward per step: all "
+              f"{cfg['P']} Gaussians, " + ("every pixel" if h == H else
+              f"the top {h} of {H} pixel rows (per-tile time scaled x{H / h:.1f} to the whole view; per-Gaussian "
+              f"stages in full)"))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": full_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -639,15 +645,15 @@ def run_product_arm(args, rank, local_rank, world):
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            g_cpu = {k: v.detach().cpu() for k, v in g.items()}
-            stride = 16
-            cpu_sample(geom, f0, g_cpu, tile_stride=64, threads=cores)  # warm-up
-            total, full, ns, Tt = cpu_sample(geom, f0, g_cpu, tile_stride=stride, threads=cores)
+            g_np = {k: v.detach().cpu().numpy() for k, v in g.items()}
+            cpu_step(geom, f0, g_np)                                        # warm-up (pages in, builds nothing)
+            reps = [cpu_step(geom, f0, g_np) for _ in range(10)]
+            best = min(r[1] for r in reps)
             line["cpu_baseline"] = {
-                "value": 1.0 / full, "unit": UNIT, "cores": cores, "kind": "port",
-                "sample": (f"pure-PyTorch oracle, same scene, ONE view: preprocess+binning of all {P} Gaussians, blend "
-                           f"fwd+bwd on {ns} of {Tt} tiles (every {stride}th) took {total:.2f} s; blend part scaled "
-                           f"x{Tt / ns:.1f} to a whole view = {full:.1f} s")}
+                "value": 1.0 / best, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": (f"C oracle (oracle/splat_oracle.c, OpenMP, {cores} host threads), same scene, ONE view "
+                           f"forward+backward over all {P} Gaussians and every pixel: best of 10 whole "
+                           f"view-iterations, {best:.2f} s each ({sum(r[1] for r in reps):.0f} s of CPU-side work)")}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

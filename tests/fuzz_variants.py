@@ -1,6 +1,7 @@
 """Randomised parity sweep of the input VARIANTS the main sweep (tests/fuzz_parity.py) leaves fixed: spherical-harmonic
 colours of every degree (forward clamp mask and SH backward), a precomputed 3D covariance instead of scales/rotations,
-and the toast composition (front + flip_x(back))/2 in one batched chain, each against the C oracle: images 1e-5 off
+the toast composition (front + flip_x(back))/2 in one batched chain, and visible_filter with its fused
+compaction and slab index range (radii and indices exact), each against the C oracle: images 1e-5 off
 fragile pixels, gradients 1e-4 relative, radii / instance counts exact.
 Usage: python tests/fuzz_variants.py [n_cases=30] [seed=0]"""
 import dataclasses
@@ -60,6 +61,49 @@ def _cov3d(gi, sm):
     return np.stack([S[:, 0, 0], S[:, 0, 1], S[:, 0, 2], S[:, 1, 1], S[:, 1, 2], S[:, 2, 2]], -1).astype(np.float32)
 
 
+def _filter_case(case, rng, W, H, F, sm, back, dev):
+    """visible_filter, its fused compaction and the slab index range against the oracle's radii: anchors over a
+    random span of frames, counts around the warp / CTA boundaries of the compaction, z-sorted for the range."""
+    from gsvc_b200.frames import CubeGeometry, slab_index_range, synthetic_gaussians, z_interval_table
+    from gsvc_b200.rasterizer import GaussianRasterizationSettings
+    P = int(rng.choice([1, 31, 32, 33, 255, 256, 257, 1000, 4097, 20000, 70001]))
+    thr = float(rng.choice([0.02, 0.05, 0.2]))
+    geom = CubeGeometry(W, H, F)
+    f0 = int(rng.integers(F)); f1 = int(min(F - 1, f0 + rng.integers(1, 40))); fid = int(rng.integers(f0, f1 + 1))
+    gs = synthetic_gaussians(P, geom, f0, f1, threshold=thr, seed=int(rng.integers(1 << 30)))
+    order = torch.argsort(gs["means3D"][:, 2], stable=True)
+    gs = {k: v[order].contiguous() for k, v in gs.items()}
+    fr = geom.frame(fid)
+    vm = fr.view_matrix_s if back else fr.view_matrix
+    st = c_oracle.OracleSettings(image_height=H, image_width=W, x_min=fr.x_min, y_min=fr.y_min, scale=fr.scale,
+                                 threshold=thr, scale_modifier=sm, viewmatrix=vm.permute(1, 0).numpy().copy())
+    want = c_oracle.visible_filter(st, gs["means3D"].numpy(), gs["scales"].numpy(), gs["rotations"].numpy())
+    rs = GaussianRasterizationSettings(
+        image_height=H, image_width=W, x_min=fr.x_min, y_min=fr.y_min, scale=fr.scale, threshold=thr,
+        bg=torch.zeros(3, device=dev), scale_modifier=sm, viewmatrix=vm.permute(1, 0).to(dev), sh_degree=0,
+        campos=fr.cam_pos, prefiltered=False, debug=False)
+    rast = GaussianRasterizer(raster_settings=rs)
+    g = {k: v.to(dev) for k, v in gs.items()}
+    want_t = torch.as_tensor(want, device=dev)
+    want_idx = torch.nonzero(want_t > 0).flatten()
+    got = rast.visible_filter(means3D=g["means3D"], scales=g["scales"], rotations=g["rotations"], cov3D_precomp=None)
+    assert torch.equal(got, want_t), (case, "filter")
+    idx, radii = rast.visible_filter_compact(means3D=g["means3D"], scales=g["scales"], rotations=g["rotations"])
+    assert torch.equal(radii, want_t) and torch.equal(idx.long(), want_idx), (case, "compact")
+    idx2, none = rast.visible_filter_compact(means3D=g["means3D"], scales=g["scales"], rotations=g["rotations"],
+                                             want_radii=False)
+    assert none is None and torch.equal(idx2, idx), (case, "compact without radii")
+    lo, hi = slab_index_range(z_interval_table(gs["means3D"][:, 2]), fr.z, thr)
+    for k in ("means3D", "scales", "rotations"):
+        g[k][:lo] = float("nan"); g[k][hi:] = float("nan")
+    part = rast.visible_filter(means3D=g["means3D"], scales=g["scales"], rotations=g["rotations"], cov3D_precomp=None,
+                               index_range=(lo, hi))
+    assert torch.equal(part, want_t), (case, "range", lo, hi)
+    idx3, radii3 = rast.visible_filter_compact(means3D=g["means3D"], scales=g["scales"], rotations=g["rotations"],
+                                               index_range=(lo, hi))
+    assert torch.equal(radii3, want_t) and torch.equal(idx3.long(), want_idx), (case, "range compact", lo, hi)
+
+
 def run(n_cases=30, seed=0, verbose=True, only_case=None):
     rng = np.random.default_rng(seed)
     dev = torch.device("cuda:0")
@@ -74,10 +118,15 @@ def run(n_cases=30, seed=0, verbose=True, only_case=None):
         bg = tuple(float(x) for x in rng.random(3)) if rng.integers(2) else (0.0, 0.0, 0.0)
         sm = float(rng.choice([1.0, 0.5, 2.0]))
         sseed = int(rng.integers(1 << 30))
-        variant = ("sh", "cov", "toast")[case % 3]
+        variant = ("sh", "cov", "toast", "filter")[case % 4]
         deg = int(rng.integers(4))
         back = bool(rng.integers(2))
         if only_case is not None and case != only_case:
+            continue
+        if variant == "filter":
+            _filter_case(case, np.random.default_rng(sseed), W, H, F, sm, back, dev)
+            if verbose:
+                print(f"case {case:3d} ok: filter {W}x{H}", flush=True)
             continue
         dL = torch.randn((3, H, W), generator=torch.Generator().manual_seed(case))
         scene = make_scene(P=P, W=W, H=H, F=F, seed=sseed, back=back, bg=bg, scale_modifier=sm)

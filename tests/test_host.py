@@ -231,3 +231,29 @@ def test_batched_and_host_paths_have_no_cpu_fallback():
     with pytest.raises(RasterizerError):
         GaussianRasterizer(raster_settings=f).visible_filter_compact(means3D=g["means3D"], scales=g["scales"],
                                                                      rotations=g["rotations"])
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the C oracle on the host cores, no GPU anywhere): exactly one stdout line, the
+    contract's keys, e2e == value with zero copy bytes, and the bounded sample when the run would be too long."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+              "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"] == "train_iters_per_s" and d["value"] > 0
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and "every pixel" in d["cpu_baseline"]["sample"]
+    import bench
+    from gsvc_b200.frames import CubeGeometry, synthetic_gaussians
+    geom = CubeGeometry(128, 96, 64)
+    g = {k: v.numpy() for k, v in synthetic_gaussians(2000, geom, 32, 32, threshold=0.05, seed=3).items()}
+    t, full, h = bench.cpu_step(geom, 32, g, rows_div=1)
+    t2, full2, h2 = bench.cpu_step(geom, 32, g, rows_div=3)
+    assert h == 96 and h2 == 32 and abs(full - t) < 1e-9 and full2 >= t2 > 0
