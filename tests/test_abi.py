@@ -87,3 +87,23 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libgsvc_rast.so"))
     with pytest.raises(_lib.RasterizerError, match="no CPU or PyTorch fallback"):
         _lib.lib()
+
+
+def test_header_is_plain_c_and_the_c_host_links():
+    """include/gsvc_rast.h compiles as C99 (no C++-isms, no torch types) and examples/c_host.c links against the
+    built library: every entry point it calls resolves.  Nothing is executed (no GPU here)."""
+    import os, shutil, subprocess, tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    if shutil.which("gcc") is None or not os.path.exists(os.path.join(cuda, "include", "cuda_runtime_api.h")):
+        import pytest
+        pytest.skip("no gcc / CUDA runtime headers")
+    import gsvc_b200._lib as L
+    assert os.path.exists(L.LIB_PATH)
+    with tempfile.TemporaryDirectory() as tmp:
+        subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-x", "c",
+                        os.path.join(root, "include", "gsvc_rast.h")], check=True)
+        subprocess.run(["gcc", "-std=c99", "-O1", "-Wall", "-Werror", "-I" + os.path.join(root, "include"),
+                        "-I" + os.path.join(cuda, "include"), os.path.join(root, "examples", "c_host.c"),
+                        "-o", os.path.join(tmp, "c_host"), "-L" + os.path.dirname(L.LIB_PATH), "-lgsvc_rast",
+                        "-L" + os.path.join(cuda, "lib64"), "-lcudart"], check=True)

@@ -286,6 +286,50 @@ def test_nonfinite_rows_are_contained(cuda_device):
         assert 0 <= n3 <= P * 35 and c3.shape == color.shape
 
 
+def test_plain_c_host_matches_oracle(cuda_device, tmp_path):
+    """The C-ABI from a plain C program (examples/c_host.c: gcc + the CUDA runtime, no Python or torch in the
+    process): allocator-callback forward + backward on a seeded scene, results against the oracle."""
+    import os, shutil, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    if shutil.which("gcc") is None or not os.path.exists(os.path.join(cuda, "include", "cuda_runtime_api.h")):
+        pytest.skip("no gcc / CUDA runtime headers on this box")
+    exe = str(tmp_path / "c_host")
+    libdir = os.path.join(root, "gsvc_b200")
+    subprocess.run(["gcc", "-std=c99", "-O1", "-Wall", "-I" + os.path.join(root, "include"),
+                    "-I" + os.path.join(cuda, "include"), os.path.join(root, "examples", "c_host.c"), "-o", exe,
+                    "-L" + libdir, "-lgsvc_rast", "-L" + os.path.join(cuda, "lib64"), "-lcudart",
+                    "-Wl,-rpath," + libdir, "-Wl,-rpath," + os.path.join(cuda, "lib64")], check=True)
+    P, W, H = 6000, 150, 90
+    scene = make_scene(P=P, W=W, H=H, F=128, seed=31, back=True, bg=(0.3, 0.1, 0.6), scale_modifier=0.5)
+    st, gi = scene["oracle_settings"], np_inputs(scene["gaussians"])
+    dL = np.random.default_rng(5).standard_normal((3, H, W)).astype(np.float32)
+    with open(tmp_path / "scene.bin", "wb") as f:
+        np.asarray([W, H, P], np.int32).tofile(f)
+        np.asarray([st.x_min, st.y_min, st.scale, st.threshold, st.scale_modifier], np.float32).tofile(f)
+        np.asarray(st.bg, np.float32).tofile(f)
+        np.asarray(st.viewmatrix, np.float32).reshape(16).tofile(f)
+        for k in ("means3D", "opacities", "colors_precomp", "scales", "rotations"):
+            np.ascontiguousarray(gi[k], np.float32).tofile(f)
+        dL.tofile(f)
+    run = subprocess.run([exe, str(tmp_path / "scene.bin"), str(tmp_path / "out.bin")], capture_output=True, text=True,
+                         timeout=120)
+    assert run.returncode == 0, run.stderr
+    fo = _oracle_forward(scene)
+    go = c_oracle.backward(fo, dL)
+    with open(tmp_path / "out.bin", "rb") as f:
+        n = int(np.fromfile(f, np.int64, 1)[0])
+        color = np.fromfile(f, np.float32, 3 * H * W).reshape(3, H, W)
+        radii = np.fromfile(f, np.int32, P)
+        grads = {k: np.fromfile(f, np.float32, P * w).reshape(P, w) for k, w in
+                 (("means3D", 3), ("colors_precomp", 3), ("opacities", 1), ("scales", 3), ("rotations", 4))}
+    assert n == fo["num_rendered"] and np.array_equal(radii, fo["radii"])
+    assert np.abs(color - fo["color"])[:, ~fo["fragile"]].max() <= FWD_ATOL
+    ok = ~go["touched_fragile"]
+    for k, a in grads.items():
+        assert _rel_err(a[ok], go[k].reshape(P, -1)[ok]) <= GRAD_RTOL, k
+
+
 def test_heavy_tile_uses_global_sort_fallback(cuda_device):
     """> 4096 instances on one tile: the per-tile sort leaves shared memory; order must stay exact."""
     from gsvc_b200.rasterizer import RasterState
