@@ -647,12 +647,12 @@ def run_product_arm(args, rank, local_rank, world):
             cores = os.cpu_count() or 1
             g_np = {k: v.detach().cpu().numpy() for k, v in g.items()}
             cpu_step(geom, f0, g_np)                                        # warm-up (pages in, builds nothing)
-            reps = [cpu_step(geom, f0, g_np) for _ in range(10)]
+            reps = [cpu_step(geom, f0, g_np) for _ in range(30)]
             best = min(r[1] for r in reps)
             line["cpu_baseline"] = {
                 "value": 1.0 / best, "unit": UNIT, "cores": cores, "kind": "port",
                 "sample": (f"C oracle (oracle/splat_oracle.c, OpenMP, {cores} host threads), same scene, ONE view "
-                           f"forward+backward over all {P} Gaussians and every pixel: best of 10 whole "
+                           f"forward+backward over all {P} Gaussians and every pixel: best of 30 whole "
                            f"view-iterations, {best:.2f} s each ({sum(r[1] for r in reps):.0f} s of CPU-side work)")}
         emit(line)
     if world > 1:
