@@ -171,6 +171,7 @@ def run_reference_arm(args, rank, world):
     cores = os.cpu_count() or 1
     from oracle import c_oracle
     c_oracle.build()
+    cores = c_oracle.set_threads(cores)                           # torchrun exports OMP_NUM_THREADS=1
     cfg, geom, f0, g = build_scene(1, "cpu")
     g_np = {k: v.numpy() for k, v in g.items()}
     H = int(geom.frame(f0).image_height)
@@ -644,7 +645,8 @@ def run_product_arm(args, rank, local_rank, world):
             "clocks": clk,
         }
         if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
+            from oracle import c_oracle
+            cores = c_oracle.set_threads(os.cpu_count() or 1)
             g_np = {k: v.detach().cpu().numpy() for k, v in g.items()}
             cpu_step(geom, f0, g_np)                                        # warm-up (pages in, builds nothing)
             reps = [cpu_step(geom, f0, g_np) for _ in range(30)]

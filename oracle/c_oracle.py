@@ -84,6 +84,15 @@ def lib():
     return _lib
 
 
+def set_threads(n: int) -> int:
+    """OpenMP threads of the oracle's parallel loops.  torchrun exports OMP_NUM_THREADS=1 to its workers, which
+    libgomp reads once at load time — a bench leg that wants every host core has to ask for them explicitly."""
+    L = lib()
+    L.omp_set_num_threads(C.c_int(int(n)))
+    L.omp_get_max_threads.restype = C.c_int
+    return int(L.omp_get_max_threads())
+
+
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
