@@ -153,6 +153,23 @@ def _require_cuda(t: torch.Tensor, what: str):
         raise RasterizerError(f"{what} must be a CUDA tensor: gsvc_b200 has no CPU fallback")
 
 
+def _check_shapes(P, sh_degree, means3D, sh=None, colors=None, opacities=None, scales=None, rotations=None, cov=None):
+    """The kernels index raw pointers by the Gaussian id: a tensor with fewer rows than means3D would be read out of
+    bounds, so shapes are checked here, like the upstream binding's `... must have dimensions (num_points, 3)`."""
+    def rows(t, width, what):
+        if t is not None and (t.dim() < 1 or t.shape[0] != P or t.numel() != P * width):
+            raise RasterizerError(f"{what} must have shape ({P}, {width}), got {tuple(t.shape)}")
+    if means3D.dim() != 2 or means3D.shape[1] != 3:
+        raise RasterizerError(f"means3D must have dimensions (num_points, 3), got {tuple(means3D.shape)}")
+    rows(colors, 3, "colors_precomp"); rows(opacities, 1, "opacities"); rows(scales, 3, "scales")
+    rows(rotations, 4, "rotations"); rows(cov, 6, "cov3D_precomp")
+    if sh is not None:
+        need = (int(sh_degree) + 1) ** 2
+        if sh.dim() != 3 or sh.shape[0] != P or sh.shape[2] != 3 or not (need <= sh.shape[1] <= 16) or sh_degree > 3:
+            raise RasterizerError(f"shs must have shape ({P}, M, 3) with {need} <= M <= 16 for sh_degree {sh_degree} "
+                                  f"(<= 3), got {tuple(sh.shape)}")
+
+
 def _align(n: int) -> int:
     return (n + 255) & ~255
 
@@ -175,6 +192,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             sc_c = _dev_f32(scales, device, "scales") if scales.numel() else None
             rot_c = _dev_f32(rotations, device, "rotations") if rotations.numel() else None
             cov_c = _dev_f32(cov3Ds_precomp, device, "cov3D_precomp") if cov3Ds_precomp.numel() else None
+            _check_shapes(P, rs.sh_degree, means3D_c, sh_c, col_c, op_c, sc_c, rot_c, cov_c)
             sh_M = sh_c.shape[1] if sh_c is not None else 0
             H, W = int(rs.image_height), int(rs.image_width)
 
@@ -334,13 +352,23 @@ class GaussianRasterizer(nn.Module):
             s = _dev_f32(scales, device, "scales")
             r = _dev_f32(rotations, device, "rotations")
             c = _dev_f32(cov3D_precomp, device, "cov3D_precomp")
+            _check_shapes(P, 0, m, scales=s, rotations=r, cov=c)
             radii = torch.empty((P,), dtype=torch.int32, device=device)
-            lo, hi = (0, 0) if index_range is None else (int(index_range[0]), int(index_range[1]))
+            lo, hi = self._index_range(index_range, P)
             if index_range is not None and lo == hi:
                 return radii.zero_()
             _lib.check(L.gsvc_rast_visible_filter(ns.ref, P, _ptr(m), _ptr(s), _ptr(r), _ptr(c), _ptr(radii), lo, hi,
                                                   _stream_ptr(device)), "gsvc_rast_visible_filter")
         return radii
+
+    @staticmethod
+    def _index_range(index_range, P):
+        if index_range is None:
+            return 0, 0
+        lo, hi = int(index_range[0]), int(index_range[1])
+        if not (0 <= lo <= hi <= P):
+            raise RasterizerError(f"index_range {(lo, hi)} is not inside [0, {P}]")
+        return lo, hi
 
     def visible_filter_compact(self, means3D, scales=None, rotations=None, cov3D_precomp=None, want_radii=True,
                                index_range=None):
@@ -364,12 +392,13 @@ class GaussianRasterizer(nn.Module):
             s = _dev_f32(scales, device, "scales")
             r = _dev_f32(rotations, device, "rotations")
             c = _dev_f32(cov3D_precomp, device, "cov3D_precomp")
+            _check_shapes(P, 0, m, scales=s, rotations=r, cov=c)
             radii = torch.empty((P,), dtype=torch.int32, device=device) if want_radii else None
             idx = torch.empty((P,), dtype=torch.int32, device=device)
             scratch = _bytes(L.gsvc_rast_compact_scratch_bytes(P), device)
             stream = _stream_ptr(device)
             slot, ticket = _count_slot()
-            lo, hi = (0, 0) if index_range is None else (int(index_range[0]), int(index_range[1]))
+            lo, hi = self._index_range(index_range, P)
             if index_range is not None and lo == hi:
                 return idx[:0], (radii.zero_() if radii is not None else None)
             _lib.check(L.gsvc_rast_visible_filter_compact(ns.ref, P, _ptr(m), _ptr(s), _ptr(r), _ptr(c), _ptr(radii),

@@ -25,8 +25,8 @@ import torch
 from . import _lib
 from ._lib import MAX_VIEWS, RasterizerError, View
 from . import rasterizer as R
-from .rasterizer import (GaussianRasterizationSettings, _NativeSettings, _align, _bytes, _count_slot, _dev_f32, _ptr,
-                         _require_cuda, _stream_ptr)
+from .rasterizer import (GaussianRasterizationSettings, _NativeSettings, _align, _bytes, _check_shapes, _count_slot,
+                         _dev_f32, _ptr, _require_cuda, _stream_ptr)
 
 _F32 = torch.float32
 _SHARED_FIELDS = ("image_height", "image_width", "x_min", "y_min", "scale", "threshold", "scale_modifier", "sh_degree")
@@ -146,6 +146,7 @@ class _RasterizeViews(torch.autograd.Function):
             sc_c = _dev_f32(scales, device, "scales") if scales.numel() else None
             rot_c = _dev_f32(rotations, device, "rotations") if rotations.numel() else None
             cov_c = _dev_f32(cov3Ds_precomp, device, "cov3D_precomp") if cov3Ds_precomp.numel() else None
+            _check_shapes(int(P), rs.sh_degree, means3D_c, sh_c, col_c, op_c, sc_c, rot_c, cov_c)
             sh_M = sh_c.shape[1] if sh_c is not None else 0
             H, W = int(rs.image_height), int(rs.image_width)
 

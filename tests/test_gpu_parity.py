@@ -245,6 +245,28 @@ def test_edge_cases(cuda_device):
     with pytest.raises(Exception):
         rast(means3D=gg["means3D"], means2D=gg["means3D"], shs=None, colors_precomp=gg["colors_precomp"],
              opacities=gg["opacities"], scales=None, rotations=None, cov3D_precomp=None)
+    # (e) row-count / width mismatches are refused on the host (the kernels index raw pointers by Gaussian id)
+    from gsvc_b200.rasterizer import RasterizerError
+    from gsvc_b200.views import rasterize_views
+    ok = dict(means3D=gg["means3D"], means2D=gg["means3D"], shs=None, colors_precomp=gg["colors_precomp"],
+              opacities=gg["opacities"], scales=gg["scales"], rotations=gg["rotations"], cov3D_precomp=None)
+    for key, bad in (("opacities", gg["opacities"][:-1]), ("scales", gg["scales"][:, :2]),
+                     ("rotations", gg["rotations"][:10]), ("colors_precomp", gg["colors_precomp"][1:]),
+                     ("means3D", gg["means3D"][:, :2])):
+        with pytest.raises(RasterizerError):
+            rast(**dict(ok, **{key: bad}))
+        if key != "means3D":
+            with pytest.raises(RasterizerError):
+                rasterize_views([rast.raster_settings] * 2, **{k: v for k, v in dict(ok, **{key: bad}).items()
+                                                               if k != "means2D"})
+    with pytest.raises(RasterizerError):                      # degree 2 needs 9 coefficients
+        GaussianRasterizer(raster_settings=product_settings(scene, cuda_device, sh_degree=2))(
+            **dict(ok, colors_precomp=None, shs=torch.zeros((500, 4, 3), device=cuda_device)))
+    with pytest.raises(RasterizerError):
+        rast.visible_filter(means3D=gg["means3D"], scales=gg["scales"][:-3], rotations=gg["rotations"], cov3D_precomp=None)
+    with pytest.raises(RasterizerError):
+        rast.visible_filter(means3D=gg["means3D"], scales=gg["scales"], rotations=gg["rotations"], cov3D_precomp=None,
+                            index_range=(10, 501))
 
 
 def test_nonfinite_rows_are_contained(cuda_device):
