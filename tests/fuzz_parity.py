@@ -2,7 +2,7 @@
 size and images smaller than a tile), Gaussian counts, densities (bucket sizes across every sort path: <=32, 64,
 128, 256, 512 per warp, CTA-wide shared, in-place global), views, backgrounds, scale modifiers; single calls through
 the records of the stage exports (bit-exact), images (1e-5 off fragile pixels), gradients (1e-4 relative), and the
-same scenes through the batched-view path.  Usage: python tests/fuzz_parity.py [n_cases=40] [seed=0]"""
+same scenes through the batched-view path.  Usage: python tests/fuzz_parity.py [n_cases=40] [seed=0] [only_case] [big]   (big: 400x300 .. 1024x600, up to 400k Gaussians)"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -51,19 +51,19 @@ def diag_pixel(fo, got, W, bg, note=""):
           f"final_T {fo['final_T'][j_, i_]:.3e}; R={fo['num_rendered']} bg={bg} {note}")
 
 
-def run(n_cases=40, seed=0, verbose=True, only_case=None):
+def run(n_cases=40, seed=0, verbose=True, only_case=None, big=False):
   rng = np.random.default_rng(seed)
   dev = torch.device("cuda:0")
   worst = dict(fwd=0.0, grad=0.0, frag=0.0)
   t_start = time.time()
   for case in range(n_cases):
-      W = int(rng.choice([7, 16, 33, 64, 100, 160, 250, 320]))
-      H = int(rng.choice([5, 16, 40, 64, 96, 130, 200]))
-      F = int(rng.choice([64, 128, 320]))
+      W = int(rng.choice([400, 512, 640, 801, 1024] if big else [7, 16, 33, 64, 100, 160, 250, 320]))
+      H = int(rng.choice([300, 400, 513, 600] if big else [5, 16, 40, 64, 96, 130, 200]))
+      F = int(rng.choice([300, 600, 1200] if big else [64, 128, 320]))
       # density: instances per tile from ~5 to ~3000
       tiles = ((W + 15) // 16) * ((H + 15) // 16)
       per_tile = float(rng.choice([4, 20, 50, 100, 200, 400, 900, 3000]))
-      P = int(min(60000, max(1, per_tile * tiles / 3.0)))
+      P = int(min(400000 if big else 60000, max(1, per_tile * tiles / 3.0)))
       back = bool(rng.integers(2))
       bg = tuple(float(x) for x in rng.random(3)) if rng.integers(2) else (0.0, 0.0, 0.0)
       sm = float(rng.choice([1.0, 0.5, 2.0]))
@@ -136,5 +136,7 @@ def run(n_cases=40, seed=0, verbose=True, only_case=None):
 
 
 if __name__ == "__main__":
-    run(int(sys.argv[1]) if len(sys.argv) > 1 else 40, int(sys.argv[2]) if len(sys.argv) > 2 else 0,
-        only_case=int(sys.argv[3]) if len(sys.argv) > 3 else None)
+    big = "big" in sys.argv[1:]
+    argv = [a for a in sys.argv[1:] if a != "big"]
+    run(int(argv[0]) if len(argv) > 0 else 40, int(argv[1]) if len(argv) > 1 else 0,
+        only_case=int(argv[2]) if len(argv) > 2 else None, big=big)
