@@ -17,6 +17,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.nn.functional as F
 
+from gsvc_b200 import sharding
 from gsvc_b200.frames import CubeGeometry, synthetic_gaussians
 from gsvc_b200.rasterizer import GaussianRasterizationSettings
 from gsvc_b200.views import ViewBatch, rasterize_views
@@ -50,8 +51,8 @@ class Gaussians(torch.nn.Module):
                     opacities=torch.sigmoid(self.op), colors_precomp=torch.sigmoid(self.col))
 
 
-def render_frames(batch, g):
-    images, radii, n = rasterize_views(batch, means3D=g["means3D"], opacities=g["opacities"],
+def render_frames(batch, g, means2D=None):
+    images, radii, n = rasterize_views(batch, means3D=g["means3D"], opacities=g["opacities"], means2D=means2D,
                                        colors_precomp=g["colors_precomp"], scales=g["scales"], rotations=g["rotations"])
     return images, radii, n
 
@@ -71,24 +72,39 @@ def fit(device, iters=200, P=20000, W=320, H=192, Fr=320, rank=0, world=1, log=N
                             dict(params=[model.rot], lr=1e-3), dict(params=[model.op], lr=5e-2),
                             dict(params=[model.col], lr=2.5e-2)])
     losses = []
+    # the densification statistic of training_statis (scene/gaussian_model.py:1298-1314): accumulated |dL/dmeans2D|
+    # and the number of views each Gaussian was drawn in, over ALL ranks' views
+    stat_accum = torch.zeros((P, sharding.STATS_WIDTH), device=device)
     for it in range(iters):
-        images, radii, n = render_frames(batch, model())
+        means2D = torch.zeros((batch.n_views, P, 3), device=device, requires_grad=True)   # viewspace_points, per view
+        images, radii, n = render_frames(batch, model(), means2D)
         loss = (images - targets).abs().mean()                    # Ll1 of train.py:409
         opt.zero_grad(set_to_none=True)
         loss.backward()
+        stats = sharding.densify_stats(means2D.grad, radii)       # one pass for the step's 4 views
         if world > 1:
             import torch.distributed as dist
-            flat = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM)           # one collective per step
+            flat = torch.cat([p.grad.reshape(-1) for p in model.parameters()] + [stats.reshape(-1) * world])
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)           # one collective per step: gradients + statistic
             flat /= world
             o = 0
             for p in model.parameters():
                 p.grad.copy_(flat[o:o + p.numel()].view_as(p))
                 o += p.numel()
+            stats = flat[o:].view_as(stats)                       # summed (not averaged) over the ranks
+        stat_accum += stats
         opt.step()
         losses.append(float(loss.detach()))
         if log and (it % 50 == 0 or it == iters - 1):
             log(f"iter {it:4d}  L1 {losses[-1]:.5f}  num_rendered {n}  visible {int((radii > 0).sum())}")
+    # what adjust_anchor would threshold (scene/gaussian_model.py: grads = offset_gradient_accum / offset_denom)
+    seen = stat_accum[:, 1] > 0
+    mean_grad = torch.where(seen, stat_accum[:, 0] / stat_accum[:, 1].clamp(min=1), torch.zeros_like(stat_accum[:, 0]))
+    fit.last_densify = dict(seen=int(seen.sum()), candidates=int((mean_grad > 2e-4).sum()),
+                            checksum=float(stat_accum.double().sum()))
+    if log:
+        log(f"densification statistic: {fit.last_densify['seen']} Gaussians drawn at least once, "
+            f"{fit.last_densify['candidates']} above the 2e-4 mean screen-gradient threshold")
     return losses
 
 

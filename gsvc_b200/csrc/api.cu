@@ -163,6 +163,21 @@ int64_t gsvc_rast_launch_count(int32_t reset)
     return reset ? g_launches.exchange(0) : g_launches.load();
 }
 
+int gsvc_rast_densify_stats(int32_t n_views, int32_t P, const float* dL_dmeans2D, const int32_t* radii, float* stats,
+                            int64_t stride, int32_t accumulate, void* stream_)
+{
+    if (n_views < 1) return fail(GSVC_RAST_ERR_INVALID, "n_views must be >= 1");
+    if (P < 0) return fail(GSVC_RAST_ERR_INVALID, "P must be >= 0");
+    if ((long long)P * n_views > 0x7fffffffll) return fail(GSVC_RAST_ERR_INVALID, "P * n_views exceeds 31 bits");
+    if (stride < 2) return fail(GSVC_RAST_ERR_INVALID, "stride must be >= 2 floats");
+    if (P > 0 && (!dL_dmeans2D || !radii || !stats))
+        return fail(GSVC_RAST_ERR_INVALID, "dL_dmeans2D/radii/stats must be non-NULL");
+    cudaError_t e = launch_densify_stats(n_views, P, dL_dmeans2D, radii, stats, (long long)stride, accumulate != 0,
+                                         static_cast<cudaStream_t>(stream_));
+    if (e != cudaSuccess) return fail(GSVC_RAST_ERR_CUDA, "densify_stats: %s", cudaGetErrorString(e));
+    return GSVC_RAST_OK;
+}
+
 int gsvc_rast_count_overflows(int32_t enable)
 {
     g_count_overflows = enable != 0;

@@ -293,6 +293,8 @@ cudaError_t launch_export_geom(int P, GeomView g, float* depth, float* xy, float
                                int32_t* rect, cudaStream_t st);
 
 cudaError_t read_overflow_events(unsigned int* host_value, bool reset, cudaStream_t st);
+cudaError_t launch_densify_stats(int n_views, int P, const float* dm2d, const int32_t* radii, float* stats,
+                                 long long stride, bool accumulate, cudaStream_t st);
 
 void count_launch(int n = 1);
 

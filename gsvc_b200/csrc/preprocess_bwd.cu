@@ -253,4 +253,44 @@ cudaError_t launch_preprocess_backward(const DevSettings& s, const PreInputs& in
     return launch_pdl(preprocess_backward_kernel, dim3((in.P + 255) / 256), dim3(256), st, s, in, radii, g, acc, out);
 }
 
+// Densification statistic at the rasterizer boundary (scene/gaussian_model.py:1298-1314 `training_statis`, called
+// once per view, pipeline/train.py:559-565): per Gaussian, over the views of a step,
+//   stats[g][0] = sum_v [radii[v][g] > 0] * |dL/dmeans2D[v][g][0:2]|,   stats[g][1] = sum_v [radii[v][g] > 0].
+// One stream pass (16 B per (view, Gaussian) in, 8 B per Gaussian out) instead of a masked gather, a norm and a
+// masked scatter-add per view.
+__global__ void __launch_bounds__(256) densify_stats_kernel(int n_views, int P, const float* __restrict__ dm2d,
+                                                            const int32_t* __restrict__ radii,
+                                                            float* __restrict__ stats, long long stride, int accumulate)
+{
+    pdl_prologue();
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= P) return;
+    float norm_sum = 0.f, count = 0.f;
+    for (int v = 0; v < n_views; v++) {
+        const size_t gv = (size_t)v * P + g;
+        if (__ldg(radii + gv) > 0) {
+            const float x = __ldg(dm2d + 3 * gv), y = __ldg(dm2d + 3 * gv + 1);
+            norm_sum += sqrtf(x * x + y * y);
+            count += 1.f;
+        }
+    }
+    float* o = stats + (size_t)g * stride;
+    if (accumulate) {
+        o[0] += norm_sum;
+        o[1] += count;
+    } else {
+        o[0] = norm_sum;
+        o[1] = count;
+    }
+}
+
+cudaError_t launch_densify_stats(int n_views, int P, const float* dm2d, const int32_t* radii, float* stats,
+                                 long long stride, bool accumulate, cudaStream_t st)
+{
+    if (P <= 0) return cudaSuccess;
+    count_launch();
+    return launch_pdl(densify_stats_kernel, dim3((P + 255) / 256), dim3(256), st, n_views, P, dm2d, radii, stats, stride,
+                      accumulate ? 1 : 0);
+}
+
 }  // namespace gsvc

@@ -66,6 +66,55 @@ def allreduce_grads(buf: torch.Tensor, average: bool = False) -> torch.Tensor:
     return buf
 
 
+STATS_WIDTH = 2   # per Gaussian: (sum over views of |dL/dmeans2D[:2]| where drawn, number of views it was drawn in)
+
+
+def step_buffer(P: int, device):
+    """ONE flat fp32 buffer per step holding the packed gradients [P,14] followed by the densification statistic
+    [P,2]: `allreduce_grads(flat)` then sums both over the ranks in a single collective.
+    Returns (flat [P*16], packed [P,14] view, stats [P,2] view)."""
+    flat = torch.zeros((P * (GRAD_WIDTH + STATS_WIDTH),), dtype=torch.float32, device=device)
+    return flat, flat[:P * GRAD_WIDTH].view(P, GRAD_WIDTH), flat[P * GRAD_WIDTH:].view(P, STATS_WIDTH)
+
+
+def densify_stats(means2D_grad: torch.Tensor, radii: torch.Tensor, out: torch.Tensor = None,
+                  accumulate: bool = False) -> torch.Tensor:
+    """The rasterizer-side half of GaussianModel.training_statis (scene/gaussian_model.py:1298-1314) for all views
+    of a step in one kernel (C-ABI gsvc_rast_densify_stats): out[g] = (sum_v |means2D_grad[v,g,:2]| over the views
+    with radii[v,g] > 0, the number of such views).  `means2D_grad` [n_views,P,3] or [P,3] (means2D.grad of
+    rasterize_views / GaussianRasterizer), `radii` [n_views,P] or [P] int32; `out` [P,2] fp32 (rows may be strided,
+    e.g. the stats view of `step_buffer`), overwritten unless `accumulate`.  The caller adds column 0 into
+    offset_gradient_accum[combined_mask] and column 1 into offset_denom[combined_mask] once per iteration instead of
+    once per view (pipeline/train.py:559-565); under frame sharding the all-reduced rows are the statistic of every
+    rank's views, so all ranks take the same densification decisions."""
+    from . import _lib
+    from .rasterizer import RasterizerError, _stream_ptr
+    if not means2D_grad.is_cuda:
+        raise RasterizerError("densify_stats needs CUDA tensors: gsvc_b200 has no CPU fallback")
+    device = means2D_grad.device
+    g = means2D_grad if means2D_grad.dim() == 3 else means2D_grad.unsqueeze(0)
+    r = radii if radii.dim() == 2 else radii.unsqueeze(0)
+    V, P = int(g.shape[0]), int(g.shape[1])
+    if g.shape[2] != 3 or tuple(r.shape) != (V, P) or r.dtype != torch.int32 or r.device != device:
+        raise RasterizerError(f"densify_stats: means2D_grad {tuple(means2D_grad.shape)} / radii {tuple(radii.shape)} "
+                              f"({radii.dtype}) do not match [n_views,P,3] fp32 / [n_views,P] int32")
+    g = g if (g.dtype == torch.float32 and g.is_contiguous()) else g.float().contiguous()
+    r = r if r.is_contiguous() else r.contiguous()
+    if out is None:
+        if accumulate:
+            raise RasterizerError("densify_stats: accumulate needs `out`")
+        out = torch.empty((P, STATS_WIDTH), dtype=torch.float32, device=device)
+    if (tuple(out.shape) != (P, STATS_WIDTH) or out.dtype != torch.float32 or out.device != device or
+            (P > 0 and out.stride(1) != 1)):
+        raise RasterizerError(f"densify_stats: out must be [P,2] fp32 on {device} with unit column stride")
+    with torch.cuda.device(device):
+        _lib.check(_lib.lib().gsvc_rast_densify_stats(V, P, g.data_ptr(), r.data_ptr(), out.data_ptr(),
+                                                      int(out.stride(0)) if P > 0 else STATS_WIDTH,
+                                                      1 if accumulate else 0, _stream_ptr(device)),
+                   "gsvc_rast_densify_stats")
+    return out
+
+
 ViewFn = Callable[[int, bool], Dict[str, torch.Tensor]]
 
 

@@ -35,7 +35,7 @@ extern "C" {
 #define GSVC_RAST_API
 #endif
 
-#define GSVC_RAST_ABI_VERSION 2
+#define GSVC_RAST_ABI_VERSION 3
 #define GSVC_RAST_TILE 16 /* tile edge in pixels; tile ids are row-major over ceil(W/16) x ceil(H/16) */
 #define GSVC_RAST_MAX_VIEWS 16 /* views per batched call (gsvc_rast_*_views) */
 
@@ -218,6 +218,22 @@ GSVC_RAST_API int gsvc_rast_backward_views(const gsvc_rast_settings *st, int32_t
                              int32_t scratch_is_zero, const float *dL_dout, float *dL_dmeans3D, float *dL_dmeans2D,
                              float *dL_dcolors, float *dL_dopacities, float *dL_dscales, float *dL_drotations,
                              float *dL_dcov3D, float *dL_dshs, float *dL_packed, void *stream);
+
+/*
+ * Densification statistic of the step at the rasterizer boundary.  The reference calls
+ * GaussianModel.training_statis once per rendered view (pipeline/train.py:559-565); per view it takes the norm of
+ * the screen-space gradient of the Gaussians that were drawn — `torch.norm(viewspace_points.grad[radii > 0, :2])`,
+ * scene/gaussian_model.py:1311 — and adds it, and a count of 1, into per-offset accumulators (:1313-1314).  This is
+ * the rasterizer-side half for all views of a step in one stream pass:
+ *     stats[g*stride + 0] (+)= sum_v [radii[v*P+g] > 0] * |dL_dmeans2D[v][g][0:2]|
+ *     stats[g*stride + 1] (+)= sum_v [radii[v*P+g] > 0]
+ * dL_dmeans2D [n_views,P,3] and radii [n_views,P] as gsvc_rast_backward_views / gsvc_rast_forward_views_launch write
+ * them (n_views = 1: the single-view call's [P,3] and [P]).  accumulate = 0 overwrites, 1 adds.  Under frame
+ * sharding the [P,2] rows are summed over the ranks with the gradients (gsvc_b200/sharding.py), which gives every
+ * rank the statistic of ALL the step's views: densification decisions stay identical across ranks.
+ */
+GSVC_RAST_API int gsvc_rast_densify_stats(int32_t n_views, int32_t P, const float *dL_dmeans2D, const int32_t *radii,
+                            float *stats, int64_t stride, int32_t accumulate, void *stream);
 
 /*
  * Stage exports for bit-exact parity tests (not used on the hot path).

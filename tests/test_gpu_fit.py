@@ -12,3 +12,5 @@ def test_fit_window_converges(cuda_device):
     assert all(l == l for l in losses)                      # no NaN
     first, last = sum(losses[:5]) / 5, sum(losses[-5:]) / 5
     assert last < 0.6 * first, (first, last)
+    d = fit.last_densify                                    # the densification statistic rode along
+    assert 0 < d["seen"] <= 6000 and 0 <= d["candidates"] <= d["seen"] and d["checksum"] > 0

@@ -203,3 +203,44 @@ def test_frame_streamer_matches_single_frames(cuda_device):
                                      rotations=params["rotations"])
             assert torch.equal(got[i], ref), f"frame {frames[i]}"
     assert not torch.equal(got[0], got[5])
+
+
+def test_densify_stats_equals_the_reference_expression(cuda_device):
+    """sharding.densify_stats == what four training_statis calls accumulate at the rasterizer boundary
+    (scene/gaussian_model.py:1311-1314: norm of viewspace_points.grad[radii > 0, :2], a count of 1 per view)."""
+    from gsvc_b200 import sharding
+    from gsvc_b200.views import rasterize_views
+    P, W, H = 15000, 192, 128
+    scenes = _scenes(P, W, H, 192, seed=47, frames=(96, 97))
+    p = _leaves(scenes[0], cuda_device)
+    m2d = torch.zeros((4, P, 3), device=cuda_device, requires_grad=True)
+    images, radii, n = rasterize_views([product_settings(s, cuda_device) for s in scenes], means3D=p["means3D"],
+                                       opacities=p["opacities"], means2D=m2d, colors_precomp=p["colors_precomp"],
+                                       scales=p["scales"], rotations=p["rotations"])
+    dL = torch.randn(images.shape, generator=torch.Generator().manual_seed(3)).to(cuda_device)
+    images.backward(dL)
+    accum = torch.zeros((P, 1), device=cuda_device)
+    denom = torch.zeros((P, 1), device=cuda_device)
+    for v in range(4):                                           # the reference's four training_statis calls
+        update_filter = radii[v] > 0
+        accum[update_filter] += torch.norm(m2d.grad[v][update_filter, :2], dim=-1, keepdim=True)
+        denom[update_filter] += 1
+    assert int((denom > 0).sum()) > 1000 and float(accum.max()) > 0
+    stats = sharding.densify_stats(m2d.grad, radii)
+    assert torch.equal(stats[:, 1:2], denom)
+    assert (stats[:, 0:1] - accum).abs().max() <= 1e-6 * accum.abs().max()
+    # into the strided view of the one-collective step buffer, accumulating a second step on top
+    flat, packed, view = sharding.step_buffer(P, cuda_device)
+    assert flat.numel() == P * 16 and packed.shape == (P, 14) and view.shape == (P, 2)
+    sharding.densify_stats(m2d.grad, radii, out=view)
+    sharding.densify_stats(m2d.grad, radii, out=view, accumulate=True)
+    assert torch.equal(view, 2 * stats) and not bool(packed.count_nonzero())
+    # single-view shapes ([P,3], [P]) and errors
+    one = sharding.densify_stats(m2d.grad[2], radii[2])
+    vis = radii[2] > 0
+    assert torch.equal(one[:, 1], vis.float())
+    assert (one[:, 0] - torch.norm(m2d.grad[2][:, :2], dim=-1) * vis).abs().max() <= 1e-6 * one[:, 0].max()
+    with pytest.raises(Exception):
+        sharding.densify_stats(m2d.grad, radii[:2])
+    with pytest.raises(Exception):
+        sharding.densify_stats(m2d.grad.cpu(), radii.cpu())
