@@ -123,6 +123,15 @@ def main():
     if rank == 0:
         print(f"L1 {losses[0]:.5f} -> {losses[-1]:.5f}")
     if world > 1:
+        # every rank must hold the same statistic (it decides densification): compare the checksums
+        mine = torch.tensor([fit.last_densify["checksum"], float(fit.last_densify["candidates"])], dtype=torch.float64,
+                            device=device)
+        every = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        assert all(torch.equal(e, every[0]) for e in every), every
+        if rank == 0:
+            print(f"densification statistic identical on all {world} ranks")
+    if world > 1:
         dist.destroy_process_group()
 
 
