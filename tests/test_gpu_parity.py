@@ -352,6 +352,48 @@ def test_plain_c_host_matches_oracle(cuda_device, tmp_path):
         assert _rel_err(a[ok], go[k].reshape(P, -1)[ok]) <= GRAD_RTOL, k
 
 
+def test_two_host_threads_on_their_own_streams(cuda_device):
+    """Two host threads, each with its own CUDA stream and scene, call forward + backward concurrently: the
+    per-thread state (pinned count slot and ticket, error text, overflow switch) must not cross; every result
+    equals the serial one (images bit-exact, gradients up to the order of the atomics)."""
+    import threading
+    scenes = [make_scene(P=7000, W=160, H=96, F=160, seed=71, back=False),
+              make_scene(P=9000, W=200, H=120, F=160, seed=72, back=True)]
+    dLs = [torch.randn((3, sc["oracle_settings"].image_height, sc["oracle_settings"].image_width),
+                       generator=torch.Generator().manual_seed(i)).to(cuda_device) for i, sc in enumerate(scenes)]
+
+    def once(i):
+        g, m2d, color, radii, n = _run_product(scenes[i], cuda_device)
+        color.backward(dLs[i])
+        return color.detach(), radii, n, [g[k].grad for k in ("means3D", "opacities", "scales", "rotations", "colors_precomp")]
+
+    serial = [once(0), once(1)]
+    torch.cuda.synchronize(cuda_device)
+    errors, results = [], [[], []]
+
+    def worker(i):
+        try:
+            stream = torch.cuda.Stream(cuda_device)
+            with torch.cuda.stream(stream):
+                for _ in range(25):
+                    results[i].append(once(i))
+            stream.synchronize()
+        except Exception as e:          # surfaced below: an assert in a thread would otherwise be lost
+            errors.append((i, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
+    for i in range(2):
+        c0, r0, n0, g0 = serial[i]
+        assert len(results[i]) == 25
+        for c, r, n, gr in results[i]:
+            assert n == n0 and torch.equal(c, c0) and torch.equal(r, r0)
+            for a, b in zip(gr, g0):
+                assert (a - b).abs().max() <= ATOMIC_RTOL * b.abs().max()
+
+
 def test_heavy_tile_uses_global_sort_fallback(cuda_device):
     """> 4096 instances on one tile: the per-tile sort leaves shared memory; order must stay exact."""
     from gsvc_b200.rasterizer import RasterState
