@@ -118,6 +118,7 @@ def main():
     torch.cuda.set_device(device)
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")   # collectives beside full-occupancy blend kernels
         dist.init_process_group("nccl", device_id=device)
     losses = fit(device, args.iters, args.P, rank=rank, world=world, log=print if rank == 0 else None)
     if rank == 0:

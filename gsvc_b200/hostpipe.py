@@ -21,6 +21,9 @@ replicated on the devices but the HOST state is sharded by rows — rank r uploa
 [r·P/G, (r+1)·P/G) of each parameter segment and the devices all-gather the rest over NVLink; the
 gradients are reduce-scattered and rank r reads back only its rows.  PCIe then carries 1/G of the bytes
 per rank (the host link, not the GPUs, is what G replicated uploads would saturate).
+The collectives run beside the blend kernels, which keep every SM full: start the process group with
+TORCH_NCCL_HIGH_PRIORITY=1 (bench.py and examples/fit_window.py do) so that NCCL's CTAs are scheduled ahead of the
+blend grid's pending ones instead of in its tail.
 """
 from __future__ import annotations
 
