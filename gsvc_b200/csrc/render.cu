@@ -29,7 +29,6 @@ constexpr int BLEND_THREADS = 128;  // 4 warps x (8x8 pixels), 2 pixels per lane
 constexpr int BLEND_WARPS = BLEND_THREADS / 32;
 constexpr int BATCH = 256;          // Gaussians staged per round (2 per thread)
 constexpr unsigned FULL = 0xffffffffu;
-constexpr float LOG2E = 1.4426950408889634f;
 
 __device__ __forceinline__ float ex2_approx(float x)
 {
@@ -59,13 +58,15 @@ __device__ __forceinline__ f2 mk2(float lo, float hi)
 __device__ __forceinline__ f2 bc2(float s) { return mk2(s, s); }
 __device__ __forceinline__ float lo(f2 a)
 {
-    float x, y;
+    float x;
+    [[maybe_unused]] float y;
     asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v));
     return x;
 }
 __device__ __forceinline__ float hi(f2 a)
 {
-    float x, y;
+    [[maybe_unused]] float x;
+    float y;
     asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v));
     return y;
 }
