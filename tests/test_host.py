@@ -169,6 +169,50 @@ def test_frame_sharded_allreduce_equals_single_rank(tmp_path):
     assert (r0 - single).abs().max() <= 1e-6 * single.abs().max() + 1e-12
 
 
+def _reference_stats(m2d_grad, radii):
+    """What four training_statis calls accumulate (scene/gaussian_model.py:1311-1314), in plain torch."""
+    P = radii.shape[1]
+    accum, denom = torch.zeros(P), torch.zeros(P)
+    for v in range(radii.shape[0]):
+        f = radii[v] > 0
+        accum[f] += torch.norm(m2d_grad[v][f, :2], dim=-1)
+        denom[f] += 1
+    return torch.stack([accum, denom], 1)
+
+
+def _stats_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    P = 300
+    gen = torch.Generator().manual_seed(50 + rank)                 # every rank sees its own frames
+    flat, packed, stats = sharding.step_buffer(P, "cpu")
+    packed.copy_(torch.randn(P, sharding.GRAD_WIDTH, generator=gen))
+    m2d = torch.randn(4, P, 3, generator=gen)
+    radii = (torch.rand(4, P, generator=gen) > 0.5).int() * 7
+    stats.copy_(_reference_stats(m2d, radii))                      # the CUDA kernel's job on a GPU box
+    mine = flat.clone()
+    sharding.allreduce_grads(flat)                                 # ONE collective: gradients + statistic
+    torch.save((mine, flat), os.path.join(out_dir, f"stats{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_step_buffer_carries_gradients_and_densification_statistic_in_one_collective(tmp_path):
+    """sharding.step_buffer: [P,14] gradients and the [P,2] densification statistic are views of ONE flat buffer,
+    so a single all-reduce gives every rank the sums over all ranks' views (world_size 2, gloo)."""
+    flat, packed, stats = sharding.step_buffer(5, "cpu")
+    assert flat.numel() == 5 * 16 and packed.shape == (5, 14) and stats.shape == (5, 2)
+    packed.fill_(1.0); stats.fill_(2.0)
+    assert float(flat.sum()) == 5 * 14 + 5 * 2 * 2                 # disjoint views covering the buffer
+    from gsvc_b200.rasterizer import RasterizerError
+    with pytest.raises(RasterizerError):                           # no CPU fallback for the kernel itself
+        sharding.densify_stats(torch.zeros(2, 5, 3), torch.zeros(2, 5, dtype=torch.int32))
+    port = _free_port()
+    mp.spawn(_stats_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    (m0, r0), (m1, r1) = torch.load(tmp_path / "stats0.pt"), torch.load(tmp_path / "stats1.pt")
+    assert torch.equal(r0, r1) and torch.equal(r0, m0 + m1)
+    assert float(r0[300 * 14:].view(300, 2)[:, 1].max()) <= 8      # at most 4 views per rank drew a Gaussian
+
+
 def _cpu_settings(W=64, H=48, F=64, back=False):
     from gsvc_b200.frames import CubeGeometry
     from gsvc_b200.rasterizer import GaussianRasterizationSettings
