@@ -106,12 +106,12 @@ __global__ void __launch_bounds__(256, 3) preprocess_backward_kernel(DevSettings
     float dm2[2] = {0.f, 0.f};
     if (vis) {
         // blend-backward accumulators: raw moments of w = Gs dL/dGs (see render.cu)
-        //   a0 = (S w dx, S w dy, S w dx^2, S w dx dy)  a1 = (S w dy^2, dL/dopacity, dL/dr, dL/dg)  a2.x = dL/db
+        //   a0 = (S w dx, S w dy, S w dx^2, S w dx dy)  a1 = (S w dy^2, S w, dL/dr, dL/dg)  a2.x = dL/db
         const float4 a0 = acc[3 * gv], a1 = acc[3 * gv + 1], a2 = acc[3 * gv + 2];
         const float4 con = geo.feat1[gv];  // conic (A, B, C), opacity
         const float gpx = -(con.x * a0.x + con.y * a0.y), gpy = -(con.z * a0.y + con.y * a0.x);
         const float gA = -0.5f * a0.z, gB = -a0.w, gC = -0.5f * a1.x;
-        dop += a1.y;
+        dop += con.w != 0.f ? a1.y / con.w : 0.f;   // a1.y = S w = opacity * S Gs dL/dalpha (zero opacity: never blended)
         const float dcv[3] = {a1.z, a1.w, a2.x};
         dcol[0] += dcv[0]; dcol[1] += dcv[1]; dcol[2] += dcv[2];
         const float w0[3] = {ldVb(s, v, 0, 0), ldVb(s, v, 0, 1), ldVb(s, v, 0, 2)};

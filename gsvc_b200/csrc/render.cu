@@ -444,42 +444,46 @@ render_backward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, c
                 const f2 dy2 = add2(bc2(f0.y), npy2);
                 const f2 nq2 = neg_falloff_log2(f1, dx, dy2);
                 const f2 Gs2 = mk2(ex2_approx(-lo(nq2)), ex2_approx(-hi(nq2)));
-                const f2 a2 = mul2(bc2(f1.w), Gs2);
-                const float aA = fminf(ALPHA_MAX, lo(a2)), aB = fminf(ALPHA_MAX, hi(a2));
+                const f2 a2 = mul2(bc2(f1.w), Gs2);                       // opacity * Gs, before the 0.99 cap
                 const unsigned int pos = (unsigned int)(pos0 - k);
-                const bool useA = (pos < S.lastA) && !(aA < ALPHA_MIN);
-                const bool useB = (pos < S.lastB) && !(aB < ALPHA_MIN);
+                // min(0.99, a) < 1/255  <=>  a < 1/255: the floor is tested on the uncapped value
+                const bool useA = (pos < S.lastA) && !(lo(a2) < ALPHA_MIN);
+                const bool useB = (pos < S.lastB) && !(hi(a2) < ALPHA_MIN);
                 // (no warp vote here: after the exact culling above 99.9 % of the evaluations that reach this point
                 //  contribute to at least one pixel — ncu source counters — and a pair that does not adds zeros)
 
                 // Branch-free: a pair that does not contribute is blended with alpha = 0, which leaves T, the
                 // behind-colour sum and every gradient sum unchanged (bit-identically).
-                const f2 ae2 = mk2(useA ? aA : 0.f, useB ? aB : 0.f);
+                // The masked UNCAPPED value am does double duty: capped it is the blended alpha, and times
+                // dL/dalpha it is w = opacity * Gs * dL/dalpha (U4: straight through the cap), already zero for a
+                // pair that does not contribute — no separate masking of dL/dalpha.
+                const f2 am2 = mk2(useA ? lo(a2) : 0.f, useB ? hi(a2) : 0.f);
+                const f2 ae2 = mk2(fminf(ALPHA_MAX, lo(am2)), fminf(ALPHA_MAX, hi(am2)));
                 const f2 om2 = sub2(bc2(1.f), ae2);
                 const f2 ra2 = mk2(rcp_approx(lo(om2)), rcp_approx(hi(om2)));
                 const f2 T2 = mul2(mk2(S.TA, S.TB), ra2);                 // T_i = T_{i+1} / (1 - alpha_i)
                 S.TA = lo(T2); S.TB = hi(T2);
                 const f2 cg2 = fma2(bc2(f2v.x), S.g0, fma2(bc2(f2v.y), S.g1, mul2(bc2(f2v.z), S.g2)));
                 const f2 Sg2 = mk2(S.SgA, S.SgB);
-                const f2 dlar = fma2(T2, cg2, neg2(mul2(ra2, Sg2)));       // dL/dalpha
-                const f2 dla2 = mk2(useA ? lo(dlar) : 0.f, useB ? hi(dlar) : 0.f);  // U4: straight through the 0.99 cap
+                const f2 dla2 = fma2(T2, cg2, neg2(mul2(ra2, Sg2)));       // dL/dalpha
                 const f2 dchan2 = mul2(ae2, T2);
                 { const f2 n = fma2(dchan2, cg2, Sg2); S.SgA = lo(n); S.SgB = hi(n); }
-                const f2 gd2 = mul2(Gs2, dla2);
-                const f2 w2 = mul2(bc2(f1.w), gd2);                        // w = opacity * Gs * dL/dalpha
+                const f2 w2 = mul2(am2, dla2);                             // w = opacity * Gs * dL/dalpha
                 const f2 wy2 = mul2(w2, dy2);
                 const f2 wyy2 = mul2(wy2, dy2);
                 const f2 cr2 = mul2(dchan2, S.g0), cgn2 = mul2(dchan2, S.g1), cb2 = mul2(dchan2, S.g2);
                 // Per-pair sums are raw moments of w = Gs * dL/dGs; the per-Gaussian kernel turns them into
                 // dL/dpix and dL/dconic (it knows A,B,C), which keeps ~9 FP32 ops out of this loop:
-                //   v = (S w dx, S w dy, S w dx^2, S w dx dy, S w dy^2, S Gs dL/dalpha, dL/dr, dL/dg), d_b = dL/db
+                //   v = (S w dx, S w dy, S w dx^2, S w dx dy, S w dy^2, S w, dL/dr, dL/dg), d_b = dL/db
+                // (S w = opacity * S Gs dL/dalpha: the per-Gaussian kernel divides by the opacity for dL/dopacity)
                 float v[8];
-                v[0] = (lo(w2) + hi(w2)) * dx;
+                const float sw = lo(w2) + hi(w2);
+                v[0] = sw * dx;
                 v[1] = lo(wy2) + hi(wy2);
                 v[2] = v[0] * dx;
                 v[3] = v[1] * dx;
                 v[4] = lo(wyy2) + hi(wyy2);
-                v[5] = lo(gd2) + hi(gd2);
+                v[5] = sw;
                 v[6] = lo(cr2) + hi(cr2);
                 v[7] = lo(cgn2) + hi(cgn2);
                 float d_b = lo(cb2) + hi(cb2);
