@@ -301,3 +301,38 @@ def test_bench_reference_arm_prints_one_json_line():
     t, full, h = bench.cpu_step(geom, 32, g, rows_div=1)
     t2, full2, h2 = bench.cpu_step(geom, 32, g, rows_div=3)
     assert h == 96 and h2 == 32 and abs(full - t) < 1e-9 and full2 >= t2 > 0
+
+
+def test_slab_index_range_never_drops_an_anchor_inside_the_slab():
+    """SURVEY.md §8f row f4 (host side): for z-sorted anchors, the index range from the codec-style interval table
+    (frames.z_interval_table / slab_index_range, utils/encodings.py:827-862) contains EVERY anchor with
+    |z - z_frame| <= threshold — for clustered, uniform, duplicate-heavy and single-anchor sets, slabs inside,
+    straddling and outside the data — and is not wider than the slab plus two intervals on each side."""
+    from gsvc_b200.frames import slab_index_range, z_interval_table
+    rng = np.random.default_rng(0)
+    for trial in range(300):
+        n = int(rng.choice([1, 2, 7, 100, 1000]))
+        kind = trial % 4
+        if kind == 0:
+            z = rng.uniform(-0.4, 0.4, n)
+        elif kind == 1:
+            z = rng.normal(rng.uniform(-0.3, 0.3), 0.02, n)
+        elif kind == 2:
+            z = np.round(rng.uniform(-0.4, 0.4, n), 2)              # many anchors exactly on interval edges
+        else:
+            z = np.full(n, rng.uniform(-0.4, 0.4))
+        z = torch.as_tensor(np.sort(z.astype(np.float32)))
+        interval = float(rng.choice([0.01, 0.003, 0.05]))
+        table = z_interval_table(z, interval)
+        for _ in range(5):
+            zf, thr = float(rng.uniform(-0.6, 0.6)), float(rng.choice([0.02, 0.05, 0.2]))
+            lo, hi = slab_index_range(table, zf, thr)
+            assert 0 <= lo <= hi <= n
+            inside = torch.nonzero((z.double() - zf).abs() <= thr).flatten()
+            if inside.numel():
+                assert lo <= int(inside[0]) and int(inside[-1]) < hi, (trial, lo, hi, int(inside[0]), int(inside[-1]))
+            kept = z[lo:hi].double()
+            if kept.numel():
+                assert float((kept - zf).abs().max()) <= thr + 3 * interval + 1e-6
+    with pytest.raises(ValueError):
+        z_interval_table(torch.tensor([0.2, 0.1]))
