@@ -165,8 +165,11 @@ def bin_and_sort(st: OracleSettings, pre):
 
 
 def forward(st: OracleSettings, means3D, opacities, scales=None, rotations=None, cov3D_precomp=None,
-            colors_precomp=None, shs=None, frag_eps: float = 4e-6):
-    """Full forward: returns dict(color[3,H,W], radii[P], num_rendered, + all intermediate state)."""
+            colors_precomp=None, shs=None, frag_eps: float = 4e-6, referee: bool = False):
+    """Full forward: returns dict(color[3,H,W], radii[P], num_rendered, + all intermediate state).
+    `referee`: evaluate the blend exponent in double (the exact value of SPEC's formula on the fp32 conic) and
+    report as `fragile` only what a well-conditioned fp32 implementation cannot decide — see splat_oracle.c
+    orc_set_power_mode.  Default off: the fp32 three-term form every GPU parity test is held to."""
     pre = preprocess(st, means3D, scales, rotations, cov3D_precomp, opacities, colors_precomp, shs)
     b = bin_and_sort(st, pre)
     H, W = st.image_height, st.image_width
@@ -176,14 +179,15 @@ def forward(st: OracleSettings, means3D, opacities, scales=None, rotations=None,
     fragile = np.zeros((H, W), np.uint8)
     pl = b["point_list"] if b["R"] > 0 else np.zeros(1, np.uint32)
     cs = st.to_c(pre["_inputs"]["sh_M"])
+    lib().orc_set_power_mode(C.c_int(1 if referee else 0))
     lib().orc_render_forward(C.byref(cs), _p(b["ranges"]), _p(pl), _p(pre["xy"]), _p(pre["conic_opacity"]),
                              _p(pre["rgb"]), _p(color), _p(final_T), _p(n_contrib), _p(fragile),
                              C.c_float(frag_eps))
     return dict(color=color, radii=pre["radii"], num_rendered=b["R"], final_T=final_T, n_contrib=n_contrib,
-                fragile=fragile.astype(bool), pre=pre, bin=b, settings=st)
+                fragile=fragile.astype(bool), pre=pre, bin=b, settings=st, referee=bool(referee))
 
 
-def backward(fwd, dL_dout):
+def backward(fwd, dL_dout, narrow_touched: bool = False):
     """A.4: returns grads dict (float64) for means3D, means2D, scales, rotations | cov3D_precomp,
     colors_precomp | shs, opacities, plus `touched_fragile[P]`."""
     st: OracleSettings = fwd["settings"]
@@ -199,6 +203,8 @@ def backward(fwd, dL_dout):
     fragile = np.ascontiguousarray(fwd["fragile"].astype(np.uint8))
     pl = b["point_list"] if b["R"] > 0 else np.zeros(1, np.uint32)
     cs = st.to_c(inp["sh_M"])
+    lib().orc_set_touched_mode(C.c_int(1 if narrow_touched else 0))   # see splat_oracle.c: default = whole tile list
+    lib().orc_set_power_mode(C.c_int(1 if fwd.get("referee") else 0))     # replay on the forward's own values
     lib().orc_render_backward(C.byref(cs), _p(b["ranges"]), _p(pl), _p(pre["xy"]), _p(pre["conic_opacity"]),
                               _p(pre["rgb"]), _p(fwd["final_T"]), _p(fwd["n_contrib"]), _p(dL_dout), C.c_int(P),
                               _p(d_pix), _p(d_conic), _p(d_op), _p(d_rgb), _p(fragile), _p(touched))

@@ -164,7 +164,7 @@ def bin_and_sort(st, pre):
                 unsorted_vals=gid.astype(np.uint32))
 
 
-def _blend_tiles(st, tiles, ranges, point_list, pix, conic, opac, rgb, bg, dtype):
+def _blend_tiles(st, tiles, ranges, point_list, pix, conic, opac, rgb, bg, dtype, exponent="quadratic"):
     """Blend a batch of tiles, padded to the longest list. Returns color [B,256,3], final_T, n_contrib [B,256]."""
     W = int(st.image_width)
     gx = (W + TILE - 1) // TILE
@@ -192,8 +192,32 @@ def _blend_tiles(st, tiles, ranges, point_list, pix, conic, opac, rgb, bg, dtype
     grgb = rgb[gid_t]       # [B,L,3]
     dx = gxy[:, None, :, 0] - px[:, :, None]
     dy = gxy[:, None, :, 1] - py[:, :, None]
-    power = -0.5 * (gcon[:, None, :, 0] * dx * dx + gcon[:, None, :, 2] * dy * dy) - gcon[:, None, :, 1] * dx * dy
-    Gs = torch.exp(power)
+    if exponent == "quadratic":
+        power = -0.5 * (gcon[:, None, :, 0] * dx * dx + gcon[:, None, :, 2] * dy * dy) - gcon[:, None, :, 1] * dx * dy
+        Gs = torch.exp(power)
+    else:
+        # The CUDA blend's evaluation order (gsvc_b200/csrc/preprocess.cu feat3, render.cu neg_falloff_log2):
+        # -power*log2(e) as the sum of squares (l11 dx + l21 dy)^2 + (l22 dy)^2, L the Cholesky factor of the conic
+        # times log2(e)/2 with the Schur complement from a compensated A*C - B*B; Gs = 2^-q.  Same function of
+        # (A, B, C, dx, dy), different rounding: what tests/test_oracle.py uses to check that the C oracle's
+        # `fragile` map covers the pixels where two correct fp32 evaluations may disagree.
+        cA, cB, cC = gcon[..., 0], gcon[..., 1], gcon[..., 2]
+        kL = 0.5 * 1.4426950408889634
+        pac, pbb = cA * cC, cB * cB
+        with torch.no_grad():   # exact residuals of the two products (what fmaf(a, c, -a*c) returns)
+            rac = (cA.double() * cC.double() - pac.double()).to(dtype)
+            rbb = (cB.double() * cB.double() - pbb.double()).to(dtype)
+        det_c = (pac - pbb) + (rac - rbb)
+        aL = cA * kL
+        r11 = torch.rsqrt(aL)
+        l11, l21 = aL * r11, (cB * kL) * r11
+        d22 = torch.clamp(det_c / cA * kL, min=1e-30)
+        l22 = d22 * torch.rsqrt(d22)
+        u = l21[:, None, :] * dy + l11[:, None, :] * dx
+        v = l22[:, None, :] * dy
+        q = u * u + v * v
+        power = -q                 # <= 0 by construction (in units of log2)
+        Gs = torch.exp2(power)
     a_raw = gop[:, None, :] * Gs
     alpha = a_raw + (torch.clamp(a_raw, max=ALPHA_MAX) - a_raw).detach()  # U4 straight-through
     with torch.no_grad():
@@ -215,7 +239,8 @@ def _blend_tiles(st, tiles, ranges, point_list, pix, conic, opac, rgb, bg, dtype
 
 
 def forward(st, means3D, opacities, scales=None, rotations=None, cov3D_precomp=None, colors_precomp=None,
-            shs=None, dtype=torch.float32, requires_grad=False, elem_budget=6_000_000, tile_subset=None):
+            shs=None, dtype=torch.float32, requires_grad=False, elem_budget=6_000_000, tile_subset=None,
+            exponent="quadratic"):
     """Full forward. Returns dict(color [3,H,W] torch, radii, num_rendered, keys, point_list, ranges, leaves)."""
     import time as _time
     _t0 = _time.perf_counter()
@@ -263,7 +288,7 @@ def forward(st, means3D, opacities, scales=None, rotations=None, cov3D_precomp=N
         tiles = order[i:i + nb]
         i += nb
         col, fT, nc, px, py = _blend_tiles(st, tiles, ranges, b["point_list"], pix, pre["conic"], pre["opac"],
-                                           pre["rgb"], bg, dtype)
+                                           pre["rgb"], bg, dtype, exponent)
         pieces.append((col, fT, nc, px, py))
     # scatter pieces into the padded image (index_put keeps autograd)
     cols = torch.cat([p_[0].reshape(-1, 3) for p_ in pieces])
