@@ -103,7 +103,8 @@ def preprocess(st, means3D, scales=None, rotations=None, cov3D_precomp=None, opa
     with torch.no_grad():
         ok = (pv[:, 2].abs() <= float(st.threshold)) & (det != 0)
     det_safe = torch.where(ok, det, torch.ones_like(det))
-    conic = torch.stack([c / det_safe, -b / det_safe, a / det_safe], dim=-1)
+    det_inv = 1.0 / det_safe          # as the C oracle and the kernels do: one reciprocal, three products
+    conic = torch.stack([c * det_inv, -b * det_inv, a * det_inv], dim=-1)
     pix = (pv[:, :2] - torch.tensor([float(st.x_min), float(st.y_min)], dtype=dtype)) * scale - 0.5
     with torch.no_grad():
         mid = 0.5 * (a + c)

@@ -1,0 +1,81 @@
+"""CPU-only randomised sweep of the oracle's REFEREE mode (oracle/splat_oracle.c orc_set_power_mode, docs/SPEC.md):
+the kernels' evaluation order of the blend exponent — sum of squares of the conic's Cholesky factor, restated in
+oracle/torch_oracle.py (exponent="cholesky", fp32, gradients by autograd) — against the C oracle with the exponent
+in double, the ambiguity of a well-conditioned fp32 evaluation as `fragile`, and the gradient exclusion narrowed to
+the Gaussians that reach a fragile pixel.  Random image sizes, densities, views, backgrounds and axis ratios from 1:1
+to 256:1.  Per case: same binning, pixels <= 1e-5 off fragile pixels, gradients <= 1e-4 (scales / rotations only up to 4:1 axes:
+beyond, the proxy's own fp32 covariance chain is the limit); reported: how much was set aside.  No GPU involved: this qualifies the CHECKER the next round's GPU sweeps will switch to.
+Usage: python tests/fuzz_referee.py [n_cases=60] [seed=0]"""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from oracle import c_oracle, torch_oracle
+from tests.scenes import make_scene, np_inputs
+
+NAMES = ("means3D", "scales", "rotations", "opacities", "colors_precomp")
+
+
+def run(n_cases=60, seed=0, verbose=True):
+    rng = np.random.default_rng(seed)
+    worst = dict(fwd=0.0, grad=0.0, fragile=0.0, compared=1.0, legacy_fragile=0.0)
+    t0 = time.time()
+    for case in range(n_cases):
+        W = int(rng.choice([33, 64, 100, 160]))
+        H = int(rng.choice([16, 40, 64, 96]))
+        tiles = ((W + 15) // 16) * ((H + 15) // 16)
+        P = int(min(8000, max(1, float(rng.choice([4, 20, 100, 400])) * tiles / 3.0)))
+        stretch = float(rng.choice([1.0, 2.0, 4.0, 8.0, 16.0]))
+        back = bool(rng.integers(2))
+        bg = tuple(float(x) for x in rng.random(3)) if rng.integers(2) else (0.0, 0.0, 0.0)
+        scene = make_scene(P=P, W=W, H=H, F=int(rng.choice([64, 128])), seed=int(rng.integers(1 << 30)), back=back,
+                           bg=bg, scale_modifier=float(rng.choice([1.0, 0.5, 2.0])))
+        g = {k: v.clone() for k, v in scene["gaussians"].items()}
+        g["scales"][:, 0] *= stretch
+        g["scales"][:, 1] /= stretch
+        gi, st = np_inputs(g), scene["oracle_settings"]
+        args = (st, gi["means3D"], gi["opacities"], gi["scales"], gi["rotations"])
+        fc = c_oracle.forward(*args, colors_precomp=gi["colors_precomp"], referee=True)
+        legacy = c_oracle.forward(*args, colors_precomp=gi["colors_precomp"])
+        ft = torch_oracle.forward(st, g["means3D"], g["opacities"], g["scales"], g["rotations"],
+                                  colors_precomp=g["colors_precomp"], requires_grad=True, exponent="cholesky")
+        assert ft["num_rendered"] == fc["num_rendered"] and np.array_equal(ft["keys"], fc["bin"]["keys"]), case
+        solid = ~fc["fragile"]
+        err = float(np.abs(ft["color"].detach().numpy() - fc["color"])[:, solid].max(initial=0.0))
+        assert err <= 1e-5, (case, err, stretch)
+        dL = torch.randn(3, H, W, generator=torch.Generator().manual_seed(case)).numpy()
+        gc, gt = c_oracle.backward(fc, dL, narrow_touched=True), torch_oracle.backward(ft, dL)
+        ok = ~gc["touched_fragile"]
+        vis = fc["radii"] > 0
+        rel = 0.0
+        for k in NAMES:
+            a = np.asarray(gt[k]).reshape(P, -1)[ok]
+            b = gc[k].reshape(P, -1)[ok]
+            if not b.size:
+                continue
+            r = float(np.abs(a - b).max() / (np.abs(gc[k]).max() + 1e-30))
+            # scales / rotations of needles are not compared: the PROXY differentiates the inverse of a nearly
+            # singular 2x2 covariance in fp32 (autograd) and is itself off by 1e-4..1e-3 there, with either form of
+            # the exponent; the kernels and the C oracle run that chain in double and are held to each other by the
+            # GPU tests.  What the blend produces (position, opacity, colour gradients) is compared for every case.
+            if k in ("scales", "rotations") and stretch > 2.0:
+                continue
+            assert r <= 1e-4, (case, k, r, stretch)
+            rel = max(rel, r)
+        compared = float(ok[vis].mean()) if vis.any() else 1.0
+        worst["fwd"] = max(worst["fwd"], err); worst["grad"] = max(worst["grad"], rel)
+        worst["fragile"] = max(worst["fragile"], float(fc["fragile"].mean()))
+        worst["legacy_fragile"] = max(worst["legacy_fragile"], float(legacy["fragile"].mean()))
+        worst["compared"] = min(worst["compared"], compared)
+        if verbose:
+            print(f"case {case:3d} ok: {W}x{H} P={P} R={fc['num_rendered']} axes {stretch * stretch:.0f}:1 back={back} "
+                  f"fwd_err={err:.1e} grad={rel:.1e} fragile={fc['fragile'].mean():.1e} (default oracle "
+                  f"{legacy['fragile'].mean():.1e}) compared={compared:.2f}", flush=True)
+    print(f"{n_cases} referee cases ok in {time.time() - t0:.0f} s; worst fwd err {worst['fwd']:.2e}, worst grad rel err "
+          f"{worst['grad']:.2e}; largest fragile fraction {worst['fragile']:.1e} (default oracle on the same scenes: "
+          f"{worst['legacy_fragile']:.1e}); smallest compared share of the visible Gaussians {worst['compared']:.2f}")
+    return worst
+
+
+if __name__ == "__main__":
+    run(int(sys.argv[1]) if len(sys.argv) > 1 else 60, int(sys.argv[2]) if len(sys.argv) > 2 else 0)
