@@ -2,7 +2,8 @@
 size and images smaller than a tile), Gaussian counts, densities (bucket sizes across every sort path: <=32, 64,
 128, 256, 512 per warp, CTA-wide shared, in-place global), views, backgrounds, scale modifiers; single calls through
 the records of the stage exports (bit-exact), images (1e-5 off fragile pixels), gradients (1e-4 relative), and the
-same scenes through the batched-view path.  Usage: python tests/fuzz_parity.py [n_cases=40] [seed=0] [only_case] [big]   (big: 400x300 .. 1024x600, up to 400k Gaussians)"""
+same scenes through the batched-view path.  Usage: python tests/fuzz_parity.py [n_cases=40] [seed=0] [only_case] [big] [referee]   (big: 400x300 .. 1024x600, up to 400k Gaussians;
+referee: the oracle's referee mode + elongated Gaussians — not yet run on a GPU)"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -51,7 +52,7 @@ def diag_pixel(fo, got, W, bg, note=""):
           f"final_T {fo['final_T'][j_, i_]:.3e}; R={fo['num_rendered']} bg={bg} {note}")
 
 
-def run(n_cases=40, seed=0, verbose=True, only_case=None, big=False):
+def run(n_cases=40, seed=0, verbose=True, only_case=None, big=False, referee=False):
   rng = np.random.default_rng(seed)
   dev = torch.device("cuda:0")
   worst = dict(fwd=0.0, grad=0.0, frag=0.0)
@@ -71,9 +72,15 @@ def run(n_cases=40, seed=0, verbose=True, only_case=None, big=False):
       if only_case is not None and case != only_case:
           continue
       scene = make_scene(P=P, W=W, H=H, F=F, seed=scene_seed, back=back, bg=bg, scale_modifier=sm)
+      if referee:
+          # next round's checker (docs/SPEC.md "Referee mode", CPU-validated in tests/fuzz_referee.py): elongated
+          # Gaussians too (axis ratios up to 256:1), the oracle's exponent in double, narrow gradient exclusion
+          stretch = float(np.random.default_rng(scene_seed).choice([1.0, 2.0, 4.0, 8.0, 16.0]))
+          scene["gaussians"]["scales"][:, 0] *= stretch
+          scene["gaussians"]["scales"][:, 1] /= stretch
       gi = np_inputs(scene["gaussians"])
       fo = c_oracle.forward(scene["oracle_settings"], gi["means3D"], gi["opacities"], gi["scales"], gi["rotations"],
-                            colors_precomp=gi["colors_precomp"])
+                            colors_precomp=gi["colors_precomp"], referee=referee)
       rs = product_settings(scene, dev)
       g = {k: v.to(dev) for k, v in scene["gaussians"].items()}
       # stage exports through the allocator-callback form (exact capacity, scatter path)
@@ -87,7 +94,7 @@ def run(n_cases=40, seed=0, verbose=True, only_case=None, big=False):
       assert np.array_equal(ranges.cpu().numpy().view(np.uint32), fo["bin"]["ranges"]), case
       # autograd call (capacity-hint path on the second call)
       dL = torch.randn((3, H, W), generator=torch.Generator().manual_seed(case))
-      go = c_oracle.backward(fo, dL.numpy())
+      go = c_oracle.backward(fo, dL.numpy(), narrow_touched=referee)
       for rep in range(2):
           p = {k: g[k].clone().requires_grad_(True) for k in NAMES}
           m2d = torch.zeros_like(p["means3D"], requires_grad=True)
@@ -136,7 +143,7 @@ def run(n_cases=40, seed=0, verbose=True, only_case=None, big=False):
 
 
 if __name__ == "__main__":
-    big = "big" in sys.argv[1:]
-    argv = [a for a in sys.argv[1:] if a != "big"]
+    big, referee = "big" in sys.argv[1:], "referee" in sys.argv[1:]
+    argv = [a for a in sys.argv[1:] if a not in ("big", "referee")]
     run(int(argv[0]) if len(argv) > 0 else 40, int(argv[1]) if len(argv) > 1 else 0,
-        only_case=int(argv[2]) if len(argv) > 2 else None, big=big)
+        only_case=int(argv[2]) if len(argv) > 2 else None, big=big, referee=referee)
