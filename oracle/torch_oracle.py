@@ -103,8 +103,7 @@ def preprocess(st, means3D, scales=None, rotations=None, cov3D_precomp=None, opa
     with torch.no_grad():
         ok = (pv[:, 2].abs() <= float(st.threshold)) & (det != 0)
     det_safe = torch.where(ok, det, torch.ones_like(det))
-    det_inv = 1.0 / det_safe          # as the C oracle and the kernels do: one reciprocal, three products
-    conic = torch.stack([c * det_inv, -b * det_inv, a * det_inv], dim=-1)
+    conic = _ConicInverse.apply(a, b, c, det_safe)
     pix = (pv[:, :2] - torch.tensor([float(st.x_min), float(st.y_min)], dtype=dtype)) * scale - 0.5
     with torch.no_grad():
         mid = 0.5 * (a + c)
@@ -163,6 +162,32 @@ def bin_and_sort(st, pre):
         ranges[st_tile[first], 1] = last
     return dict(R=R, keys=skeys, point_list=point_list, ranges=ranges, unsorted_keys=keys,
                 unsorted_vals=gid.astype(np.uint32))
+
+
+class _ConicInverse(torch.autograd.Function):
+    """conic = (c, -b, a) / det with the forward exactly as the C oracle and the kernels compute it (one reciprocal,
+    three products, in the working precision) and the BACKWARD in double: the derivative of the inverse of a nearly
+    singular 2x2 covariance (elongated Gaussians) loses 1e-4..1e-3 in fp32, which is why the kernels
+    (preprocess_bwd.cu) and the C oracle run this chain in double too."""
+
+    @staticmethod
+    def forward(ctx, a, b, c, det_safe):
+        ctx.save_for_backward(a, b, c, det_safe)
+        det_inv = 1.0 / det_safe
+        return torch.stack([c * det_inv, -b * det_inv, a * det_inv], dim=-1)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b, c, det_safe = ctx.saved_tensors
+        ad, bd, cd, gd = a.double(), b.double(), c.double(), g.double()
+        det = ad * cd - bd * bd
+        det = torch.where(det == 0, torch.ones_like(det), det)      # culled rows: their incoming gradient is zero
+        i2 = 1.0 / (det * det)
+        gA, gB, gC = gd[:, 0], gd[:, 1], gd[:, 2]
+        ga = (-cd * cd * gA + bd * cd * gB - bd * bd * gC) * i2
+        gb = (2 * bd * cd * gA - (ad * cd + bd * bd) * gB + 2 * ad * bd * gC) * i2
+        gc = (-bd * bd * gA + ad * bd * gB - ad * ad * gC) * i2
+        return ga.to(a.dtype), gb.to(a.dtype), gc.to(a.dtype), None
 
 
 def _blend_tiles(st, tiles, ranges, point_list, pix, conic, opac, rgb, bg, dtype, exponent="quadratic"):

@@ -4,7 +4,7 @@ oracle/torch_oracle.py (exponent="cholesky", fp32, gradients by autograd) — ag
 in double, the ambiguity of a well-conditioned fp32 evaluation as `fragile`, and the gradient exclusion narrowed to
 the Gaussians that reach a fragile pixel.  Random image sizes, densities, views, backgrounds and axis ratios from 1:1
 to 256:1.  Per case: same binning, pixels <= 1e-5 off fragile pixels, gradients <= 1e-4 (scales / rotations only up to 4:1 axes:
-beyond, the proxy's own fp32 covariance chain is the limit); reported: how much was set aside.  No GPU involved: this qualifies the CHECKER the next round's GPU sweeps will switch to.
+beyond, the proxy's own fp32 accumulation is the limit); reported: how much was set aside.  No GPU involved: this qualifies the CHECKER the next round's GPU sweeps will switch to.
 Usage: python tests/fuzz_referee.py [n_cases=60] [seed=0]"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -54,10 +54,10 @@ def run(n_cases=60, seed=0, verbose=True):
             if not b.size:
                 continue
             r = float(np.abs(a - b).max() / (np.abs(gc[k]).max() + 1e-30))
-            # scales / rotations of needles are not compared: the PROXY differentiates the inverse of a nearly
-            # singular 2x2 covariance in fp32 (autograd) and is itself off by 1e-4..1e-3 there, with either form of
-            # the exponent; the kernels and the C oracle run that chain in double and are held to each other by the
-            # GPU tests.  What the blend produces (position, opacity, colour gradients) is compared for every case.
+            # scales / rotations of needles are not compared: the PROXY accumulates the blend's conic gradients and
+            # runs most of the covariance chain in fp32 (autograd) and is itself off by 1e-4..1e-3 there, with either
+            # form of the exponent; the kernels and the C oracle accumulate and chain in double and are held to each
+            # other by the GPU tests.  Position, opacity and colour gradients are compared for every case.
             if k in ("scales", "rotations") and stretch > 2.0:
                 continue
             assert r <= 1e-4, (case, k, r, stretch)
