@@ -380,6 +380,8 @@ static int forward_render_core(const gsvc_rast_settings* st, const DevSettings& 
     ImageView im = image_view(image, d.W, d.H, d.n_views);
     // the scatter cursors were consumed by a previous attempt: reset them
     CK(cudaMemsetAsync(im.tile_cursor, 0, (size_t)d.gx * d.gy * d.n_views * sizeof(unsigned int), stream), "cursor reset");
+    // ... and so was the overflow flag of that attempt (the blend backward refuses to replay an overflowed frame)
+    CK(cudaMemsetAsync(&im.hdr->overflow, 0, sizeof(unsigned int), stream), "overflow flag reset");
     if (d.accumulate)
         CK(cudaMemsetAsync(out_color, 0, (size_t)n_out * 3 * d.W * d.H * sizeof(float), stream), "zero out_color");
     return render_stages(d, P, g, im, binning, capacity, out_color, stream, dbg);
@@ -456,7 +458,7 @@ static int backward_core(const gsvc_rast_settings* st, const DevSettings& d, int
     BinView b = bin_view(const_cast<void*>(binning), capacity);
     float4* acc = static_cast<float4*>(scratch);
     PreInputs in{P, means3D, shs, colors_precomp, nullptr, scales, rotations, cov3D_precomp, 0, P};
-    { StageScope t(ST_RENDER_BWD, stream); CK(launch_render_backward(d, P, g, im, b, dL_dout, acc, scratch_is_zero != 0, stream), "render_backward"); }
+    { StageScope t(ST_RENDER_BWD, stream); CK(launch_render_backward(d, P, g, im, b, capacity, dL_dout, acc, scratch_is_zero != 0, stream), "render_backward"); }
     { StageScope t(ST_PREPROCESS_BWD, stream); CK(launch_preprocess_backward(d, in, radii, g, acc, out, stream), "preprocess_backward"); }
     return 0;
 }

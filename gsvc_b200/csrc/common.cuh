@@ -167,6 +167,22 @@ __host__ __device__ inline unsigned int ordered_u32(float z)
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
+// [P,4] float rows (quaternions and their gradients) move as ONE 16-byte access when the base pointer allows it and as
+// four scalars otherwise: the C-ABI promises nothing beyond float alignment, and a torch slice of a flat parameter
+// buffer at float offset 10*P (hostpipe / graphed layouts) is only 8-byte aligned when P is odd.
+__device__ __forceinline__ float4 ld_row4(const float* __restrict__ base, size_t row)
+{
+    if ((reinterpret_cast<uintptr_t>(base) & 15u) == 0u) return __ldg(reinterpret_cast<const float4*>(base) + row);
+    const float* p = base + 4 * row;
+    return make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+}
+__device__ __forceinline__ void st_row4(float* __restrict__ base, size_t row, float4 v)
+{
+    if ((reinterpret_cast<uintptr_t>(base) & 15u) == 0u) { reinterpret_cast<float4*>(base)[row] = v; return; }
+    float* p = base + 4 * row;
+    p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w;
+}
+
 // ---- programmatic dependent launch (sm_90+): every kernel of a forward / backward chain is launched with
 // programmaticStreamSerializationAllowed, signals launch_dependents on entry and waits for its predecessor's
 // memory before touching any data, so launch latency and prologue of kernel N+1 overlap the tail of kernel N.
@@ -277,7 +293,7 @@ cudaError_t launch_scatter(const DevSettings& s, int P, GeomView g, ImageView im
 cudaError_t launch_sort_tiles(const DevSettings& s, ImageView im, BinView b, long long cap, cudaStream_t st);
 cudaError_t launch_render_forward(const DevSettings& s, GeomView g, ImageView im, BinView b, long long cap,
                                   float* out_color, cudaStream_t st);
-cudaError_t launch_render_backward(const DevSettings& s, int P, GeomView g, ImageView im, BinView b,
+cudaError_t launch_render_backward(const DevSettings& s, int P, GeomView g, ImageView im, BinView b, long long cap,
                                    const float* dL_dout, float4* acc, bool acc_is_zero, cudaStream_t st);
 struct BwdOutputs {
     float* dL_dmeans3D; float* dL_dmeans2D; float* dL_dcolors; float* dL_dopacities;   // dL_dmeans2D is [n_views,P,3]

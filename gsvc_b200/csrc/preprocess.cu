@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(DevSettings s, PreInput
     float4 q_pre = make_float4(1.f, 0.f, 0.f, 0.f);
     if (!in.cov3D_precomp) {
         sc[0] = __ldg(in.scales + 3 * g); sc[1] = __ldg(in.scales + 3 * g + 1); sc[2] = __ldg(in.scales + 3 * g + 2);
-        q_pre = __ldg(reinterpret_cast<const float4*>(in.rotations) + g);
+        q_pre = ld_row4(in.rotations, (size_t)g);
     }
     // The CTA's view matrix (strided device tensor: 12 loads + 64-bit stride arithmetic per thread otherwise) is
     // fetched once by 12 threads and broadcast through shared memory; the Gaussian's own loads above are already

@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(256, 3) preprocess_backward_kernel(DevSettings
 #pragma unroll
             for (int k = 0; k < 6; k++) cov[k] = in.cov3D_precomp[6 * (size_t)g + k];
         } else {
-            const float4 q = reinterpret_cast<const float4*>(in.rotations)[g];
+            const float4 q = ld_row4(in.rotations, (size_t)g);
             const double r = q.x, x = q.y, y = q.z, z = q.w;
             R[0] = 1. - 2. * (y * y + z * z); R[1] = 2. * (x * y - r * z); R[2] = 2. * (x * z + r * y);
             R[3] = 2. * (x * y + r * z); R[4] = 1. - 2. * (x * x + z * z); R[5] = 2. * (y * z - r * x);
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(256, 3) preprocess_backward_kernel(DevSettings
                 }
                 dsc[j] += (float)(t * (double)s.scale_modifier);
             }
-            const float4 q = reinterpret_cast<const float4*>(in.rotations)[g];
+            const float4 q = ld_row4(in.rotations, (size_t)g);
             const double r = q.x, x = q.y, y = q.z, z = q.w;
             drot[0] += (float)(2. * (-z * gR[1] + y * gR[2] + z * gR[3] - x * gR[5] - y * gR[6] + x * gR[7]));
             drot[1] += (float)(2. * (y * gR[1] + z * gR[2] + y * gR[3] - 2. * x * gR[4] - r * gR[5] + z * gR[6] + r * gR[7] -
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(256, 3) preprocess_backward_kernel(DevSettings
     if (out.dL_dcolors) { out.dL_dcolors[3 * g] = dcol[0]; out.dL_dcolors[3 * g + 1] = dcol[1]; out.dL_dcolors[3 * g + 2] = dcol[2]; }
     if (out.dL_dopacities) out.dL_dopacities[g] = dop;
     if (out.dL_dscales) { out.dL_dscales[3 * g] = dsc[0]; out.dL_dscales[3 * g + 1] = dsc[1]; out.dL_dscales[3 * g + 2] = dsc[2]; }
-    if (out.dL_drotations) reinterpret_cast<float4*>(out.dL_drotations)[g] = make_float4(drot[0], drot[1], drot[2], drot[3]);
+    if (out.dL_drotations) st_row4(out.dL_drotations, (size_t)g, make_float4(drot[0], drot[1], drot[2], drot[3]));
     if (out.dL_dcov3D) {
 #pragma unroll
         for (int k = 0; k < 6; k++) out.dL_dcov3D[6 * (size_t)g + k] = dcov[k];

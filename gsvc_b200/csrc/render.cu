@@ -353,8 +353,8 @@ struct PairBwd {
 };
 
 __global__ void __launch_bounds__(BLEND_THREADS)
-render_backward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, const float* __restrict__ dL_dout,
-                       float* __restrict__ acc /* [P][12] */)
+render_backward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, unsigned long long cap,
+                       const float* __restrict__ dL_dout, float* __restrict__ acc /* [P][12] */)
 {
     __shared__ float4 s_feat[3 * BATCH];
     __shared__ unsigned int s_max[BLEND_WARPS];
@@ -380,6 +380,11 @@ render_backward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, c
     const uint2 rg = im.ranges[blockIdx.x];
     const int n = (int)(rg.y - rg.x);
     if (n <= 0) return;
+    // Capacity overflow (only a CUDA-graph replay can get here with one: the eager caller re-runs the forward on a
+    // larger buffer first): the forward skipped the overflowed tiles, so their final_T / n_contrib are stale and the
+    // point list beyond `cap` does not exist.  The whole launch is void — the frame is invalid and its owner is told
+    // so by capacity_ok() — hence every tile leaves before it reads a list entry.
+    if ((unsigned long long)rg.y > cap || im.hdr->overflow != 0u) return;
 
     const float bg0 = __ldg(s.bg), bg1 = __ldg(s.bg + 1), bg2 = __ldg(s.bg + 2);
     PairBwd S{};
@@ -406,7 +411,7 @@ render_backward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, c
     unsigned int bmax = 0;
 #pragma unroll
     for (int w = 0; w < BLEND_WARPS; w++) bmax = max(bmax, s_max[w]);
-    const int m_len = (int)bmax;  // list entries [0, m_len) are replayed, back to front
+    const int m_len = min((int)bmax, n);  // list entries [0, m_len) are replayed, back to front
 
     // lanes 0,4,..,28 own the 8 reduced sums (index lane/4), lane 1 the ninth: one atomic instruction
     const bool red_lane = (lane & 3) == 0 || lane == 1;
@@ -495,7 +500,7 @@ render_backward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, c
     }
 }
 
-cudaError_t launch_render_backward(const DevSettings& s, int P, GeomView g, ImageView im, BinView b,
+cudaError_t launch_render_backward(const DevSettings& s, int P, GeomView g, ImageView im, BinView b, long long cap,
                                    const float* dL_dout, float4* acc, bool acc_is_zero, cudaStream_t st)
 {
     if (!acc_is_zero) {
@@ -505,8 +510,8 @@ cudaError_t launch_render_backward(const DevSettings& s, int P, GeomView g, Imag
     const int T = s.gx * s.gy * s.n_views;
     if (T <= 0 || P <= 0) return cudaSuccess;
     count_launch();
-    return launch_pdl(render_backward_kernel, dim3(T), dim3(BLEND_THREADS), st, s, g, im, b, dL_dout,
-                      reinterpret_cast<float*>(acc));
+    return launch_pdl(render_backward_kernel, dim3(T), dim3(BLEND_THREADS), st, s, g, im, b, (unsigned long long)cap,
+                      dL_dout, reinterpret_cast<float*>(acc));
 }
 
 }  // namespace gsvc

@@ -47,6 +47,10 @@ class GraphedStep:
         self.warmup = max(int(warmup), 1)
         self.graph = None
         self.color = self.radii = None
+        # the graph's own pinned count word: its scan kernel publishes num_rendered here on every replay, whatever
+        # other graphs or eager calls of this thread do meanwhile
+        self.slot = R.CountSlot()
+        self.capacity = None
         self.recapture()
 
     def _call(self, p, means2D):
@@ -81,25 +85,26 @@ class GraphedStep:
         R.overflow_events(self.device)      # an eager warm-up call that outgrew its hint re-ran by itself: not ours
         self.num_rendered_at_capture = n
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with R.own_count_slot(self.slot), torch.cuda.graph(self.graph):
             self.color, self.radii, _ = self._run()
+        rs = self.batch.settings[0] if self.batch is not None else self.rast.raster_settings
+        key = (self.device.index, self.P, int(rs.image_height), int(rs.image_width))
+        self.capacity = R._captured_caps.get(key + ((self.batch.n_views,) if self.batch is not None else ()))
 
     def __call__(self):
         self.graph.replay()
         return self.color, self.radii, self.packed
 
     def num_rendered(self) -> int:
-        """Instance count of the last replay (call after a synchronisation)."""
-        return R.last_num_rendered()
+        """Instance count of this graph's last replay (call after a synchronisation)."""
+        return self.slot.value()
 
     def capacity_ok(self) -> bool:
         """After a synchronisation: no replay since the last check ran out of the instance capacity fixed at
         capture time (sticky device-side counter), and the last replay's published count fits too."""
-        rs = self.batch.settings[0] if self.batch is not None else self.rast.raster_settings
         if R.overflow_events(self.device) > 0:
             return False
-        return R.captured_capacity_ok(self.device, self.P, int(rs.image_height), int(rs.image_width),
-                                      self.batch.n_views if self.batch is not None else None)
+        return self.capacity is None or self.num_rendered() <= self.capacity
 
 
 class FrameStreamer:

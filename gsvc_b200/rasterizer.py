@@ -13,6 +13,7 @@ plumbing.  There is no CPU / eager fallback: CPU tensors raise.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import threading
 from typing import NamedTuple, Optional
@@ -40,10 +41,37 @@ class GaussianRasterizationSettings(NamedTuple):
     debug: bool
 
 
-# instance-capacity hint per (device, P, H, W): the last num_rendered seen, so that the binning buffer
-# can be sized before the instance count of THIS call is known (no mid-pipeline host synchronisation)
+# Instance-capacity prediction, so that the binning buffer can be sized — and scatter / sort / blend launched — before
+# the instance count of THIS call is known (no mid-pipeline host synchronisation):
+#   _capacity_hint[(device, P, H, W[, V])]  the last num_rendered seen for exactly this shape (CUDA-graph capture
+#                                           requires it: a replay's capacity is fixed);
+#   _density_hint[(device, H, W[, V])]      instances per INPUT Gaussian at this image size, a slowly decaying
+#                                           maximum.  The reference's render() hands over a different P on every
+#                                           call (the Gaussians of the anchors visible in THAT view,
+#                                           ortho_gaussian_renderer/renderer.py:28-37), so an exact-shape hint never
+#                                           hits there; the density of instances per Gaussian, however, is a
+#                                           property of the scene's scale distribution and moves slowly.
 _capacity_hint: dict = {}
+_density_hint: dict = {}
 _count_slots = threading.local()
+
+
+def _predict_capacity(key_exact, key_density, P: int):
+    """(capacity to launch with or 0 = unknown, exact-shape hint or None)."""
+    hint = _capacity_hint.get(key_exact)
+    if hint is not None:
+        return int(hint * 1.25) + 4096, hint
+    dens = _density_hint.get(key_density)
+    if dens is not None and P > 0:
+        return int(dens * P * 1.3) + 4096, None
+    return 0, None
+
+
+def _record_capacity(key_exact, key_density, P: int, num_rendered: int) -> None:
+    _capacity_hint[key_exact] = num_rendered
+    if P > 0:
+        d = num_rendered / P
+        _density_hint[key_density] = max(d, 0.97 * _density_hint.get(key_density, 0.0))
 
 
 _captured_caps: dict = {}
@@ -75,7 +103,22 @@ def overflow_events(device=None, reset: bool = True) -> int:
 
 
 class _PackedTarget:
-    buf = None  # process-wide on purpose: autograd runs backward on its own thread
+    """Target of sharding.packed_backward.  Process-wide on purpose (autograd runs the backward on its own thread),
+    and therefore SINGLE-USE per context: the first rasterizer backward that fits the buffer takes it, any further
+    backward inside the same context (a second rasterizer call of the same P in one loss.backward(), another model
+    on another thread) gets ordinary dense gradients instead of silently overwriting the first one's."""
+    buf = None
+    taken = False
+    lock = threading.Lock()
+
+    def take(self, P, device, ok: bool):
+        with self.lock:
+            b = self.buf
+            if (b is None or self.taken or not ok or tuple(b.shape) != (P, 14) or b.device != device or
+                    b.dtype != torch.float32 or not b.is_contiguous()):
+                return None
+            self.taken = True
+            return b
 
 
 _packed_target = _PackedTarget()
@@ -137,15 +180,44 @@ def _bytes(n: int, device) -> torch.Tensor:
     return torch.empty(int(n), dtype=torch.uint8, device=device)
 
 
-def _count_slot():
-    """One pinned, device-addressable 64-bit word per host thread + a ticket counter (see gsvc_rast.h)."""
+class CountSlot:
+    """A pinned, device-addressable 64-bit word the tile scan publishes `ticket << 40 | num_rendered` into."""
+
+    def __init__(self):
+        self.tensor = torch.zeros(1, dtype=torch.int64).pin_memory()
+        self.ptr = self.tensor.data_ptr()
+        self.ticket = 0
+
+    def value(self) -> int:
+        return int(self.tensor[0].item()) & ((1 << 40) - 1)
+
+
+@contextlib.contextmanager
+def own_count_slot(slot: "CountSlot"):
+    """Rasterizer calls of this thread inside the context publish their instance count to `slot` instead of the
+    thread's shared one.  A CUDA graph bakes the slot's address into its scan kernel, so every captured graph gets a
+    slot of its own (GraphedStep does this): replays on different streams no longer overwrite each other's count,
+    and the slot lives as long as the graph's owner, not as long as the capturing thread."""
     st = _count_slots
-    if not hasattr(st, "slot"):
-        st.slot = torch.zeros(1, dtype=torch.int64).pin_memory()
-        st.ptr = st.slot.data_ptr()
-        st.ticket = 0
-    st.ticket = (st.ticket % 0xFFFFFE) + 1
-    return st.ptr, st.ticket
+    prev = getattr(st, "override", None)
+    st.override = slot
+    try:
+        yield slot
+    finally:
+        st.override = prev
+
+
+def _count_slot():
+    """One pinned count word per host thread (or the caller's own, see own_count_slot) + a ticket counter."""
+    st = _count_slots
+    slot = getattr(st, "override", None)
+    if slot is None:
+        if not hasattr(st, "own"):
+            st.own = CountSlot()
+            st.slot = st.own.tensor      # (last_num_rendered reads it)
+        slot = st.own
+    slot.ticket = (slot.ticket % 0xFFFFFE) + 1
+    return slot.ptr, slot.ticket
 
 
 def _require_cuda(t: torch.Tensor, what: str):
@@ -196,9 +268,8 @@ class _RasterizeGaussians(torch.autograd.Function):
             sh_M = sh_c.shape[1] if sh_c is not None else 0
             H, W = int(rs.image_height), int(rs.image_width)
 
-            hint_key = (device.index, P, H, W)
-            hint = _capacity_hint.get(hint_key)
-            cap = 0 if hint is None else int(hint * 1.25) + 4096
+            hint_key, dens_key = (device.index, P, H, W), (device.index, H, W)
+            cap, hint = _predict_capacity(hint_key, dens_key, P)
             # CUDA-graph capture (torch.cuda.graph around the caller's step): nothing may wait on the device, so
             # the instance count of the last eager call stands in for num_rendered and the binning capacity is
             # fixed generously; captured_capacity_ok() tells the caller after a replay whether it sufficed.
@@ -249,7 +320,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                     _lib.check(L.gsvc_rast_forward_render(ns.ref, P, geom_p, image_p, bin_p, cap, color.data_ptr(),
                                                           stream), "gsvc_rast_forward_render")
                 if not capturing:
-                    _capacity_hint[hint_key] = num_rendered
+                    _record_capacity(hint_key, dens_key, P, num_rendered)
             except Exception:
                 if rs.debug:
                     torch.save((means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
@@ -282,11 +353,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             g_out = _dev_f32(grad_out_color, device, "grad_out_color")
             # frame-sharded training: write (means3D, colours, opacity, scales, rotation) gradients straight into
             # the caller's [P,14] all-reduce buffer (gsvc_b200.sharding.packed_backward) and return views of it
-            packed = _packed_target.buf
-            if packed is not None and (col is None or sc is None or packed.shape != (P, 14) or
-                                       packed.device != device or packed.dtype != _F32 or
-                                       not packed.is_contiguous()):
-                packed = None
+            packed = _packed_target.take(P, device, col is not None and sc is not None)
             # one allocation for every gradient (contiguous slices) and the accumulator scratch
             widths = (3, 3, 1, 3 if col is not None else 0, ctx.sh_M * 3 if sh is not None else 0,
                       3 if sc is not None else 0, 4 if rot is not None else 0, 6 if cov is not None else 0)

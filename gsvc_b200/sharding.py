@@ -38,15 +38,21 @@ def pack_grads(grads: Dict[str, torch.Tensor], out: torch.Tensor = None) -> torc
 
 @contextlib.contextmanager
 def packed_backward(buf: torch.Tensor):
-    """While active, the rasterizer backward writes the GRAD_LAYOUT gradients directly into `buf` ([P,14] fp32,
-    contiguous, on the rasterizer's device) and returns views of it, so the all-reduce needs no pack pass."""
+    """While active, the FIRST rasterizer backward that fits writes the GRAD_LAYOUT gradients directly into `buf`
+    ([P,14] fp32, contiguous, on the rasterizer's device) and returns views of it, so the all-reduce needs no pack
+    pass.  One context serves one backward: a second rasterizer backward inside it (the reference loop's four
+    render() calls under one loss.backward()) returns ordinary dense gradients — batch the views of a step into one
+    call (views.rasterize_views) to get all of them into the buffer."""
     from . import rasterizer
-    prev = rasterizer._packed_target.buf
-    rasterizer._packed_target.buf = buf
+    t = rasterizer._packed_target
+    with t.lock:
+        prev = (t.buf, t.taken)
+        t.buf, t.taken = buf, False
     try:
         yield buf
     finally:
-        rasterizer._packed_target.buf = prev
+        with t.lock:
+            t.buf, t.taken = prev
 
 
 def unpack_grads(buf: torch.Tensor) -> Dict[str, torch.Tensor]:

@@ -150,9 +150,8 @@ class _RasterizeViews(torch.autograd.Function):
             sh_M = sh_c.shape[1] if sh_c is not None else 0
             H, W = int(rs.image_height), int(rs.image_width)
 
-            hint_key = (device.index, P, H, W, V)
-            hint = R._capacity_hint.get(hint_key)
-            cap = 0 if hint is None else int(hint * 1.25) + 4096
+            hint_key, dens_key = (device.index, P, H, W, V), (device.index, H, W, V)
+            cap, hint = R._predict_capacity(hint_key, dens_key, P)
             capturing = torch.cuda.is_current_stream_capturing()
             if capturing:
                 if hint is None:
@@ -194,7 +193,7 @@ class _RasterizeViews(torch.autograd.Function):
                     _lib.check(L.gsvc_rast_forward_views_render(nv.ref, V, nv.views, n_out, P, geom_p, image_p, bin_p, cap,
                                                                 color.data_ptr(), stream), "gsvc_rast_forward_views_render")
                 if not capturing:
-                    R._capacity_hint[hint_key] = num_rendered
+                    R._record_capacity(hint_key, dens_key, P, num_rendered)
 
             except Exception:
                 if rs.debug:   # upstream behaviour of the single-view call (snapshot for debugging)
@@ -224,10 +223,7 @@ class _RasterizeViews(torch.autograd.Function):
         bin_p = binning.data_ptr() if binning is not None else base + n_geom + n_img + n_acc
         with torch.cuda.device(device):
             g_out = _dev_f32(grad_out_color, device, "grad_out_color")
-            packed = R._packed_target.buf
-            if packed is not None and (col is None or sc is None or packed.shape != (P, 14) or
-                                       packed.device != device or packed.dtype != _F32 or not packed.is_contiguous()):
-                packed = None
+            packed = R._packed_target.take(P, device, col is not None and sc is not None)
             widths = (3, 3 * V, 1, 3 if col is not None else 0, ctx.sh_M * 3 if sh is not None else 0,
                       3 if sc is not None else 0, 4 if rot is not None else 0, 6 if cov is not None else 0)
             n_scratch = 0 if n_acc else L.gsvc_rast_backward_scratch_bytes(P * V) // 4

@@ -1,14 +1,18 @@
 """Randomised parity sweep on the GPU against the C oracle: random image sizes (including non-multiples of the tile
 size and images smaller than a tile), Gaussian counts, densities (bucket sizes across every sort path: <=32, 64,
 128, 256, 512 per warp, CTA-wide shared, in-place global), views, backgrounds, scale modifiers; single calls through
-the records of the stage exports (bit-exact), images (1e-5 off fragile pixels), gradients (1e-4 relative), and the
-same scenes through the batched-view path.  Usage: python tests/fuzz_parity.py [n_cases=40] [seed=0] [only_case] [big] [referee]   (big: 400x300 .. 1024x600, up to 400k Gaussians;
-referee: the oracle's referee mode + elongated Gaussians — not yet run on a GPU)"""
+the records of the stage exports (bit-exact), images (1e-5 off fragile pixels), gradients (1e-4 of the tensor's
+largest entry AND the per-Gaussian criterion of tests/parity.py, every visible Gaussian compared), and the same
+scenes through the batched-view path.  The oracle runs in referee mode; every case draws an axis-ratio stretch from
+{1, 2, 4, 8, 16} (ratios 1:1 .. 256:1 on top of the generator's spread; the Gaussian count shrinks with the needles'
+area so that list lengths stay those of the density drawn).
+Usage: python tests/fuzz_parity.py [n_cases=40] [seed=0] [only_case] [big]   (big: 400x300 .. 1024x600, up to 400k Gaussians)"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 from oracle import c_oracle
+from tests import parity
 from tests.scenes import make_scene, np_inputs, product_settings
 from gsvc_b200.rasterizer import GaussianRasterizer, RasterState
 from gsvc_b200.views import ViewBatch, rasterize_views
@@ -52,10 +56,11 @@ def diag_pixel(fo, got, W, bg, note=""):
           f"final_T {fo['final_T'][j_, i_]:.3e}; R={fo['num_rendered']} bg={bg} {note}")
 
 
-def run(n_cases=40, seed=0, verbose=True, only_case=None, big=False, referee=False):
+def run(n_cases=40, seed=0, verbose=True, only_case=None, big=False, referee=True):
+  assert referee, "the default-mode oracle is no longer what the GPU path is held to (tests/parity.py)"
   rng = np.random.default_rng(seed)
   dev = torch.device("cuda:0")
-  worst = dict(fwd=0.0, grad=0.0, frag=0.0)
+  worst = dict(fwd=0.0, grad=0.0, frag=0.0, row_fail=0.0, row_worst=0.0, compared=1.0, gaussians=0)
   t_start = time.time()
   for case in range(n_cases):
       W = int(rng.choice([400, 512, 640, 801, 1024] if big else [7, 16, 33, 64, 100, 160, 250, 320]))
@@ -71,16 +76,11 @@ def run(n_cases=40, seed=0, verbose=True, only_case=None, big=False, referee=Fal
       scene_seed = int(rng.integers(1 << 30))
       if only_case is not None and case != only_case:
           continue
-      scene = make_scene(P=P, W=W, H=H, F=F, seed=scene_seed, back=back, bg=bg, scale_modifier=sm)
-      if referee:
-          # next round's checker (docs/SPEC.md "Referee mode", CPU-validated in tests/fuzz_referee.py): elongated
-          # Gaussians too (axis ratios up to 256:1), the oracle's exponent in double, narrow gradient exclusion
-          stretch = float(np.random.default_rng(scene_seed).choice([1.0, 2.0, 4.0, 8.0, 16.0]))
-          scene["gaussians"]["scales"][:, 0] *= stretch
-          scene["gaussians"]["scales"][:, 1] /= stretch
+      stretch = float(np.random.default_rng(scene_seed).choice([1.0, 1.0, 2.0, 4.0, 8.0, 16.0]))
+      P = max(1, int(P / stretch ** 2))
+      scene = make_scene(P=P, W=W, H=H, F=F, seed=scene_seed, back=back, bg=bg, scale_modifier=sm, stretch=stretch)
       gi = np_inputs(scene["gaussians"])
-      fo = c_oracle.forward(scene["oracle_settings"], gi["means3D"], gi["opacities"], gi["scales"], gi["rotations"],
-                            colors_precomp=gi["colors_precomp"], referee=referee)
+      fo = parity.oracle_forward(scene["oracle_settings"], gi)
       rs = product_settings(scene, dev)
       g = {k: v.to(dev) for k, v in scene["gaussians"].items()}
       # stage exports through the allocator-callback form (exact capacity, scatter path)
@@ -93,40 +93,34 @@ def run(n_cases=40, seed=0, verbose=True, only_case=None, big=False, referee=Fal
       assert np.array_equal(pl.cpu().numpy().view(np.uint32), fo["bin"]["point_list"]), case
       assert np.array_equal(ranges.cpu().numpy().view(np.uint32), fo["bin"]["ranges"]), case
       # autograd call (capacity-hint path on the second call)
-      dL = torch.randn((3, H, W), generator=torch.Generator().manual_seed(case))
-      go = c_oracle.backward(fo, dL.numpy(), narrow_touched=referee)
+      dL = parity.masked_dL(fo, torch.randn((3, H, W), generator=torch.Generator().manual_seed(case)))
+      go = parity.oracle_backward(fo, dL)
+      frag = fo["fragile"]
+      # thousands of contributors per pixel (the densest draws) put more pixels near a decision: bounded, and reported
+      assert frag.mean() <= 0.05, (case, float(frag.mean()))
       for rep in range(2):
           p = {k: g[k].clone().requires_grad_(True) for k in NAMES}
           m2d = torch.zeros_like(p["means3D"], requires_grad=True)
           color, radii, n = GaussianRasterizer(raster_settings=rs)(
               means3D=p["means3D"], means2D=m2d, shs=None, colors_precomp=p["colors_precomp"], opacities=p["opacities"],
               scales=p["scales"], rotations=p["rotations"], cov3D_precomp=None)
-          grads = torch.autograd.grad(color, [p[k] for k in NAMES], grad_outputs=dL.to(dev))
+          grads = torch.autograd.grad(color, [p[k] for k in NAMES] + [m2d], grad_outputs=torch.as_tensor(dL).to(dev))
           assert n == fo["num_rendered"]
           err = np.abs(color.detach().cpu().numpy() - fo["color"])
-          frag = fo["fragile"]
           e = err[:, ~frag].max(initial=0.0)
           if e > 1e-5 and only_case is not None:
-              diag_pixel(fo, color.detach().cpu().numpy(), W, bg, f"W={W} H={H} P={P} back={back} sm={sm}")
+              diag_pixel(fo, color.detach().cpu().numpy(), W, bg, f"W={W} H={H} P={P} back={back} sm={sm} stretch={stretch}")
               continue
           assert e <= 1e-5, (case, e)
           worst["fwd"] = max(worst["fwd"], float(e)); worst["frag"] = max(worst["frag"], float(frag.mean()))
-          ok = ~go["touched_fragile"]
-          for k, gr in zip(NAMES, grads):
-              a = gr.cpu().numpy().reshape(P, -1)[ok]; b = go[k].reshape(P, -1)[ok]
-              if b.size == 0:
-                  continue
-              rel = np.abs(a - b).max() / (np.abs(b).max() + 1e-30)
-              if rel > 1e-4 and only_case is not None:
-                  i = np.unravel_index(np.abs(a - b).argmax(), a.shape)
-                  gid = np.nonzero(ok)[0][i[0]]
-                  print(f"DIAG {k}: rel {rel:.3e} at gaussian {gid} comp {i[1]}: got {a[i]:.9e} ref {b[i]:.9e} max|ref| {np.abs(b).max():.3e}; "
-                        f"W={W} H={H} P={P} R={fo['num_rendered']} back={back} sm={sm} bg={bg} scene_seed={scene_seed}")
-                  print("  opacity", gi['opacities'][gid], "scales_px", gi['scales'][gid] * scene['frame'].scale * sm, "radius", fo['radii'][gid],
-                        "xy", fo['pre']['xy'][gid], "fragile px", int(fo['fragile'].sum()))
-                  continue
-              assert rel <= 1e-4, (case, k, rel)
-              worst["grad"] = max(worst["grad"], float(rel))
+          got = dict(zip(NAMES + ("means2D",), grads))
+          # (a scene of a handful of Gaussians: one row is more than 1 % of them)
+          nvis = int((fo["radii"] > 0).sum())
+          st_ = parity.check_grads(fo, go, got, what=f"case {case}: ",
+                                   row_fail_max=max(parity.ROW_FAIL_MAX, 1.5 / max(nvis, 1)))
+          worst["grad"] = max(worst["grad"], st_["rel"]); worst["row_fail"] = max(worst["row_fail"], st_["row_fail"])
+          worst["row_worst"] = max(worst["row_worst"], st_["row_worst"])
+          worst["gaussians"] += nvis if rep == 0 else 0
       # the same view twice in one batch (plain) == the single call, bit for bit
       with torch.no_grad():
           imgs, rad2, n2 = rasterize_views(ViewBatch([rs, rs]), means3D=g["means3D"], opacities=g["opacities"],
@@ -136,14 +130,17 @@ def run(n_cases=40, seed=0, verbose=True, only_case=None, big=False, referee=Fal
       mx = int(np.diff(fo["bin"]["ranges"].astype(np.int64), axis=1).max(initial=0))
       if verbose:
         print(f"case {case:3d} ok: {W}x{H} P={P} R={fo['num_rendered']} max_bucket={mx} back={back} sm={sm} "
-            f"fwd_err={e:.1e} fragile={frag.mean():.1e}", flush=True)
+            f"axes {stretch * stretch:.0f}:1 fwd_err={e:.1e} fragile={frag.mean():.1e} grad={st_['rel']:.1e} "
+            f"rows_missing={st_['row_fail']:.1e} worst_row={st_['row_worst']:.2f}", flush=True)
   print(f"{n_cases} cases ok in {time.time() - t_start:.0f} s; worst fwd err {worst['fwd']:.2e}, worst grad rel err "
-      f"{worst['grad']:.2e}, worst fragile fraction {worst['frag']:.1e}")
+      f"{worst['grad']:.2e}, worst fragile pixel share {worst['frag']:.1e}; every visible Gaussian compared "
+      f"({worst['gaussians']} in all): largest share of a tensor's rows missing the per-Gaussian criterion "
+      f"{worst['row_fail']:.1e}, worst row {worst['row_worst']:.2f}x its tolerance")
   return worst
 
 
 if __name__ == "__main__":
-    big, referee = "big" in sys.argv[1:], "referee" in sys.argv[1:]
+    big = "big" in sys.argv[1:]
     argv = [a for a in sys.argv[1:] if a not in ("big", "referee")]
     run(int(argv[0]) if len(argv) > 0 else 40, int(argv[1]) if len(argv) > 1 else 0,
-        only_case=int(argv[2]) if len(argv) > 2 else None, big=big, referee=referee)
+        only_case=int(argv[2]) if len(argv) > 2 else None, big=big)

@@ -110,7 +110,7 @@ def test_reference_call_sequence_front_and_back(cuda_device):
     st = OracleSettings(image_height=H, image_width=W, x_min=fr.x_min, y_min=fr.y_min, scale=fr.scale, threshold=0.05,
                         bg=np.zeros(3, np.float32), viewmatrix=fr.view_matrix.permute(1, 0).numpy().copy(),
                         campos=fr.cam_pos.numpy())
-    fo = c_oracle.forward(st, xyz, opacity, scaling, rot, colors_precomp=color)
+    fo = c_oracle.forward(st, xyz, opacity, scaling, rot, colors_precomp=color, referee=True)
     assert fo["num_rendered"] == out_f["num_rendered"]
     np.testing.assert_array_equal(out_f["radii"].cpu().numpy(), fo["radii"])
     err = np.abs(out_f["rendered_image"].detach().cpu().numpy() - fo["color"])[:, ~fo["fragile"]]

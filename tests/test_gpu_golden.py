@@ -11,7 +11,8 @@ import numpy as np
 import pytest
 import torch
 
-from tests.scenes import make_scene, product_settings
+from tests import parity
+from tests.scenes import golden_scene, make_scene, product_settings
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -23,7 +24,52 @@ def _sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "*.npz"))), ids=os.path.basename)
+V1 = sorted(p for p in glob.glob(os.path.join(GOLDEN, "*.npz")) if not p.endswith("_v2.npz"))
+V2 = sorted(glob.glob(os.path.join(GOLDEN, "*_v2.npz")))
+
+
+@pytest.mark.parametrize("path", V2, ids=os.path.basename)
+def test_cuda_path_reproduces_the_v2_fixture(cuda_device, path):
+    """Round-2 fixtures (referee oracle, seed gradient zeroed on its fragile pixels): a 1080p-wide dense strip, an
+    ordinary scene with needles, degree-3 SH colours, each with fragile pixels.  Integer stages by hash, image 1e-5
+    off the stored fragile set, and EVERY visible Gaussian's gradient at the per-tensor and per-Gaussian bars."""
+    from gsvc_b200.rasterizer import GaussianRasterizer, RasterState
+    z = np.load(path)
+    cfg = ast.literal_eval(str(z["cfg"]))
+    scene, gi, deg = golden_scene(cfg)
+    H, W = cfg["H"], cfg["W"]
+    frag = np.unpackbits(z["fragile"])[:H * W].reshape(H, W).astype(bool)
+    assert frag.any() and int(z["referee"]) == 1
+    rs = product_settings(scene, cuda_device, sh_degree=deg or 0)
+    g = {k: torch.as_tensor(v).to(cuda_device) for k, v in gi.items()}
+    colour = dict(shs=g["shs"]) if deg is not None else dict(colors_precomp=g["colors_precomp"])
+    st = RasterState(rs, g["means3D"], g["opacities"], scales=g["scales"], rotations=g["rotations"], **colour)
+    keys, pl, ranges = st.export_keys()
+    fT, n_contrib = st.export_image()
+    assert st.num_rendered == int(z["num_rendered"])
+    np.testing.assert_array_equal(st.radii.cpu().numpy(), z["radii"])
+    assert _sha(keys.cpu().numpy().view(np.uint64)) == str(z["keys_sha"])
+    assert _sha(pl.cpu().numpy().view(np.uint32)) == str(z["point_list_sha"])
+    assert _sha(ranges.cpu().numpy().view(np.uint32)) == str(z["ranges_sha"])
+    np.testing.assert_array_equal(n_contrib.cpu().numpy().astype(np.uint16)[~frag], z["n_contrib"][~frag])
+    names = [k for k in ("means3D", "scales", "rotations", "opacities", "colors_precomp", "shs") if k in g]
+    p = {k: g[k].clone().requires_grad_(True) for k in names}
+    m2d = torch.zeros_like(p["means3D"], requires_grad=True)
+    color, radii, n = GaussianRasterizer(raster_settings=rs)(
+        means3D=p["means3D"], means2D=m2d, shs=p.get("shs"), colors_precomp=p.get("colors_precomp"),
+        opacities=p["opacities"], scales=p["scales"], rotations=p["rotations"], cov3D_precomp=None)
+    assert n == int(z["num_rendered"])
+    fo = dict(color=z["color"], fragile=frag, radii=z["radii"])
+    parity.check_forward(fo, color, max_fragile=1e-2)
+    dL = parity.masked_dL(fo, torch.randn(3, H, W, generator=torch.Generator().manual_seed(int(z["dL_seed"]))))
+    grads = torch.autograd.grad(color, [p[k] for k in names] + [m2d], grad_outputs=torch.as_tensor(dL).to(cuda_device))
+    stored = dict(means3D="g_means3D", scales="g_scales", rotations="g_rotations", opacities="g_opacities",
+                  colors_precomp="g_colors", shs="g_shs", means2D="g_means2D")
+    got = dict(zip(names + ["means2D"], grads))
+    parity.check_grads(fo, {k: z[stored[k]] for k in got}, got)
+
+
+@pytest.mark.parametrize("path", V1, ids=os.path.basename)
 def test_cuda_path_reproduces_the_golden_fixture(cuda_device, path):
     from gsvc_b200.rasterizer import GaussianRasterizer, RasterState
     z = np.load(path)

@@ -2,15 +2,17 @@
 GaussianRasterizer, against the CPU oracle on the same seeded inputs.
 
 Bars (BASELINE.json north_star): integer stages (radii, tile rects, sorted keys, point list, tile ranges,
-num_rendered, n_contrib) bit-exact; forward pixels <= 1e-5 abs; gradients <= 1e-4 relative.
-Pixels where a discontinuous decision (alpha floor 1/255, T stop 1e-4, power>0) sits within 4e-6 relative of
-flipping are reported by the oracle (`fragile`) and compared at the looser discontinuity bound instead.
+num_rendered, n_contrib) bit-exact; forward pixels <= 1e-5 abs; gradients <= 1e-4 relative — per tensor AND per
+Gaussian.  Every comparison goes through tests/parity.py: the oracle in referee mode (exponent in double), a bounded
+fragile share of the image, seed gradients zeroed on the fragile pixels so that EVERY visible Gaussian is compared;
+scenes with elongated Gaussians (axis ratios 4:1 .. 256:1) are part of the suite.
 """
 import numpy as np
 import pytest
 import torch
 
 from oracle import c_oracle
+from tests import parity
 from tests.scenes import make_scene, np_inputs, product_settings
 
 pytestmark = pytest.mark.gpu
@@ -28,11 +30,7 @@ def _to_dev(g, device):
 
 
 def _oracle_forward(scene, **over):
-    gi = np_inputs(scene["gaussians"])
-    gi.update(over)
-    return c_oracle.forward(scene["oracle_settings"], gi["means3D"], gi["opacities"], gi.get("scales"),
-                            gi.get("rotations"), cov3D_precomp=gi.get("cov3D_precomp"),
-                            colors_precomp=gi.get("colors_precomp"), shs=gi.get("shs"))
+    return parity.oracle_forward(scene["oracle_settings"], np_inputs(scene["gaussians"]), **over)
 
 
 def _check_stages(scene, fo, state):
@@ -51,25 +49,7 @@ def _check_stages(scene, fo, state):
     np.testing.assert_array_equal(ranges.cpu().numpy().view(np.uint32), fo["bin"]["ranges"])
 
 
-def _check_forward(fo, color, fT=None, nc=None):
-    ref = fo["color"]
-    got = color.detach().cpu().numpy()
-    frag = fo["fragile"]
-    err = np.abs(got - ref)
-    solid = err[:, ~frag]
-    assert solid.max(initial=0.0) <= FWD_ATOL, f"max abs err {solid.max()} on non-fragile pixels"
-    assert frag.mean() < 2e-3
-    if frag.any():
-        assert err[:, frag].max() <= 2.0 / 255.0 + 1e-3   # one flipped alpha-floor / stop decision at most
-    if nc is not None:
-        np.testing.assert_array_equal(nc.cpu().numpy().view(np.uint32)[~frag], fo["n_contrib"][~frag])
-    if fT is not None:
-        assert np.abs(fT.cpu().numpy() - fo["final_T"])[~frag].max(initial=0.0) <= 1e-5
-
-
-def _rel_err(a, b):
-    scale = np.abs(b).max() + 1e-30
-    return np.abs(a - b).max() / scale
+_check_forward = parity.check_forward
 
 
 def _run_product(scene, device, requires_grad=True, **over):
@@ -118,22 +98,60 @@ def test_forward_backward_vs_oracle(cuda_device, back):
     assert radii.dtype == torch.int32
     np.testing.assert_array_equal(radii.cpu().numpy(), fo["radii"])
     _check_forward(fo, color)
-    dL = torch.randn(color.shape, generator=torch.Generator().manual_seed(5))
-    color.backward(dL.to(cuda_device))
-    go = c_oracle.backward(fo, dL.numpy())
-    ok = ~go["touched_fragile"]
+    dL = parity.masked_dL(fo, torch.randn(color.shape, generator=torch.Generator().manual_seed(5)))
+    color.backward(torch.as_tensor(dL).to(cuda_device))
+    go = parity.oracle_backward(fo, dL)
     got = dict(means3D=g["means3D"].grad, means2D=means2D.grad, scales=g["scales"].grad,
                rotations=g["rotations"].grad, opacities=g["opacities"].grad,
                colors_precomp=g["colors_precomp"].grad)
-    for k, v in got.items():
-        a = v.cpu().numpy().reshape(v.shape[0], -1)[ok]
-        b = go[k].reshape(v.shape[0], -1)[ok]
-        assert _rel_err(a, b) <= GRAD_RTOL, f"{k}: rel err {_rel_err(a, b)}"
+    parity.check_grads(fo, go, got)
     assert (means2D.grad[:, 2] == 0).all()
     # culled Gaussians get exactly zero gradients
     culled = torch.as_tensor(fo["radii"] == 0, device=cuda_device)
     for k, v in got.items():
         assert (v[culled] == 0).all(), k
+
+
+@pytest.mark.parametrize("back", [False, True])
+@pytest.mark.parametrize("stretch", [2.0, 4.0, 8.0, 16.0])
+def test_elongated_gaussians_vs_oracle(cuda_device, stretch, back):
+    """Needle-like Gaussians, axis ratios 4:1, 16:1, 64:1, 256:1 on top of the generator's spread — the regime the
+    kernels' Cholesky exponent exists for, judged by the referee oracle (exponent in double).  The Gaussian count
+    shrinks with the needles' area so that per-pixel lists stay at the density of an ordinary scene."""
+    from gsvc_b200.rasterizer import RasterState
+    P = int(20000 / stretch ** 2)
+    scene = make_scene(P=P, W=256, H=256, F=256, back=back, seed=3, stretch=stretch)
+    fo = _oracle_forward(scene)
+    gd = _to_dev(scene["gaussians"], cuda_device)
+    state = RasterState(product_settings(scene, cuda_device), gd["means3D"], gd["opacities"],
+                        colors_precomp=gd["colors_precomp"], scales=gd["scales"], rotations=gd["rotations"])
+    _check_stages(scene, fo, state)
+    g, means2D, color, radii, n = _run_product(scene, cuda_device)
+    assert n == fo["num_rendered"]
+    _check_forward(fo, color, max_fragile=5e-3)
+    dL = parity.masked_dL(fo, torch.randn(color.shape, generator=torch.Generator().manual_seed(6)))
+    color.backward(torch.as_tensor(dL).to(cuda_device))
+    go = parity.oracle_backward(fo, dL)
+    got = {k: g[k].grad for k in parity.GRAD_NAMES}
+    got["means2D"] = means2D.grad
+    parity.check_grads(fo, go, got)
+
+
+@pytest.mark.parametrize("back", [False, True])
+def test_ordinary_scene_with_needles_vs_oracle(cuda_device, back):
+    """An ordinary-density scene in which 3 % of the Gaussians are needles (axis ratios 4:1 .. 256:1 at random)."""
+    scene = make_scene(P=20000, W=256, H=256, F=256, back=back, seed=1, needle_mix=0.03)
+    fo = _oracle_forward(scene)
+    g, means2D, color, radii, n = _run_product(scene, cuda_device)
+    assert n == fo["num_rendered"]
+    np.testing.assert_array_equal(radii.cpu().numpy(), fo["radii"])
+    _check_forward(fo, color, max_fragile=5e-3)
+    dL = parity.masked_dL(fo, torch.randn(color.shape, generator=torch.Generator().manual_seed(7)))
+    color.backward(torch.as_tensor(dL).to(cuda_device))
+    go = parity.oracle_backward(fo, dL)
+    got = {k: g[k].grad for k in parity.GRAD_NAMES}
+    got["means2D"] = means2D.grad
+    parity.check_grads(fo, go, got)
 
 
 def test_second_call_uses_capacity_hint_and_matches(cuda_device):
@@ -178,12 +196,11 @@ def test_cov3d_precomp_path(cuda_device):
     g, means2D, color, radii, n = _run_product(scene, cuda_device, scales=None, rotations=None, cov3D_precomp=cov)
     assert n == fo["num_rendered"]
     _check_forward(fo, color)
-    dL = torch.randn(color.shape, generator=torch.Generator().manual_seed(8))
-    color.backward(dL.to(cuda_device))
-    go = c_oracle.backward(fo, dL.numpy())
-    ok = ~go["touched_fragile"]
-    a = g["cov3D_precomp"].grad.cpu().numpy()[ok]
-    assert _rel_err(a, go["cov3D_precomp"][ok]) <= GRAD_RTOL
+    dL = parity.masked_dL(fo, torch.randn(color.shape, generator=torch.Generator().manual_seed(8)))
+    color.backward(torch.as_tensor(dL).to(cuda_device))
+    go = parity.oracle_backward(fo, dL)
+    parity.check_grads(fo, go, dict(cov3D_precomp=g["cov3D_precomp"].grad, means3D=g["means3D"].grad,
+                                    opacities=g["opacities"].grad, colors_precomp=g["colors_precomp"].grad))
     assert pre["radii"].shape == (6000,)
 
 
@@ -206,12 +223,11 @@ def test_sh_colour_path(cuda_device, deg):
                            opacities=g["opacities"], scales=g["scales"], rotations=g["rotations"], cov3D_precomp=None)
     assert n == fo["num_rendered"]
     _check_forward(fo, color)
-    dL = torch.randn(color.shape, generator=torch.Generator().manual_seed(2))
-    color.backward(dL.to(cuda_device))
-    go = c_oracle.backward(fo, dL.numpy())
-    ok = ~go["touched_fragile"]
-    assert _rel_err(g["shs"].grad.cpu().numpy()[ok], go["shs"][ok]) <= GRAD_RTOL
-    assert _rel_err(g["means3D"].grad.cpu().numpy()[ok], go["means3D"][ok]) <= GRAD_RTOL
+    dL = parity.masked_dL(fo, torch.randn(color.shape, generator=torch.Generator().manual_seed(2)))
+    color.backward(torch.as_tensor(dL).to(cuda_device))
+    go = parity.oracle_backward(fo, dL)
+    parity.check_grads(fo, go, dict(shs=g["shs"].grad, means3D=g["means3D"].grad, scales=g["scales"].grad,
+                                    rotations=g["rotations"].grad, opacities=g["opacities"].grad))
 
 
 def test_edge_cases(cuda_device):
@@ -325,7 +341,8 @@ def test_plain_c_host_matches_oracle(cuda_device, tmp_path):
     P, W, H = 6000, 150, 90
     scene = make_scene(P=P, W=W, H=H, F=128, seed=31, back=True, bg=(0.3, 0.1, 0.6), scale_modifier=0.5)
     st, gi = scene["oracle_settings"], np_inputs(scene["gaussians"])
-    dL = np.random.default_rng(5).standard_normal((3, H, W)).astype(np.float32)
+    fo = _oracle_forward(scene)
+    dL = parity.masked_dL(fo, np.random.default_rng(5).standard_normal((3, H, W)).astype(np.float32))
     with open(tmp_path / "scene.bin", "wb") as f:
         np.asarray([W, H, P], np.int32).tofile(f)
         np.asarray([st.x_min, st.y_min, st.scale, st.threshold, st.scale_modifier], np.float32).tofile(f)
@@ -337,8 +354,7 @@ def test_plain_c_host_matches_oracle(cuda_device, tmp_path):
     run = subprocess.run([exe, str(tmp_path / "scene.bin"), str(tmp_path / "out.bin")], capture_output=True, text=True,
                          timeout=120)
     assert run.returncode == 0, run.stderr
-    fo = _oracle_forward(scene)
-    go = c_oracle.backward(fo, dL)
+    go = parity.oracle_backward(fo, dL)
     with open(tmp_path / "out.bin", "rb") as f:
         n = int(np.fromfile(f, np.int64, 1)[0])
         color = np.fromfile(f, np.float32, 3 * H * W).reshape(3, H, W)
@@ -346,10 +362,8 @@ def test_plain_c_host_matches_oracle(cuda_device, tmp_path):
         grads = {k: np.fromfile(f, np.float32, P * w).reshape(P, w) for k, w in
                  (("means3D", 3), ("colors_precomp", 3), ("opacities", 1), ("scales", 3), ("rotations", 4))}
     assert n == fo["num_rendered"] and np.array_equal(radii, fo["radii"])
-    assert np.abs(color - fo["color"])[:, ~fo["fragile"]].max() <= FWD_ATOL
-    ok = ~go["touched_fragile"]
-    for k, a in grads.items():
-        assert _rel_err(a[ok], go[k].reshape(P, -1)[ok]) <= GRAD_RTOL, k
+    parity.check_forward(fo, color)
+    parity.check_grads(fo, go, grads)
 
 
 def test_two_host_threads_on_their_own_streams(cuda_device):
@@ -411,7 +425,7 @@ def test_heavy_tile_uses_global_sort_fallback(cuda_device):
     state = RasterState(product_settings(scene, cuda_device), g["means3D"], g["opacities"],
                         colors_precomp=g["colors_precomp"], scales=g["scales"], rotations=g["rotations"])
     _check_stages(scene, fo, state)
-    _check_forward(fo, state.color)
+    _check_forward(fo, state.color, max_fragile=5e-3)   # thousands of contributors per pixel at opacities 0.02-0.04
 
 
 def test_toast_two_view_composition(cuda_device):
@@ -458,8 +472,7 @@ def test_large_gaussians_nonzero_bg_scale_modifier_and_debug(cuda_device):
     gs["scales"] = gs["scales"] * 6.0                       # sigma up to ~180 px after the modifier
     gs["opacities"] = gs["opacities"] * 0.3
     gi = np_inputs(gs)
-    fo = c_oracle.forward(scene["oracle_settings"], gi["means3D"], gi["opacities"], gi["scales"], gi["rotations"],
-                          colors_precomp=gi["colors_precomp"])
+    fo = parity.oracle_forward(scene["oracle_settings"], gi)
     assert (fo["pre"]["tiles_touched"] > 64).sum() > 50
     rs = product_settings(scene, cuda_device, debug=True)
     g = {k: v.to(cuda_device) for k, v in gs.items()}
@@ -477,15 +490,12 @@ def test_large_gaussians_nonzero_bg_scale_modifier_and_debug(cuda_device):
     assert n == fo["num_rendered"]
     np.testing.assert_array_equal(radii.cpu().numpy(), fo["radii"])
     _check_forward(fo, color)
-    dL = torch.randn(color.shape, generator=torch.Generator().manual_seed(12))
-    color.backward(dL.to(cuda_device))
-    go = c_oracle.backward(fo, dL.numpy())
-    ok = ~go["touched_fragile"]
-    for k in ("means3D", "scales", "rotations", "opacities", "colors_precomp"):
-        a = g[k].grad.float().cpu().numpy().reshape(600, -1)[ok]
-        b = go[k].reshape(600, -1)[ok]
-        assert _rel_err(a, b) <= GRAD_RTOL, f"{k}: {_rel_err(a, b)}"
-    assert _rel_err(m2d.grad.cpu().numpy()[ok], go["means2D"][ok]) <= GRAD_RTOL
+    dL = parity.masked_dL(fo, torch.randn(color.shape, generator=torch.Generator().manual_seed(12)))
+    color.backward(torch.as_tensor(dL).to(cuda_device))
+    go = parity.oracle_backward(fo, dL)
+    got = {k: g[k].grad.float() for k in parity.GRAD_NAMES}
+    got["means2D"] = m2d.grad
+    parity.check_grads(fo, go, got)
 
 
 def test_retain_graph_double_backward_is_consistent(cuda_device):
@@ -721,3 +731,82 @@ def test_graph_replay_detects_capacity_overflow(cuda_device):
                                  colors_precomp=params["colors_precomp"], opacities=params["opacities"],
                                  scales=params["scales"], rotations=params["rotations"], cov3D_precomp=None)
     assert n == step.num_rendered() and torch.equal(color, ref) and torch.equal(radii, ref_radii)
+
+
+def test_graph_replay_overflow_with_backward_captured_is_contained(cuda_device):
+    """a replay whose captured graph includes the BACKWARD outgrows its instance capacity.  The
+    forward skips the overflowed tiles; the blend backward must then leave before it reads a point list that does
+    not exist (it used to index past the capacity: out-of-bounds atomics).  The step reports capacity_ok() False,
+    nothing faults, and a re-capture makes it valid again."""
+    from gsvc_b200 import rasterizer
+    from gsvc_b200.graphed import GraphedStep
+    from gsvc_b200.rasterizer import GaussianRasterizer
+    from gsvc_b200.sharding import GRAD_LAYOUT
+    P = 20000
+    scene = make_scene(P=P, W=256, H=160, F=256, seed=61)
+    rast = GaussianRasterizer(raster_settings=product_settings(scene, cuda_device))
+    params = {k: v.to(cuda_device).clone() for k, v in scene["gaussians"].items()}
+    dL = torch.randn((3, 160, 256), generator=torch.Generator().manual_seed(9)).to(cuda_device)
+    rasterizer.overflow_events(cuda_device)
+    step = GraphedStep(rast, params, dL)
+    step()
+    torch.cuda.synchronize()
+    assert step.capacity_ok()
+    with torch.no_grad():
+        params["scales"].mul_(8.0)
+    for _ in range(3):
+        _, _, packed = step()
+    torch.cuda.synchronize()                                   # a fault in the backward would surface here
+    assert not step.capacity_ok()
+    assert torch.isfinite(packed).all()
+    step.recapture()
+    color, radii, packed = step()
+    torch.cuda.synchronize()
+    assert step.capacity_ok()
+    leaves = {k: params[k].clone().requires_grad_(True) for k, _ in GRAD_LAYOUT}
+    m2d = torch.zeros_like(leaves["means3D"], requires_grad=True)
+    ref, ref_radii, n = rast(means3D=leaves["means3D"], means2D=m2d, shs=None, colors_precomp=leaves["colors_precomp"],
+                             opacities=leaves["opacities"], scales=leaves["scales"], rotations=leaves["rotations"],
+                             cov3D_precomp=None)
+    grads = torch.autograd.grad(ref, [leaves[k] for k, _ in GRAD_LAYOUT], grad_outputs=dL)
+    assert n == step.num_rendered() and torch.equal(color, ref) and torch.equal(radii, ref_radii)
+    want = torch.cat([x.reshape(P, -1) for x in grads], dim=1)
+    assert (packed - want).abs().max() <= ATOMIC_RTOL * want.abs().max()
+
+
+@pytest.mark.parametrize("P", [4001, 4002])
+def test_rotations_at_any_float_alignment(cuda_device, P):
+    """quaternions are read 16 bytes at a time only when the pointer allows it.  Slices of one
+    flat parameter buffer (the hostpipe / GraphedStep layout puts rotations at float offset 10*P: 8-byte aligned for
+    odd P) and deliberately 4-byte-offset tensors give the results of freshly allocated ones, forward and backward,
+    and so does the filter."""
+    from gsvc_b200.rasterizer import GaussianRasterizer
+    scene = make_scene(P=P, W=128, H=96, F=128, seed=5)
+    g = _to_dev(scene["gaussians"], cuda_device)
+    rast = GaussianRasterizer(raster_settings=product_settings(scene, cuda_device))
+    dL = torch.randn((3, 96, 128), generator=torch.Generator().manual_seed(1)).to(cuda_device)
+    names = ("means3D", "colors_precomp", "opacities", "scales", "rotations")
+
+    def call(p):
+        leaves = {k: p[k].detach().requires_grad_(True) for k in names}
+        color, radii, n = rast(means3D=leaves["means3D"], means2D=torch.zeros_like(leaves["means3D"]), shs=None,
+                               colors_precomp=leaves["colors_precomp"], opacities=leaves["opacities"],
+                               scales=leaves["scales"], rotations=leaves["rotations"], cov3D_precomp=None)
+        return color, radii, torch.autograd.grad(color, [leaves[k] for k in names], grad_outputs=dL)
+
+    c0, r0, g0 = call(g)
+    for shift in (0, 1, 2, 3):
+        flat = torch.zeros(14 * P + 8, device=cuda_device)
+        p, off = {}, shift
+        for k, w in (("means3D", 3), ("colors_precomp", 3), ("opacities", 1), ("scales", 3), ("rotations", 4)):
+            p[k] = flat[off:off + w * P].view(P, w)
+            p[k].copy_(g[k])
+            off += w * P
+        assert p["rotations"].is_contiguous()
+        c1, r1, g1 = call(p)
+        torch.cuda.synchronize()
+        assert torch.equal(c1, c0) and torch.equal(r1, r0)
+        for a, b in zip(g1, g0):
+            assert (a - b).abs().max() <= ATOMIC_RTOL * b.abs().max()
+        f = rast.visible_filter(means3D=p["means3D"], scales=p["scales"], rotations=p["rotations"], cov3D_precomp=None)
+        assert torch.equal(f, r0)
