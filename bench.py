@@ -33,6 +33,14 @@ UNIT = "iters/s (1 iter = rasterizer fwd+bwd of one 1080p view, 200k Gaussians)"
 THRESHOLD = 0.05  # /root/reference/cfgs/cfg_20240919.yaml:13
 
 
+def dist_stats(ms_list):
+    """median / p10 / p90 / min / mean of a list of per-step times (ms)."""
+    a = sorted(ms_list)
+    n = len(a)
+    q = lambda f: a[min(n - 1, int(f * n))]
+    return {"n": n, "median_ms": q(0.5), "p10_ms": q(0.1), "p90_ms": q(0.9), "min_ms": a[0], "mean_ms": sum(a) / n}
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -214,6 +222,7 @@ def run_product_arm(args, rank, local_rank, world):
     from gsvc_b200.rasterizer import GaussianRasterizer
     from gsvc_b200.sharding import GRAD_LAYOUT, packed_backward
     from gsvc_b200.views import ViewBatch, rasterize_views
+    from gsvc_b200.graphed import FrameStreamer
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py product arm needs a CUDA device (no CPU fallback exists)")
@@ -316,6 +325,7 @@ def run_product_arm(args, rank, local_rank, world):
         t = torch.tensor([total_ms], dtype=torch.float64, device=device)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        timed.last_per_step = per_step
         return float(t.item()), out
 
     # ---- warm-up (also sets the instance-capacity hints so no step re-sizes its buffers)
@@ -370,7 +380,17 @@ def run_product_arm(args, rank, local_rank, world):
     # best of REPEATS measurements of exactly K steps each (a shared host occasionally stalls a step for
     # milliseconds; the minimum over repeats is the reproducible figure, as for MEASURED_PEAKS.json)
     REPEATS = 3
-    total_ms = min(timed(toast_graphed, args.steps)[0] for _ in range(REPEATS))
+    per_step_all = []
+    totals = []
+    for _ in range(REPEATS):
+        totals.append(timed(toast_graphed, args.steps)[0])
+        per_step_all += timed.last_per_step
+    total_ms = min(totals)
+    # distribution of the per-step device time over >= 100 steps (this rank; SURVEY.md §8d asks for median, p10, p90)
+    while len(per_step_all) < 100:
+        timed(toast_graphed, max(args.steps, 20))
+        per_step_all += timed.last_per_step
+    step_stats = dist_stats(per_step_all)
     if graphs is not None and not graphs[0].capacity_ok():
         raise SystemExit("the captured instance capacity was exceeded (cannot happen with a fixed scene)")
     launches = kernels_per_step * args.steps
@@ -394,6 +414,207 @@ def run_product_arm(args, rank, local_rank, world):
     for w in pending:
         if w is not None:
             w.wait()
+
+
+    # ---- the reference's real call pattern (ortho_gaussian_renderer/renderer.py:28-98): a DIFFERENT P on every call
+    # (the Gaussians of the anchors visible in that view), eager, through GaussianRasterizer and autograd.  Each step
+    # takes a prefix of a 240k-Gaussian set with P uniform in 200k +- 20 %; the binning capacity comes from the
+    # instances-per-Gaussian density hint, so scatter / sort / blend are launched before num_rendered is known.
+    dropin = None
+    if world == 1:
+        from gsvc_b200 import rasterizer as R_
+        gbig = synthetic_gaussians(int(cfg["P"] * 1.2), geom, f0, f0, threshold=THRESHOLD, seed=12, device=device)
+        rng = np.random.default_rng(7)
+        sizes = [int(cfg["P"] * (0.8 + 0.4 * rng.random())) for _ in range(64)]
+        it = [0]
+
+        def dropin_step():
+            Pi = sizes[it[0] % len(sizes)]
+            it[0] += 1
+            p = {k: gbig[k][:Pi].detach().requires_grad_(True) for k, _ in GRAD_LAYOUT}
+            means2D = torch.zeros_like(p["means3D"], requires_grad=True)
+            color, radii, n = rast(means3D=p["means3D"], means2D=means2D, shs=None, colors_precomp=p["colors_precomp"],
+                                   opacities=p["opacities"], scales=p["scales"], rotations=p["rotations"],
+                                   cov3D_precomp=None)
+            return torch.autograd.grad(color, [p[k] for k, _ in GRAD_LAYOUT], grad_outputs=dL[0])
+
+        for _ in range(8):
+            dropin_step()
+        torch.cuda.synchronize(device)
+        before = dict(R_.capacity_stats)
+        ms = min(timed(dropin_step, args.steps)[0] for _ in range(REPEATS))
+        st_ = dist_stats(timed.last_per_step)
+        dropin = {"ms_per_view": ms / args.steps, "iters_per_s": 1000.0 * args.steps / ms, "median_ms": st_["median_ms"],
+                  "p10_ms": st_["p10_ms"], "p90_ms": st_["p90_ms"], "P_min": min(sizes), "P_max": max(sizes),
+                  "ratio_to_single_view_graph": (ms / args.steps) / (single_ms / args.steps),
+                  "capacity_rerenders": R_.capacity_stats["rerendered"] - before["rerendered"],
+                  "calls": R_.capacity_stats["calls"] - before["calls"],
+                  "note": "eager GaussianRasterizer + autograd, P drawn per step from 200k +- 20 % (prefixes of one "
+                          "240k set); mean P = 200k, so ms_per_view compares with single_view.graph at P = 200k"}
+        del gbig
+
+    # ---- GPU comparator (baseline/naive: the published 3DGS rasterizer structure on cub::DeviceScan /
+    # cub::DeviceRadixSort, one pixel per thread, per-pixel-atomic backward, sm_100a build; test infrastructure):
+    # the same config-2 view, forward + backward, eager with its one host synchronisation per forward
+    gpu_baseline = None
+    if world == 1 and not args.no_gpu_baseline:
+        try:
+            from baseline.naive import naive as NV
+            nv = NV.NaiveRasterizer(front)
+            a_ = [params[k] for k in ("means3D", "scales", "rotations", "opacities", "colors_precomp")]
+
+            def naive_step():
+                nv.forward(*a_)
+                return nv.backward(dL[0])
+
+            def naive_fwd():
+                return nv.forward(*a_)
+
+            for _ in range(3):
+                naive_step()
+            torch.cuda.synchronize(device)
+            nb_ms = min(timed(naive_step, args.steps)[0] for _ in range(REPEATS))
+            nf_ms = min(timed(naive_fwd, args.steps)[0] for _ in range(REPEATS))
+            NV.timing(True)
+            naive_step()
+            torch.cuda.synchronize(device)
+            nstages = NV.stage_times()
+            NV.timing(False)
+            gpu_baseline = {"value": 1000.0 * args.steps / nb_ms, "unit": UNIT, "ms_per_view": nb_ms / args.steps,
+                            "fwd_views_per_s": 1000.0 * args.steps / nf_ms, "stage_ms": {k: round(v, 5) for k, v in nstages.items()},
+                            "num_rendered": nv.R, "kind": "upstream-design comparator (baseline/naive), same scene, same SPEC",
+                            "speedup_single_view_graph": (nb_ms / args.steps) / (single_ms / args.steps),
+                            "speedup_single_view_eager": (nb_ms / args.steps) / (eager_ms / args.steps)}
+        except Exception as e:  # the comparator is optional infrastructure: say why it is absent
+            gpu_baseline = {"unavailable": f"{type(e).__name__}: {e}"}
+
+    # ---- BASELINE config 4: 1M Gaussians, 1080p, forward only (stream decode), both views
+    config4 = None
+    if world == 1:
+        c4 = CONFIGS[4]
+        g4 = synthetic_gaussians(c4["P"], geom, f0, f0, threshold=THRESHOLD, seed=4, device=device)
+        rast_b = GaussianRasterizer(raster_settings=back)
+
+        def c4_plain():
+            with torch.no_grad():
+                kw = dict(means2D=g4["means3D"], shs=None, colors_precomp=g4["colors_precomp"], opacities=g4["opacities"],
+                          scales=g4["scales"], rotations=g4["rotations"], cov3D_precomp=None)
+                a = rast(means3D=g4["means3D"], **kw)
+                b = rast_b(means3D=g4["means3D"], **kw)
+                return (a[0] + torch.flip(b[0], dims=(-1,))) * 0.5, a[2] + b[2]
+
+        for _ in range(3):
+            img4, R4 = c4_plain()
+        torch.cuda.synchronize(device)
+        plain_ms = min(timed(c4_plain, args.steps)[0] for _ in range(REPEATS))
+        streamed4 = None
+        if graphs is not None:
+            st4 = FrameStreamer(front, back, g4, n_streams=4)
+            for _ in range(8):
+                st4.render(front.viewmatrix, back.viewmatrix)
+            st4.synchronize()
+            best = None
+            for _ in range(REPEATS):
+                sync_all()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(args.steps):
+                    st4.render(front.viewmatrix, back.viewmatrix)
+                st4.wait()
+                for s_ in st4.streams:
+                    torch.cuda.current_stream(device).wait_stream(s_)
+                e1.record()
+                sync_all()
+                best = e0.elapsed_time(e1) if best is None else min(best, e0.elapsed_time(e1))
+            streamed4 = best if st4.capacity_ok() else None
+            del st4
+        config4 = {"workload": "1M Gaussians, 1920x1080, forward only, front + back view per frame (BASELINE.json configs[3])",
+                   "P": c4["P"], "R_frame": int(R4),
+                   "plain_calls": {"frames_per_s": 1000.0 * args.steps / plain_ms, "views_per_s": 2000.0 * args.steps / plain_ms,
+                                   "ms_per_frame": plain_ms / args.steps,
+                                   "how": "two eager GaussianRasterizer calls + flip + average per frame"},
+                   "streamed": None if streamed4 is None else {
+                       "frames_per_s": 1000.0 * args.steps / streamed4, "views_per_s": 2000.0 * args.steps / streamed4,
+                       "ms_per_frame": streamed4 / args.steps, "how": "gsvc_b200.graphed.FrameStreamer, 4 streams"}}
+        del g4
+
+    # ---- BASELINE config 5: 2M Gaussians, 3840x2160, forward + backward of one view (tile lists / sort stress)
+    config5 = None
+    if world == 1:
+        c5 = CONFIGS[5]
+        geom5 = CubeGeometry(c5["W"], c5["H"], c5["F"])
+        f5 = c5["F"] // 2
+        g5 = synthetic_gaussians(c5["P"], geom5, f5, f5, threshold=THRESHOLD, seed=5, device=device)
+        rast5 = GaussianRasterizer(raster_settings=settings_for(geom5, f5, device))
+        dL5 = torch.randn((3, c5["H"], c5["W"]), generator=torch.Generator().manual_seed(5)).to(device)
+        step5 = GraphedStep(rast5, g5, dL5) if graphs is not None else None
+
+        def c5_eager():
+            p = {k: g5[k].detach().requires_grad_(True) for k, _ in GRAD_LAYOUT}
+            m2 = torch.zeros_like(p["means3D"], requires_grad=True)
+            color, radii, n = rast5(means3D=p["means3D"], means2D=m2, shs=None, colors_precomp=p["colors_precomp"],
+                                    opacities=p["opacities"], scales=p["scales"], rotations=p["rotations"], cov3D_precomp=None)
+            torch.autograd.grad(color, [p[k] for k, _ in GRAD_LAYOUT], grad_outputs=dL5)
+            return n
+
+        for _ in range(3):
+            R5 = c5_eager()
+        torch.cuda.synchronize(device)
+        n5 = max(5, args.steps // 2)
+        e5_ms = min(timed(c5_eager, n5)[0] for _ in range(2))
+        g5_ms = min(timed(step5, n5)[0] for _ in range(2)) if step5 is not None else None
+        config5 = {"workload": "2M Gaussians, 3840x2160, forward + backward of one view (BASELINE.json configs[4])",
+                   "P": c5["P"], "R": int(R5), "T": ((c5["W"] + 15) // 16) * ((c5["H"] + 15) // 16),
+                   "eager": {"iters_per_s": 1000.0 * n5 / e5_ms, "ms_per_view": e5_ms / n5},
+                   "graph": None if g5_ms is None else {"iters_per_s": 1000.0 * n5 / g5_ms, "ms_per_view": g5_ms / n5}}
+        del g5, step5, dL5
+
+    # ---- BASELINE config 3: 500k Gaussians shared by an 8-frame TSW window, the 8 frames dealt round-robin to the N
+    # ranks (STRONG scaling: 16 / N views per rank in one batched chain), then ONE fp32 sum all-reduce of the [P,14]
+    # gradient buffer (28 MB) — issued after the backward and waited for INSIDE the timed events.
+    config3 = None
+    if 8 % world == 0:
+        c3 = CONFIGS[3]
+        frames3 = list(range(f0, f0 + c3["window"]))
+        g3 = synthetic_gaussians(c3["P"], geom, frames3[0], frames3[-1], threshold=THRESHOLD, seed=3, device=device)
+        mine = [f for i, f in enumerate(frames3) if i % world == rank]
+        batch3 = ViewBatch.toasts([(settings_for(geom, f, device), settings_for(geom, f, device, back=True)) for f in mine])
+        dL3 = torch.randn((len(mine), 3, H, W), generator=torch.Generator().manual_seed(300 + rank)).to(device)
+        buf3 = torch.empty((c3["P"], 14), dtype=torch.float32, device=device)
+        for _ in range(2):
+            rasterize_views(batch3, means3D=g3["means3D"], opacities=g3["opacities"], colors_precomp=g3["colors_precomp"],
+                            scales=g3["scales"], rotations=g3["rotations"])
+        step3 = GraphedStep(batch3, g3, dL3, packed=buf3) if graphs is not None else None
+
+        def c3_compute():
+            if step3 is not None:
+                return step3()
+            p = {k: g3[k].detach().requires_grad_(True) for k, _ in GRAD_LAYOUT}
+            img, _, _ = rasterize_views(batch3, means3D=p["means3D"], opacities=p["opacities"],
+                                        colors_precomp=p["colors_precomp"], scales=p["scales"], rotations=p["rotations"])
+            with packed_backward(buf3):
+                torch.autograd.grad(img, [p[k] for k, _ in GRAD_LAYOUT], grad_outputs=dL3)
+
+        def c3_step():
+            c3_compute()
+            if world > 1:
+                dist.all_reduce(buf3, op=dist.ReduceOp.SUM)      # on the compute stream: the step ends when it has
+
+        n3 = max(5, args.steps // 2)
+        for _ in range(3):
+            c3_step()
+        torch.cuda.synchronize(device)
+        w_ms = min(timed(c3_step, n3)[0] for _ in range(REPEATS))
+        c_ms = min(timed(c3_compute, n3)[0] for _ in range(REPEATS)) if world > 1 else w_ms
+        config3 = {"workload": "500k Gaussians, 8-frame TSW window (16 views) of a 600-frame 1080p video, frames dealt "
+                               "round-robin to the ranks, NCCL fp32 sum all-reduce of [P,14] per window (BASELINE.json configs[2])",
+                   "P": c3["P"], "scaling": "strong", "n_gpus": world, "views_per_rank": 2 * len(mine),
+                   "window_ms": w_ms / n3, "windows_per_s": 1000.0 * n3 / w_ms, "view_iters_per_s": 16000.0 * n3 / w_ms,
+                   "compute_only_window_ms": c_ms / n3, "exposed_collective_us": 1000.0 * (w_ms - c_ms) / n3,
+                   "allreduce_bytes": c3["P"] * 14 * 4 if world > 1 else 0,
+                   "timing": "max over ranks; the all-reduce is issued on the compute stream after the backward and the "
+                             "step's end event follows it"}
+        del g3, step3, buf3, dL3
 
     # ---- forward frames as an independent stream (video decode / evaluation: fixed Gaussians, one frame after the
     # other): graphed.FrameStreamer replays them round-robin on 4 CUDA streams so the binning of frame i+1 runs
@@ -602,6 +823,24 @@ def run_product_arm(args, rank, local_rank, world):
                        "graph_fallback": graph_note,
                        "l2": "256 MiB flush between timed steps (outside the per-step events)",
                        "timing": "best of 3 repeats of exactly K steps; per-step CUDA events summed; max over ranks",
+                       "step_ms_distribution": step_stats,
+                       # the rest of BASELINE.json's table, in a key the driver's record keeps (full dicts below)
+                       "baseline_table": {
+                           "config2_fwd_frames_per_s": per_s(fwd_ms, 1), "config2_fwd_views_per_s": per_s(fwd_ms, NV),
+                           "config2_train_view_iters_per_s": value,
+                           "config2_single_view_graph_iters_per_s": per_s(single_ms, 1),
+                           "config2_single_view_eager_iters_per_s": per_s(eager_ms, 1),
+                           "config2_dropin_eager_variable_P_iters_per_s": None if dropin is None else dropin["iters_per_s"],
+                           "config2_dropin_eager_vs_graph": None if dropin is None else dropin["ratio_to_single_view_graph"],
+                           "config2_gpu_baseline_iters_per_s": (gpu_baseline or {}).get("value"),
+                           "config3_window_ms": None if config3 is None else config3["window_ms"],
+                           "config3_view_iters_per_s": None if config3 is None else config3["view_iters_per_s"],
+                           "config3_exposed_collective_us": None if config3 is None else config3["exposed_collective_us"],
+                           "config4_fwd_frames_per_s_plain": None if config4 is None else config4["plain_calls"]["frames_per_s"],
+                           "config4_fwd_frames_per_s_streamed": None if not (config4 and config4["streamed"]) else config4["streamed"]["frames_per_s"],
+                           "config5_train_iters_per_s_graph": None if not (config5 and config5["graph"]) else config5["graph"]["iters_per_s"],
+                           "config5_train_iters_per_s_eager": None if config5 is None else config5["eager"]["iters_per_s"],
+                           "config5_R": None if config5 is None else config5["R"]},
                        "parallelism": f"frame-sharded x{world}" + (", NCCL fp32 sum all-reduce of [P,14] grads per step" if world > 1 else "")},
             "fwd_views_per_s": per_s(fwd_ms, NV),
             "fwd_frames_per_s": per_s(fwd_ms, 1),
@@ -622,6 +861,8 @@ def run_product_arm(args, rank, local_rank, world):
                           "fwd_views_per_s": per_s(eager_fwd_ms, 1)},
                 "note": "one GaussianRasterizer call = one view (no all-reduce): replayed from a CUDA graph, and "
                         "called eagerly through autograd (one host wait per forward for num_rendered)"},
+            "dropin_eager": dropin, "gpu_baseline": gpu_baseline, "config3": config3, "config4": config4, "config5": config5,
+            "step_ms_distribution": step_stats,
             "ms_per_step_with_stage_events": staged_ms / args.steps,
             "stage_ms": {k: round(v, 5) for k, v in stage_avg.items()},
             "fwd_stage_ms": {k: round(v, 5) for k, v in fwd_stage_avg.items()},
@@ -695,6 +936,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="gsvc", choices=["gsvc", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

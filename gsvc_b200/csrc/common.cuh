@@ -42,10 +42,11 @@ struct DevSettings {
 };
 
 // ---- per-Gaussian state ("geom") -------------------------------------------------------------
-//  feat0 = (pix.x, pix.y, B/A, B/C)   (the ratios steer the blend kernels' exact sub-tile culling)
+//  feat0 = (pix.x, pix.y, rho_hi, B/C)   rho = B/A as rho_hi + rho_lo (fp64 quotient split into two floats); the two
+//          ratios also steer the blend kernels' exact sub-tile culling
 //  feat1 = (conic.A, conic.B, conic.C, opacity)      feat2 = (r, g, b, view depth)
-//  feat3 = (l11, l21, l22, opacity): Cholesky factor of the conic times log2(e)/2 — what the blend kernels evaluate:
-//          alpha = opacity * 2^-((l11 dx + l21 dy)^2 + (l22 dy)^2)
+//  feat3 = (l11, rho_lo, l22, opacity): Cholesky factor L = (l11 0; l11 rho, l22) of the conic times log2(e)/2 —
+//          what the blend kernels evaluate: alpha = opacity * 2^-((l11 (dx + rho dy))^2 + (l22 dy)^2)
 //  rect  = tile rectangle (minx, miny, maxx, maxy), max exclusive; all-zero when culled
 struct GeomView {
     float4* feat0;
@@ -152,8 +153,9 @@ inline size_t bin_bytes(long long cap)
 }
 
 // Per-Gaussian gradient accumulators written by the blend backward (3 float4 per Gaussian):
-//  acc0 = (S w dx, S w dy, S w dx^2, S w dx dy)  acc1 = (S w dy^2, dL/dopacity, dL/dr, dL/dg)  acc2 = (dL/db,0,0,0)
-//  with w = Gs * dL/dGs summed over the Gaussian's pixels; preprocess_backward turns the moments into dL/dpix, dL/dconic
+//  acc0 = (S w u, S w v, S w u^2, S w u v)  acc1 = (S w v^2, S w, dL/dr, dL/dg)  acc2 = (dL/db,0,0,0)
+//  with w = Gs * dL/dGs summed over the Gaussian's pixels and (u, v) = L^T (xy - pixel) the offset whitened by the
+//  Cholesky factor in feat3; preprocess_backward turns the moments into dL/dpix, dL/dcov2D (a congruence with L)
 inline size_t bwd_scratch_bytes(int P) { return align_up((size_t)P * 48, 256) + 256; }
 
 // U2: order-preserving float -> uint32 (ascending key == ascending view depth, negatives included)
@@ -181,6 +183,73 @@ __device__ __forceinline__ void st_row4(float* __restrict__ base, size_t row, fl
     if ((reinterpret_cast<uintptr_t>(base) & 15u) == 0u) { reinterpret_cast<float4*>(base)[row] = v; return; }
     float* p = base + 4 * row;
     p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w;
+}
+
+// ---- the forward's covariance arithmetic, contraction-proof ---------------------------------------------------------
+// Sigma = (R S)(R S)^T and cov2D = scale^2 (W Sigma W^T)[0:2,0:2] + 0.3 I in fp32 with every product and sum rounded
+// separately, in this order (explicit _rn intrinsics: never fused, whatever -fmad says).  The preprocess kernel
+// builds radii / rectangles / the conic from these numbers, bit-reproducibly against the scalar CPU oracle; the
+// per-Gaussian backward evaluates d(conic)/d(cov2D) at THE SAME fp32 (a, b, c) — for an elongated Gaussian the
+// inverse is so ill-conditioned (det = a c - b^2 cancels by the squared axis ratio) that "the same to 1e-7" would
+// already be a different Gaussian along the long axis.
+#define GSVC_MUL(a, b) __fmul_rn((a), (b))
+#define GSVC_ADD(a, b) __fadd_rn((a), (b))
+#define GSVC_SUB(a, b) __fsub_rn((a), (b))
+
+// Quaternion (r,x,y,z) -> rotation, convention of /root/reference/utils/general_utils.py:98-119, used as given
+// (callers normalise: guassian.py:287).
+__device__ __forceinline__ void quat_to_rot(const float4 q, float R[9])
+{
+    const float r = q.x, x = q.y, y = q.z, z = q.w;
+    R[0] = GSVC_SUB(1.f, GSVC_MUL(2.f, GSVC_ADD(GSVC_MUL(y, y), GSVC_MUL(z, z))));
+    R[1] = GSVC_MUL(2.f, GSVC_SUB(GSVC_MUL(x, y), GSVC_MUL(r, z)));
+    R[2] = GSVC_MUL(2.f, GSVC_ADD(GSVC_MUL(x, z), GSVC_MUL(r, y)));
+    R[3] = GSVC_MUL(2.f, GSVC_ADD(GSVC_MUL(x, y), GSVC_MUL(r, z)));
+    R[4] = GSVC_SUB(1.f, GSVC_MUL(2.f, GSVC_ADD(GSVC_MUL(x, x), GSVC_MUL(z, z))));
+    R[5] = GSVC_MUL(2.f, GSVC_SUB(GSVC_MUL(y, z), GSVC_MUL(r, x)));
+    R[6] = GSVC_MUL(2.f, GSVC_SUB(GSVC_MUL(x, z), GSVC_MUL(r, y)));
+    R[7] = GSVC_MUL(2.f, GSVC_ADD(GSVC_MUL(y, z), GSVC_MUL(r, x)));
+    R[8] = GSVC_SUB(1.f, GSVC_MUL(2.f, GSVC_ADD(GSVC_MUL(x, x), GSVC_MUL(y, y))));
+}
+
+__device__ __forceinline__ float dot3_rn(float a0, float b0, float a1, float b1, float a2, float b2)
+{
+    return GSVC_ADD(GSVC_ADD(GSVC_MUL(a0, b0), GSVC_MUL(a1, b1)), GSVC_MUL(a2, b2));
+}
+
+__device__ __forceinline__ void cov3d_from_scale_rot(const float* s3, float mod, const float4 q, float cov[6])
+{
+    float R[9], M[9];
+    quat_to_rot(q, R);
+    const float sx = GSVC_MUL(mod, s3[0]), sy = GSVC_MUL(mod, s3[1]), sz = GSVC_MUL(mod, s3[2]);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        M[3 * i + 0] = GSVC_MUL(R[3 * i + 0], sx);
+        M[3 * i + 1] = GSVC_MUL(R[3 * i + 1], sy);
+        M[3 * i + 2] = GSVC_MUL(R[3 * i + 2], sz);
+    }
+    cov[0] = dot3_rn(M[0], M[0], M[1], M[1], M[2], M[2]);
+    cov[1] = dot3_rn(M[0], M[3], M[1], M[4], M[2], M[5]);
+    cov[2] = dot3_rn(M[0], M[6], M[1], M[7], M[2], M[8]);
+    cov[3] = dot3_rn(M[3], M[3], M[4], M[4], M[5], M[5]);
+    cov[4] = dot3_rn(M[3], M[6], M[4], M[7], M[5], M[8]);
+    cov[5] = dot3_rn(M[6], M[6], M[7], M[7], M[8], M[8]);
+}
+
+// cov2D = scale^2 (W Sigma W^T)[0:2,0:2] + 0.3 I  — the orthographic Jacobian is scale*[I2|0] (no perspective term)
+__device__ __forceinline__ void cov2d_ortho(const float cov[6], const float w0[3], const float w1[3], float scale,
+                                            float& a, float& b, float& c)
+{
+    const float u00 = dot3_rn(cov[0], w0[0], cov[1], w0[1], cov[2], w0[2]);
+    const float u01 = dot3_rn(cov[1], w0[0], cov[3], w0[1], cov[4], w0[2]);
+    const float u02 = dot3_rn(cov[2], w0[0], cov[4], w0[1], cov[5], w0[2]);
+    const float u10 = dot3_rn(cov[0], w1[0], cov[1], w1[1], cov[2], w1[2]);
+    const float u11 = dot3_rn(cov[1], w1[0], cov[3], w1[1], cov[4], w1[2]);
+    const float u12 = dot3_rn(cov[2], w1[0], cov[4], w1[1], cov[5], w1[2]);
+    const float s2 = GSVC_MUL(scale, scale);
+    a = GSVC_ADD(GSVC_MUL(s2, dot3_rn(w0[0], u00, w0[1], u01, w0[2], u02)), LOWPASS);
+    b = GSVC_MUL(s2, dot3_rn(w0[0], u10, w0[1], u11, w0[2], u12));
+    c = GSVC_ADD(GSVC_MUL(s2, dot3_rn(w1[0], u10, w1[1], u11, w1[2], u12)), LOWPASS);
 }
 
 // ---- programmatic dependent launch (sm_90+): every kernel of a forward / backward chain is launched with

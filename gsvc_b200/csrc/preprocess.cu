@@ -23,56 +23,7 @@ __device__ const float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.
                                    0.3731763325901154f, -0.4570457994644658f, 1.445305721320277f,
                                    -0.5900435899266435f};
 
-// Quaternion (r,x,y,z) -> rotation, convention of /root/reference/utils/general_utils.py:98-119,
-// used as given (callers normalise: guassian.py:287).
-__device__ __forceinline__ void quat_to_rot(const float4 q, float R[9])
-{
-    const float r = q.x, x = q.y, y = q.z, z = q.w;
-    R[0] = 1.f - 2.f * (y * y + z * z);
-    R[1] = 2.f * (x * y - r * z);
-    R[2] = 2.f * (x * z + r * y);
-    R[3] = 2.f * (x * y + r * z);
-    R[4] = 1.f - 2.f * (x * x + z * z);
-    R[5] = 2.f * (y * z - r * x);
-    R[6] = 2.f * (x * z - r * y);
-    R[7] = 2.f * (y * z + r * x);
-    R[8] = 1.f - 2.f * (x * x + y * y);
-}
-
-__device__ __forceinline__ void cov3d_from_scale_rot(const float* s3, float mod, const float4 q, float cov[6])
-{
-    float R[9], M[9];
-    quat_to_rot(q, R);
-    const float sx = mod * s3[0], sy = mod * s3[1], sz = mod * s3[2];
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        M[3 * i + 0] = R[3 * i + 0] * sx;
-        M[3 * i + 1] = R[3 * i + 1] * sy;
-        M[3 * i + 2] = R[3 * i + 2] * sz;
-    }
-    cov[0] = M[0] * M[0] + M[1] * M[1] + M[2] * M[2];
-    cov[1] = M[0] * M[3] + M[1] * M[4] + M[2] * M[5];
-    cov[2] = M[0] * M[6] + M[1] * M[7] + M[2] * M[8];
-    cov[3] = M[3] * M[3] + M[4] * M[4] + M[5] * M[5];
-    cov[4] = M[3] * M[6] + M[4] * M[7] + M[5] * M[8];
-    cov[5] = M[6] * M[6] + M[7] * M[7] + M[8] * M[8];
-}
-
-// cov2D = scale^2 (W Sigma W^T)[0:2,0:2] + 0.3 I  — the orthographic Jacobian is scale*[I2|0] (no perspective term)
-__device__ __forceinline__ void cov2d_ortho(const float cov[6], const float w0[3], const float w1[3], float scale,
-                                            float& a, float& b, float& c)
-{
-    const float u00 = cov[0] * w0[0] + cov[1] * w0[1] + cov[2] * w0[2];
-    const float u01 = cov[1] * w0[0] + cov[3] * w0[1] + cov[4] * w0[2];
-    const float u02 = cov[2] * w0[0] + cov[4] * w0[1] + cov[5] * w0[2];
-    const float u10 = cov[0] * w1[0] + cov[1] * w1[1] + cov[2] * w1[2];
-    const float u11 = cov[1] * w1[0] + cov[3] * w1[1] + cov[4] * w1[2];
-    const float u12 = cov[2] * w1[0] + cov[4] * w1[1] + cov[5] * w1[2];
-    const float s2 = scale * scale;
-    a = s2 * (w0[0] * u00 + w0[1] * u01 + w0[2] * u02) + LOWPASS;
-    b = s2 * (w0[0] * u10 + w0[1] * u11 + w0[2] * u12);
-    c = s2 * (w1[0] * u10 + w1[1] * u11 + w1[2] * u12) + LOWPASS;
-}
+// quat_to_rot / cov3d_from_scale_rot / cov2d_ortho: common.cuh (shared, bit for bit, with the per-Gaussian backward)
 
 __device__ __forceinline__ void sh_to_rgb(int deg, const float* sh, const float p[3], const float campos[3],
                                           float rgb[3], uint8_t clamped[3])
@@ -307,20 +258,29 @@ __global__ void __launch_bounds__(256) preprocess_kernel(DevSettings s, PreInput
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
             acc_to_zero[3 * gv] = z; acc_to_zero[3 * gv + 1] = z; acc_to_zero[3 * gv + 2] = z;
         }
-        // What the blend kernels evaluate: the Cholesky factor L of the STORED conic (A, B; B, C) times log2(e)/2,
-        //   alpha = op * 2^-((l11 dx + l21 dy)^2 + (l22 dy)^2),
-        // a sum of squares where A dx^2 + B dx dy + C dy^2 cancels.  The Schur complement C - B^2/A itself cancels
-        // for an elongated, rotated Gaussian (B^2 ~ A C): it comes from A C - B^2 with the products' rounding errors
-        // recovered by FMAs (two-product), so L represents the quadratic form of exactly these three fp32 numbers to
-        // fp32 relative accuracy — which is what the reference evaluates.
+        // What the blend kernels evaluate: the STORED conic (A, B; B, C) times log2(e)/2 = K, factored as L L^T with
+        // L = (l11 0; l11 rho, l22), rho = B / A:
+        //   alpha = op * 2^-(u^2 + v^2),   u = l11 (dx + rho dy),   v = l22 dy
+        // a sum of squares where A dx^2 + 2 B dx dy + C dy^2 cancels.  Two places need more than fp32 for an elongated,
+        // rotated Gaussian (B^2 ~ A C):
+        //  * the Schur complement C - B^2/A behind l22: from A C - B^2 with the products' rounding errors recovered by
+        //    FMAs (two-product);
+        //  * the shear rho.  dx + rho dy cancels along the needle (hundreds of pixels against a result of a few), so a
+        //    1e-7 relative error of rho is 1e-4 px of lateral offset 1000 px out — 1e-4 relative in alpha for a needle
+        //    half a pixel wide, and the same in every moment its gradients are made of (found by the referee checker:
+        //    scale / rotation gradients of 256:1 needles off by 4e-4).  rho is therefore carried as an unevaluated
+        //    sum rho_hi + rho_lo of two floats from the fp64 quotient, and the blend accumulates dx + rho_hi dy +
+        //    rho_lo dy with FMAs (exact products, rounding at the small result).
+        // l11 and l22 only scale u and v: their fp32 rounding is a 1e-7 relative error of the exponent, harmless.
         const float kL = 0.5f * 1.4426950408889634f;
         const float pac = cA * cC, pbb = cB * cB;
         const float det_c = (pac - pbb) + (fmaf(cA, cC, -pac) - fmaf(cB, cB, -pbb));
         const float aL = cA * kL;
-        const float r11 = rsqrtf(aL);                          // A > 0: cov2D is positive definite (+0.3 on the diagonal)
         const float d22 = fmaxf(__fdividef(det_c, cA) * kL, 1e-30f);
-        geo.feat0[gv] = make_float4(px, py, __fdividef(cB, cA), __fdividef(cB, cC));   // culling aids: approximate is fine
-        geo.feat3[gv] = make_float4(aL * r11, (cB * kL) * r11, d22 * rsqrtf(d22), op);
+        const double rho = (double)cB / (double)cA;            // A > 0: cov2D is positive definite (+0.3 on the diagonal)
+        const float rho_hi = (float)rho, rho_lo = (float)(rho - (double)rho_hi);
+        geo.feat0[gv] = make_float4(px, py, rho_hi, __fdividef(cB, cC));   // .z, .w also steer the blend's sub-tile culling
+        geo.feat3[gv] = make_float4(aL * rsqrtf(aL), rho_lo, d22 * rsqrtf(d22), op);
         geo.feat1[gv] = make_float4(cA, cB, cC, op);
         geo.feat2[gv] = make_float4(rgb[0], rgb[1], rgb[2], vz);
         geo.rect[gv] = make_ushort4((unsigned short)rminx, (unsigned short)rminy, (unsigned short)rmaxx,

@@ -105,17 +105,56 @@ __global__ void __launch_bounds__(256, 3) preprocess_backward_kernel(DevSettings
     const bool vis = radii[gv] > 0;
     float dm2[2] = {0.f, 0.f};
     if (vis) {
-        // blend-backward accumulators: raw moments of w = Gs dL/dGs (see render.cu)
-        //   a0 = (S w dx, S w dy, S w dx^2, S w dx dy)  a1 = (S w dy^2, S w, dL/dr, dL/dg)  a2.x = dL/db
+        // blend-backward accumulators: raw moments of w = Gs dL/dGs in the whitened offset (u, v) = L^T d (render.cu)
+        //   a0 = (S w u, S w v, S w u^2, S w u v)  a1 = (S w v^2, S w, dL/dr, dL/dg)  a2.x = dL/db
+        // with L L^T = K * (stored fp32 conic), K = log2(e)/2, L = (l11 0; l11 rho, l22), rho = rho_hi + rho_lo, as the
+        // preprocess kernel stored it (feat0.z, feat3)
         const float4 a0 = acc[3 * gv], a1 = acc[3 * gv + 1], a2 = acc[3 * gv + 2];
-        const float4 con = geo.feat1[gv];  // conic (A, B, C), opacity
-        const float gpx = -(con.x * a0.x + con.y * a0.y), gpy = -(con.z * a0.y + con.y * a0.x);
-        const float gA = -0.5f * a0.z, gB = -a0.w, gC = -0.5f * a1.x;
+        const float4 con = geo.feat3[gv];  // (l11, rho_lo, l22, opacity)
+        const double rho = (double)geo.feat0[gv].z + (double)con.y;
+        const float w0[3] = {ldVb(s, v, 0, 0), ldVb(s, v, 0, 1), ldVb(s, v, 0, 2)};
+        const float w1[3] = {ldVb(s, v, 1, 0), ldVb(s, v, 1, 1), ldVb(s, v, 1, 2)};
+        const double W0[3] = {w0[0], w0[1], w0[2]}, W1[3] = {w1[0], w1[1], w1[2]};
+
+        // Sigma and cov2D = (a b; b c) exactly as the forward formed them (fp32, the shared contraction-proof
+        // routines of common.cuh): the conic the blend evaluated is fl(inverse) of THESE numbers, so this is the point
+        // at which d(conic)/d(cov2D) = -Q (.) Q is taken — in fp64 from here on.  (Recomputing them in fp64 from the
+        // inputs gives "the same" (a, b, c) to 1e-7, which for an elongated Gaussian is a different inverse: det
+        // cancels by the squared axis ratio.  The oracle and the upstream design differentiate at the forward's values
+        // too.)
+        float covf[6], Rf[9];
+        double R[9], sv[3] = {0., 0., 0.};
+        if (in.cov3D_precomp) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) covf[k] = in.cov3D_precomp[6 * (size_t)g + k];
+        } else {
+            const float4 q = ld_row4(in.rotations, (size_t)g);
+            const float sc3[3] = {in.scales[3 * g], in.scales[3 * g + 1], in.scales[3 * g + 2]};
+            cov3d_from_scale_rot(sc3, s.scale_modifier, q, covf);
+            quat_to_rot(q, Rf);
+#pragma unroll
+            for (int k = 0; k < 9; k++) R[k] = Rf[k];
+#pragma unroll
+            for (int k = 0; k < 3; k++) sv[k] = (double)s.scale_modifier * (double)sc3[k];
+        }
+        float af, bf, cf;
+        cov2d_ortho(covf, w0, w1, s.scale, af, bf, cf);
+        const double a = af, b = bf, c = cf;
+        const double det_inv = 1. / (a * c - b * b);
+        const double qA = c * det_inv, qB = -b * det_inv, qC = a * det_inv;        // Q, exact to fp64
+        // d = L^-T (u v)  =>  Q d = X (u v) with X = Q L^-T (equal to L / K up to the conic's fp32 rounding)
+        const double l11 = con.x, l21 = l11 * rho, l22 = con.z;
+        const double i11 = 1. / l11, i22 = 1. / l22, i12 = -rho * i22;              // L^-T = (i11 i12; 0 i22)
+        const double x00 = qA * i11, x01 = qA * i12 + qB * i22;
+        const double x10 = qB * i11, x11 = qB * i12 + qC * i22;
+        // dL/dpix: the blend evaluates the exponent with the STORED conic = L L^T / K, so d(power)/dd = -(L L^T / K) d
+        // and dL/dpix = -(1/K) L (S w u, S w v) — exactly, not through Q
+        const double Kd = 0.5 * 1.4426950408889634;
+        const float gpx = (float)(-(l11 * (double)a0.x) / Kd);
+        const float gpy = (float)(-(l21 * (double)a0.x + l22 * (double)a0.y) / Kd);
         dop += con.w != 0.f ? a1.y / con.w : 0.f;   // a1.y = S w = opacity * S Gs dL/dalpha (zero opacity: never blended)
         const float dcv[3] = {a1.z, a1.w, a2.x};
         dcol[0] += dcv[0]; dcol[1] += dcv[1]; dcol[2] += dcv[2];
-        const float w0[3] = {ldVb(s, v, 0, 0), ldVb(s, v, 0, 1), ldVb(s, v, 0, 2)};
-        const float w1[3] = {ldVb(s, v, 1, 0), ldVb(s, v, 1, 1), ldVb(s, v, 1, 2)};
         const float p[3] = {in.means3D[3 * g], in.means3D[3 * g + 1], in.means3D[3 * g + 2]};
 
         if (in.shs && out.dL_dshs) {
@@ -131,72 +170,41 @@ __global__ void __launch_bounds__(256, 3) preprocess_backward_kernel(DevSettings
         dm2[0] = gpx * 0.5f * (float)s.W;  // U3
         dm2[1] = gpy * 0.5f * (float)s.H;
 
-        // Forward recomputation of Sigma and cov2D, then the conic -> cov2D -> Sigma -> (scale, quaternion)
-        // chain.  The chain divides by det^2 and sums terms of opposite sign, so it is evaluated in
-        // fp64 (a few hundred flops per visible Gaussian in an HBM-bound kernel: free on B200) — in
-        // fp32 the cancellation alone costs ~3e-5 relative on rotation gradients.
-        double cov[6], R[9], sv[3] = {0., 0., 0.};
-        const double W0[3] = {w0[0], w0[1], w0[2]}, W1[3] = {w1[0], w1[1], w1[2]};
+        // dL/dcov2D = -Q (dL/dQ) Q = (1/2) S w (Q d)(Q d)^T = (1/2) X M X^T, M = S w [u v][u v]^T the whitened moments:
+        // a congruence — no division by det^2, no terms that cancel for an elongated Gaussian.
+        const double muu = a0.z, muv = a0.w, mvv = a1.x;
+        const double Jr0[3] = {(double)s.scale * W0[0], (double)s.scale * W0[1], (double)s.scale * W0[2]};   // J = scale * W[0:2,:]
+        const double Jr1[3] = {(double)s.scale * W1[0], (double)s.scale * W1[1], (double)s.scale * W1[2]};
         if (in.cov3D_precomp) {
+            // the covariance itself is the parameter: dL/dSigma = J^T (1/2 X M X^T) J, symmetric entries summed
+            const double t00 = x00 * muu + x01 * muv, t01 = x00 * muv + x01 * mvv;      // rows of X M
+            const double t10 = x10 * muu + x11 * muv, t11 = x10 * muv + x11 * mvv;
+            const double da = 0.5 * (t00 * x00 + t01 * x01), db = t00 * x10 + t01 * x11, dc = 0.5 * (t10 * x10 + t11 * x11);
+            double Gm[9];
 #pragma unroll
-            for (int k = 0; k < 6; k++) cov[k] = in.cov3D_precomp[6 * (size_t)g + k];
-        } else {
-            const float4 q = ld_row4(in.rotations, (size_t)g);
-            const double r = q.x, x = q.y, y = q.z, z = q.w;
-            R[0] = 1. - 2. * (y * y + z * z); R[1] = 2. * (x * y - r * z); R[2] = 2. * (x * z + r * y);
-            R[3] = 2. * (x * y + r * z); R[4] = 1. - 2. * (x * x + z * z); R[5] = 2. * (y * z - r * x);
-            R[6] = 2. * (x * z - r * y); R[7] = 2. * (y * z + r * x); R[8] = 1. - 2. * (x * x + y * y);
+            for (int k = 0; k < 3; k++)
 #pragma unroll
-            for (int k = 0; k < 3; k++) sv[k] = (double)s.scale_modifier * (double)in.scales[3 * g + k];
-            double M[9];
-#pragma unroll
-            for (int i = 0; i < 3; i++)
-#pragma unroll
-                for (int j = 0; j < 3; j++) M[3 * i + j] = R[3 * i + j] * sv[j];
-            cov[0] = M[0] * M[0] + M[1] * M[1] + M[2] * M[2];
-            cov[1] = M[0] * M[3] + M[1] * M[4] + M[2] * M[5];
-            cov[2] = M[0] * M[6] + M[1] * M[7] + M[2] * M[8];
-            cov[3] = M[3] * M[3] + M[4] * M[4] + M[5] * M[5];
-            cov[4] = M[3] * M[6] + M[4] * M[7] + M[5] * M[8];
-            cov[5] = M[6] * M[6] + M[7] * M[7] + M[8] * M[8];
-        }
-        const double u0[3] = {cov[0] * W0[0] + cov[1] * W0[1] + cov[2] * W0[2], cov[1] * W0[0] + cov[3] * W0[1] + cov[4] * W0[2],
-                              cov[2] * W0[0] + cov[4] * W0[1] + cov[5] * W0[2]};
-        const double u1[3] = {cov[0] * W1[0] + cov[1] * W1[1] + cov[2] * W1[2], cov[1] * W1[0] + cov[3] * W1[1] + cov[4] * W1[2],
-                              cov[2] * W1[0] + cov[4] * W1[1] + cov[5] * W1[2]};
-        const double s2 = (double)s.scale * (double)s.scale;
-        const double a = s2 * (W0[0] * u0[0] + W0[1] * u0[1] + W0[2] * u0[2]) + (double)LOWPASS;
-        const double b = s2 * (W0[0] * u1[0] + W0[1] * u1[1] + W0[2] * u1[2]);
-        const double c = s2 * (W1[0] * u1[0] + W1[1] * u1[1] + W1[2] * u1[2]) + (double)LOWPASS;
-        const double det = a * c - b * b;
-        const double d2 = 1. / (det * det);
-        const double GA = gA, GB = gB, GC = gC;
-        // conic = (c, -b, a)/det  ->  cov2D entries (a, b, c)
-        double da = d2 * (-c * c * GA + b * c * GB - b * b * GC);
-        double db = d2 * (2. * b * c * GA - (det + 2. * b * b) * GB + 2. * a * b * GC);
-        double dc = d2 * (-b * b * GA + a * b * GB - a * a * GC);
-        da *= s2; db *= s2; dc *= s2;
-        // G[k][l] = dL/dSigma[k][l] treating the 9 entries as independent
-        double Gm[9];
-#pragma unroll
-        for (int k = 0; k < 3; k++)
-#pragma unroll
-            for (int l = 0; l < 3; l++) Gm[3 * k + l] = da * W0[k] * W0[l] + db * W0[k] * W1[l] + dc * W1[k] * W1[l];
-        if (in.cov3D_precomp) {
+                for (int l = 0; l < 3; l++) Gm[3 * k + l] = da * Jr0[k] * Jr0[l] + db * Jr0[k] * Jr1[l] + dc * Jr1[k] * Jr1[l];
             dcov[0] += (float)Gm[0]; dcov[1] += (float)(Gm[1] + Gm[3]); dcov[2] += (float)(Gm[2] + Gm[6]);
             dcov[3] += (float)Gm[4]; dcov[4] += (float)(Gm[5] + Gm[7]); dcov[5] += (float)Gm[8];
         } else {
-            // Sigma = M M^T, M = R diag(mod*s):  dL/dM = (G + G^T) M
+            // cov2D = N N^T + 0.3 I with N = J R diag(mod * s) (2x3, column j = the image of axis j), so
+            //   dL/dN = 2 (1/2 X M X^T) N = X M Z,  Z = X^T N   and   dL/d(R diag) = J^T X M Z.
+            // Column by column: z_j = X^T n_j is the WHITENED image of axis j, formed in fp64 (for the long axis of a
+            // needle Q n_j cancels by the squared axis ratio — fine in fp64), and only then meets the fp32 moments.
+            // Going through the 3x3 dL/dSigma instead projects its dominant short-axis component away again for
+            // the long axis and loses that ratio in accuracy (1e-7 * 256^2 on the test scenes).
             double dM[9];
 #pragma unroll
-            for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) {
+                const double n0 = (Jr0[0] * R[j] + Jr0[1] * R[3 + j] + Jr0[2] * R[6 + j]) * sv[j];
+                const double n1 = (Jr1[0] * R[j] + Jr1[1] * R[3 + j] + Jr1[2] * R[6 + j]) * sv[j];
+                const double z0 = x00 * n0 + x10 * n1, z1 = x01 * n0 + x11 * n1;         // X^T n_j
+                const double m0 = muu * z0 + muv * z1, m1 = muv * z0 + mvv * z1;         // M z_j
+                const double b0 = x00 * m0 + x01 * m1, b1 = x10 * m0 + x11 * m1;         // X M z_j
 #pragma unroll
-                for (int j = 0; j < 3; j++) {
-                    double t = 0.;
-#pragma unroll
-                    for (int k = 0; k < 3; k++) t += (Gm[3 * i + k] + Gm[3 * k + i]) * (R[3 * k + j] * sv[j]);
-                    dM[3 * i + j] = t;
-                }
+                for (int i = 0; i < 3; i++) dM[3 * i + j] = Jr0[i] * b0 + Jr1[i] * b1;
+            }
             double gR[9];
 #pragma unroll
             for (int j = 0; j < 3; j++) {

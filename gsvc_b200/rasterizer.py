@@ -54,6 +54,9 @@ class GaussianRasterizationSettings(NamedTuple):
 _capacity_hint: dict = {}
 _density_hint: dict = {}
 _count_slots = threading.local()
+# how often the predicted capacity fell short and scatter / sort / blend had to be re-enqueued on a larger buffer
+# (eager calls only; bench.py reports it for the variable-P drop-in leg)
+capacity_stats = {"calls": 0, "rerendered": 0, "cold": 0}
 
 
 def _predict_capacity(key_exact, key_density, P: int):
@@ -311,9 +314,11 @@ class _RasterizeGaussians(torch.autograd.Function):
                     num_rendered = _lib.check(L.gsvc_rast_wait_count(slot, ticket, stream), "gsvc_rast_wait_count")
                 if num_rendered > 0xFFFFFFFF:
                     raise RasterizerError(f"num_rendered {num_rendered} exceeds 32-bit tile ranges")
+                capacity_stats["calls"] += 1
                 if num_rendered > cap or cap == 0:
-                    # first call for this shape, or the hint was too small: size exactly and run the
+                    # first call at this image size, or the prediction was too small: size exactly and run the
                     # scatter / sort / blend stages on the state that is already in place (stream-ordered)
+                    capacity_stats["cold" if cap == 0 else "rerendered"] += 1
                     cap = max(num_rendered, 1)
                     binning = _bytes(L.gsvc_rast_binning_bytes(cap), device)
                     bin_p = binning.data_ptr()

@@ -448,6 +448,7 @@ void orc_render_backward(const orc_settings *st, const uint32_t *ranges, const u
             uint32_t last = n_contrib[pix];
             float Gd[3], accum[3] = {0.f, 0.f, 0.f}, last_col[3] = {0.f, 0.f, 0.f};
             float last_alpha = 0.f;
+            double Td = (double)T_final, accum_d[3] = {0., 0., 0.}, last_col_d[3] = {0., 0., 0.}, last_alpha_d = 0.;
             for (int c = 0; c < 3; c++) Gd[c] = dL_dout[(size_t)c * H * W + pix];
             float bg_dot = st->bg[0] * Gd[0] + st->bg[1] * Gd[1] + st->bg[2] * Gd[2];
             float pxf = (float)i, pyf = (float)j;
@@ -482,6 +483,49 @@ void orc_render_backward(const orc_settings *st, const uint32_t *ranges, const u
                 if (power > 0.f) continue;
                 float alpha = fminf(ALPHA_MAX, co[3] * Gs);
                 if (alpha < ALPHA_MIN) continue;
+                if (g_power_f64) {
+                    /* Referee mode: the decisions above are the forward's (same fp32 alpha); the VALUES of the
+                     * derivative are formed in double from the same fp32 state (conic, xy, rgb, final_T).  With fp32
+                     * products the three conic moments of a pair round independently, and the way from dL/dconic to
+                     * dL/dcov2D (division by det^2, terms that cancel) amplifies that by the squared axis ratio of
+                     * an elongated Gaussian: measured against this branch, the fp32-product replay is off by up to
+                     * 1e-5 of a tensor's largest entry and up to 4x the per-Gaussian tolerance of tests/parity.py
+                     * on needle scenes — too close to the 1e-4 bar for the thing that referees it. */
+                    double ad = fmin((double)ALPHA_MAX, (double)co[3] * exp(exponent_f64(co, dx, dy)));
+                    double Gsd = exp(exponent_f64(co, dx, dy));
+                    Td = Td / (1.0 - ad);
+                    double dchan_d = ad * Td, dla = 0.0;
+                    for (int c = 0; c < 3; c++) {
+                        double col = rgb[3 * g + c];
+                        accum_d[c] = last_alpha_d * last_col_d[c] + (1.0 - last_alpha_d) * accum_d[c];
+                        last_col_d[c] = col;
+                        dla += (col - accum_d[c]) * (double)Gd[c];
+                        double v = dchan_d * (double)Gd[c];
+#pragma omp atomic
+                        dL_drgb[3 * g + c] += v;
+                    }
+                    dla *= Td;
+                    last_alpha_d = ad;
+                    dla += (-(double)T_final / (1.0 - ad)) * (double)bg_dot;
+                    double dLdG = (double)co[3] * dla;                   /* U4: straight-through the 0.99 cap */
+                    double x = dx, y = dy, gdxd = Gsd * x, gdyd = Gsd * y;
+                    double v0 = dLdG * (-gdxd * co[0] - gdyd * co[1]), v1 = dLdG * (-gdyd * co[2] - gdxd * co[1]);
+                    double cAd = -0.5 * gdxd * x * dLdG, cBd = -gdxd * y * dLdG, cCd = -0.5 * gdyd * y * dLdG;
+                    double vod = Gsd * dla;
+#pragma omp atomic
+                    dL_dpix[2 * g] += v0;
+#pragma omp atomic
+                    dL_dpix[2 * g + 1] += v1;
+#pragma omp atomic
+                    dL_dconic[3 * g] += cAd;
+#pragma omp atomic
+                    dL_dconic[3 * g + 1] += cBd;
+#pragma omp atomic
+                    dL_dconic[3 * g + 2] += cCd;
+#pragma omp atomic
+                    dL_dopacity[g] += vod;
+                    continue;
+                }
                 T = T / (1.f - alpha);
                 float dchan = alpha * T;
                 float dL_dalpha = 0.f;

@@ -222,9 +222,10 @@ def _blend_tiles(st, tiles, ranges, point_list, pix, conic, opac, rgb, bg, dtype
         power = -0.5 * (gcon[:, None, :, 0] * dx * dx + gcon[:, None, :, 2] * dy * dy) - gcon[:, None, :, 1] * dx * dy
         Gs = torch.exp(power)
     else:
-        # The CUDA blend's evaluation order (gsvc_b200/csrc/preprocess.cu feat3, render.cu neg_falloff_log2):
-        # -power*log2(e) as the sum of squares (l11 dx + l21 dy)^2 + (l22 dy)^2, L the Cholesky factor of the conic
-        # times log2(e)/2 with the Schur complement from a compensated A*C - B*B; Gs = 2^-q.  Same function of
+        # The CUDA blend's evaluation order (gsvc_b200/csrc/preprocess.cu feat0/feat3, render.cu neg_falloff_log2):
+        # -power*log2(e) as the sum of squares (l11 (dx + rho dy))^2 + (l22 dy)^2, L = (l11 0; l11 rho, l22) the
+        # Cholesky factor of the conic times log2(e)/2 with the Schur complement from a compensated A*C - B*B and
+        # the shear rho = B/A carried as a sum of two floats, accumulated with FMAs; Gs = 2^-q.  Same function of
         # (A, B, C, dx, dy), different rounding: what tests/test_oracle.py uses to check that the C oracle's
         # `fragile` map covers the pixels where two correct fp32 evaluations may disagree.
         cA, cB, cC = gcon[..., 0], gcon[..., 1], gcon[..., 2]
@@ -235,11 +236,16 @@ def _blend_tiles(st, tiles, ranges, point_list, pix, conic, opac, rgb, bg, dtype
             rbb = (cB.double() * cB.double() - pbb.double()).to(dtype)
         det_c = (pac - pbb) + (rac - rbb)
         aL = cA * kL
-        r11 = torch.rsqrt(aL)
-        l11, l21 = aL * r11, (cB * kL) * r11
+        l11 = aL * torch.rsqrt(aL)
         d22 = torch.clamp(det_c / cA * kL, min=1e-30)
         l22 = d22 * torch.rsqrt(d22)
-        u = l21[:, None, :] * dy + l11[:, None, :] * dx
+        rho = cB.double() / cA.double()
+        rho_hi = rho.to(dtype)
+        rho_lo = (rho - rho_hi.double()).to(dtype)
+        # fma(rho_lo, dy, fma(rho_hi, dy, dx)): exact product + sum in double, rounded once per FMA
+        t = (dx.double() + rho_hi.double()[:, None, :] * dy.double()).to(dtype)
+        t = (t.double() + rho_lo.double()[:, None, :] * dy.double()).to(dtype)
+        u = l11[:, None, :] * t
         v = l22[:, None, :] * dy
         q = u * u + v * v
         power = -q                 # <= 0 by construction (in units of log2)

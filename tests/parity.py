@@ -10,8 +10,8 @@ fp32 evaluation cannot decide one of the discontinuous tests).  Checker side, no
     pixel: 3-20 % of them, 70 % for screen-filling splats).  What is not exercised is the gradient of <= 0.5 % of
     the pixels, whose code path is that of every other pixel;
   * per tensor: (a) max|a-b| <= 1e-4 max|b| (the north-star bar); (b) PER GAUSSIAN, row-wise:
-    |a-b| <= ROW_RTOL |b_row| + ROW_ATOL max|b| — the share of rows that miss it is returned and bounded
-    (ROW_FAIL_MAX), and no row may miss the ROW_HARD x wider bar at all;
+    |a-b| <= ROW_RTOL |b_row| + ROW_ATOL max|b| for EVERY visible Gaussian (ROW_FAIL_MAX = 0; the share of rows
+    that miss it and the worst row in units of its tolerance are returned for the sweep records);
   * culled Gaussians must have exactly zero gradients; a scene with nothing visible must have all-zero gradients.
 """
 from __future__ import annotations
@@ -24,8 +24,8 @@ FWD_ATOL = 1e-5          # north_star: forward pixels within 1e-5 absolute
 GRAD_RTOL = 1e-4         # north_star: gradients within 1e-4 relative (of the tensor's largest entry)
 ROW_RTOL = 1e-4          # per-Gaussian criterion: |a - b| <= ROW_RTOL * max_c|b_row| + ROW_ATOL * max|b|
 ROW_ATOL = 1e-6
-ROW_FAIL_MAX = 0.01      # at most this share of the compared rows may miss the per-Gaussian criterion ...
-ROW_HARD = 10.0          # ... and none may miss it by more than this factor
+ROW_FAIL_MAX = 0.0       # no Gaussian may miss the per-Gaussian criterion (measured on B200: worst row 0.44x its
+ROW_HARD = 1.0           # tolerance over the sweeps in profiles/r3_fuzz_*.txt, needles of 256:1 axes included)
 MAX_FRAGILE = 2e-3       # share of the pixels the oracle may call undecidable on an ordinary scene
 
 GRAD_NAMES = ("means3D", "scales", "rotations", "opacities", "colors_precomp")
