@@ -459,8 +459,8 @@ def run_product_arm(args, rank, local_rank, world):
     gpu_baseline = None
     if world == 1 and not args.no_gpu_baseline:
         try:
-            from baseline.naive import naive as NV
-            nv = NV.NaiveRasterizer(front)
+            from baseline.naive import naive as NAIVE
+            nv = NAIVE.NaiveRasterizer(front)
             a_ = [params[k] for k in ("means3D", "scales", "rotations", "opacities", "colors_precomp")]
 
             def naive_step():
@@ -475,11 +475,11 @@ def run_product_arm(args, rank, local_rank, world):
             torch.cuda.synchronize(device)
             nb_ms = min(timed(naive_step, args.steps)[0] for _ in range(REPEATS))
             nf_ms = min(timed(naive_fwd, args.steps)[0] for _ in range(REPEATS))
-            NV.timing(True)
+            NAIVE.timing(True)
             naive_step()
             torch.cuda.synchronize(device)
-            nstages = NV.stage_times()
-            NV.timing(False)
+            nstages = NAIVE.stage_times()
+            NAIVE.timing(False)
             gpu_baseline = {"value": 1000.0 * args.steps / nb_ms, "unit": UNIT, "ms_per_view": nb_ms / args.steps,
                             "fwd_views_per_s": 1000.0 * args.steps / nf_ms, "stage_ms": {k: round(v, 5) for k, v in nstages.items()},
                             "num_rendered": nv.R, "kind": "upstream-design comparator (baseline/naive), same scene, same SPEC",
@@ -615,6 +615,44 @@ def run_product_arm(args, rank, local_rank, world):
                    "timing": "max over ranks; the all-reduce is issued on the compute stream after the backward and the "
                              "step's end event follows it"}
         del g3, step3, buf3, dL3
+
+
+    # ---- row f2, second half: the generator's epilogue between the MLPs and the rasterizer call
+    # (guassian.py:147-153, 251-293) fused (gsvc_b200.generate) against the PyTorch expression it replaces, forward and
+    # forward + backward, 100k visible of 600k anchors x 10 offsets (reference scale: init_anchor_num x n_offsets)
+    epilogue = None
+    if world == 1:
+        from gsvc_b200.generate import neural_gaussians_epilogue, reference_epilogue
+        Na, Ka, nv_ = 600_000, 10, 100_000
+        gg_ = torch.Generator().manual_seed(9)
+        rr = lambda *s_: torch.randn(*s_, generator=gg_).to(device)
+        ep_in = [torch.rand(Na, 3, generator=gg_).to(device), 0.3 * rr(Na, Ka, 3), torch.exp(0.3 * rr(Na, 6) - 3.0),
+                 (torch.rand(Na, Ka, 1, generator=gg_) > 0.3).float().to(device)]
+        ep_vis = torch.sort(torch.randperm(Na, generator=gg_)[:nv_])[0].to(torch.int32).to(device)
+        ep_mlp = [torch.tanh(rr(nv_, Ka)), torch.sigmoid(rr(nv_, Ka * 3)), rr(nv_, Ka * 7), 0.1 * rr(nv_, Ka * 3)]
+        lo_, hi_ = torch.zeros(1, 3, device=device), torch.ones(1, 3, device=device)
+        for t_ in ep_in[:3] + ep_mlp:
+            t_.requires_grad_(True)
+
+        def ep_run(fn, backward, **kw):
+            def step():
+                o = fn(ep_in[0], ep_in[1], ep_in[2], ep_in[3], ep_vis, ep_mlp[0], ep_mlp[1], ep_mlp[2], ep_mlp[3], lo_, hi_, **kw)
+                if backward:
+                    torch.autograd.grad(o.xyz.sum() + o.color.sum() + o.opacity.sum() + o.scaling.sum() + o.rot.sum(),
+                                        ep_in[:3] + ep_mlp)
+                return o
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize(device)
+            return min(timed(step, max(5, args.steps // 2))[0] for _ in range(2)) / max(5, args.steps // 2)
+
+        epilogue = {"anchors": Na, "visible": nv_, "n_offsets": Ka,
+                    "fused_fwd_ms": ep_run(neural_gaussians_epilogue, False), "torch_fwd_ms": ep_run(reference_epilogue, False, K=Ka),
+                    "fused_fwd_bwd_ms": ep_run(neural_gaussians_epilogue, True), "torch_fwd_bwd_ms": ep_run(reference_epilogue, True, K=Ka),
+                    "note": "gsvc_b200.generate.neural_gaussians_epilogue (gather by visible index + mask + select + activate, "
+                            "3 kernels, count through the pinned slot) vs the reference's PyTorch expression restated in "
+                            "generate.reference_epilogue (boolean-mask gathers, repeat / cat / mask-index / split)"}
+        del ep_in, ep_mlp
 
     # ---- forward frames as an independent stream (video decode / evaluation: fixed Gaussians, one frame after the
     # other): graphed.FrameStreamer replays them round-robin on 4 CUDA streams so the binning of frame i+1 runs
@@ -840,7 +878,9 @@ def run_product_arm(args, rank, local_rank, world):
                            "config4_fwd_frames_per_s_streamed": None if not (config4 and config4["streamed"]) else config4["streamed"]["frames_per_s"],
                            "config5_train_iters_per_s_graph": None if not (config5 and config5["graph"]) else config5["graph"]["iters_per_s"],
                            "config5_train_iters_per_s_eager": None if config5 is None else config5["eager"]["iters_per_s"],
-                           "config5_R": None if config5 is None else config5["R"]},
+                           "config5_R": None if config5 is None else config5["R"],
+                           "f2_epilogue_fused_vs_torch_fwd_bwd_ms": None if epilogue is None else
+                           [epilogue["fused_fwd_bwd_ms"], epilogue["torch_fwd_bwd_ms"]]},
                        "parallelism": f"frame-sharded x{world}" + (", NCCL fp32 sum all-reduce of [P,14] grads per step" if world > 1 else "")},
             "fwd_views_per_s": per_s(fwd_ms, NV),
             "fwd_frames_per_s": per_s(fwd_ms, 1),
@@ -861,7 +901,7 @@ def run_product_arm(args, rank, local_rank, world):
                           "fwd_views_per_s": per_s(eager_fwd_ms, 1)},
                 "note": "one GaussianRasterizer call = one view (no all-reduce): replayed from a CUDA graph, and "
                         "called eagerly through autograd (one host wait per forward for num_rendered)"},
-            "dropin_eager": dropin, "gpu_baseline": gpu_baseline, "config3": config3, "config4": config4, "config5": config5,
+            "generator_epilogue": epilogue, "dropin_eager": dropin, "gpu_baseline": gpu_baseline, "config3": config3, "config4": config4, "config5": config5,
             "step_ms_distribution": step_stats,
             "ms_per_step_with_stage_events": staged_ms / args.steps,
             "stage_ms": {k: round(v, 5) for k, v in stage_avg.items()},

@@ -10,7 +10,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libgsvc_rast.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # gsvc_rast_status
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_OVERFLOW = 0, -1, -2, -3, -4
@@ -79,6 +79,9 @@ SIGNATURES = {
     "gsvc_rast_launch_count": (_i64, [_i32]),
     "gsvc_rast_stage_timing": (C.c_int, [_i32]),
     "gsvc_rast_stage_times": (C.c_int, [C.POINTER(C.c_float)]),
+    "gsvc_gen_epilogue_scratch_bytes": (_sz, [_i32, _i32]),
+    "gsvc_gen_epilogue_forward": (C.c_int, [_i32, _i32] + [_vp] * 20 + [_vp, C.c_uint32, _vp]),
+    "gsvc_gen_epilogue_backward": (C.c_int, [_i32, _i32] + [_vp] * 26),
 }
 
 STAGES = ("preprocess", "tile_scan", "scatter", "sort_tiles", "render_forward", "render_backward",

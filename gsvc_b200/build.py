@@ -25,6 +25,7 @@ SOURCES = {
     "binning.cu": [],
     "render.cu": [],
     "preprocess_bwd.cu": [],
+    "epilogue.cu": [],
     "api.cu": [],
 }
 

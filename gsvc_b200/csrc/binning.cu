@@ -20,6 +20,9 @@ namespace gsvc {
 // Multi-CTA single-pass scan: CTA b scans its 1024 tiles (one tile per thread, coalesced), publishes
 // its aggregate (flag bit 63) and adds up the aggregates of all predecessors (decoupled look-back on
 // aggregates only: nothing depends on a predecessor's look-back, so there is no serial chain).
+// b is NOT blockIdx.x but a ticket drawn on entry: whoever holds ticket b knows that tickets 0..b-1 were drawn by
+// CTAs that are already running, so spinning on their aggregates cannot deadlock however the hardware orders or
+// limits the residency of the grid (a 16-view 4K batch is 507 CTAs of 1024 threads, more than fit at once).
 // The partials array sits right behind tile_count and is zeroed by the same memset.  The last CTA
 // also writes num_rendered, tagged with the caller's ticket, straight into mapped pinned host memory
 // so the host learns R as soon as the scan ends — long before the blend kernel finishes.
@@ -31,8 +34,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(int T, ImageVie
 {
     __shared__ unsigned long long warp_sums[SCAN_THREADS / 32];
     __shared__ unsigned long long s_prefix;
+    __shared__ int s_ticket;
     pdl_prologue();
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, b = blockIdx.x;
+    const int nb = (int)gridDim.x;
+    if (threadIdx.x == 0) s_ticket = (int)atomicAdd(im.scan_partials + nb, 1ull);   // the word behind the aggregates
+    __syncthreads();
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, b = s_ticket;
     const int t = b * SCAN_THREADS + tid;
     const unsigned int c = t < T ? im.tile_count[t] : 0u;
     unsigned long long v = c;
@@ -68,7 +75,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(int T, ImageVie
         }
         if (lane == 0) {
             s_prefix = prefix;
-            if (b == (int)gridDim.x - 1) {
+            if (b == nb - 1) {
                 const unsigned long long R = prefix + total;
                 im.hdr->num_rendered = R;
                 im.hdr->overflow = 0u;

@@ -67,7 +67,8 @@ struct ImageView {
     ImageHeader* hdr;
     // T below = n_views * tiles per view, H*W = n_views * pixels per view (virtual tiles / pixels)
     unsigned int* tile_count;   // [T] instances per tile (atomics in preprocess)
-    unsigned long long* scan_partials;  // [ceil(T/1024)] per-CTA aggregates of the tile scan (zeroed with tile_count)
+    unsigned long long* scan_partials;  // [T/1024 + 1] per-CTA aggregates of the tile scan, then ONE ticket word
+                                        // (the scan's dynamic CTA order); all zeroed with tile_count
     unsigned int* tile_offset;  // [T] exclusive scan of tile_count
     unsigned int* tile_cursor;  // [T] scatter cursors
     uint2* ranges;              // [T] (start,end) — (0,0) for untouched tiles, as identifyTileRanges leaves them
@@ -119,7 +120,7 @@ inline ImageView image_view(void* buf, int W, int H, int n_views = 1)
     ImageView v;
     v.hdr = carve<ImageHeader>(p, 1);
     v.tile_count = carve<unsigned int>(p, T);
-    v.scan_partials = carve<unsigned long long>(p, T / 1024 + 1);
+    v.scan_partials = carve<unsigned long long>(p, T / 1024 + 2);
     v.tile_offset = carve<unsigned int>(p, T);
     v.tile_cursor = carve<unsigned int>(p, T);
     v.ranges = carve<uint2>(p, T);
@@ -132,7 +133,7 @@ inline size_t image_bytes(int W, int H, int n_views = 1)
     char* p = nullptr;
     size_t T = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE) * n_views;
     size_t N = (size_t)W * H * n_views;
-    carve<ImageHeader>(p, 1); carve<unsigned int>(p, T); carve<unsigned long long>(p, T / 1024 + 1);
+    carve<ImageHeader>(p, 1); carve<unsigned int>(p, T); carve<unsigned long long>(p, T / 1024 + 2);
     carve<unsigned int>(p, T); carve<unsigned int>(p, T); carve<uint2>(p, T); carve<float>(p, N); carve<unsigned int>(p, N);
     return (size_t)p + 256;
 }

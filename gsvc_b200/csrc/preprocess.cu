@@ -305,6 +305,15 @@ __global__ void __launch_bounds__(256) preprocess_kernel(DevSettings s, PreInput
 
 }
 
+// the compaction scan on its own (the generator epilogue, epilogue.cu, compacts with the same three-kernel scheme)
+cudaError_t launch_compact_scan(int n_ctas, const unsigned int* cta_count, unsigned int* cta_offset,
+                                unsigned long long* count_dev, unsigned long long* host_slot, unsigned int ticket,
+                                cudaStream_t st)
+{
+    return launch_pdl(compact_scan_kernel, dim3(1), dim3(1024), st, n_ctas, cta_count, cta_offset, count_dev, host_slot,
+                      ticket);
+}
+
 cudaError_t launch_visible_filter(const DevSettings& s, const PreInputs& in, int32_t* radii, cudaStream_t st)
 {
     if (in.P <= 0) return cudaSuccess;
@@ -347,7 +356,7 @@ cudaError_t launch_preprocess(const DevSettings& s, const PreInputs& in, int32_t
 {
     // one memset clears the per-tile counters and the scan's per-CTA partials that sit right behind them
     const size_t T = (size_t)s.gx * s.gy * s.n_views;
-    const size_t nbytes = reinterpret_cast<char*>(im.scan_partials + (T / 1024 + 1)) - reinterpret_cast<char*>(im.tile_count);
+    const size_t nbytes = reinterpret_cast<char*>(im.scan_partials + (T / 1024 + 2)) - reinterpret_cast<char*>(im.tile_count);
     cudaError_t e = cudaMemsetAsync(im.tile_count, 0, nbytes, st);
     if (e != cudaSuccess) return e;
     if (in.P <= 0) return cudaSuccess;

@@ -35,7 +35,7 @@ extern "C" {
 #define GSVC_RAST_API
 #endif
 
-#define GSVC_RAST_ABI_VERSION 3
+#define GSVC_RAST_ABI_VERSION 4
 #define GSVC_RAST_TILE 16 /* tile edge in pixels; tile ids are row-major over ceil(W/16) x ceil(H/16) */
 #define GSVC_RAST_MAX_VIEWS 16 /* views per batched call (gsvc_rast_*_views) */
 
@@ -275,6 +275,48 @@ GSVC_RAST_API int64_t gsvc_rast_overflow_events(int32_t reset, void *stream);
 /* Number of kernel launches issued by this library (all threads) since the last reset
  * (bench.py reports it as gpu_launches). */
 GSVC_RAST_API int64_t gsvc_rast_launch_count(int32_t reset);
+
+/*
+ * Fused epilogue of the neural-Gaussian generator: everything
+ * /root/reference/ortho_gaussian_renderer/guassian.py does between its four per-anchor MLPs and the rasterizer call —
+ * the boolean-mask gathers of the visible anchors' rows (:147-153), opacity * mask and the opacity > 0 selection
+ * (:251-258), the repeat / cat / mask-index / split of a [N_vis*K, 22] tensor (:275-281), scaling = s[3:6] *
+ * sigmoid(.), rot = normalize(.), xyz = clamp(anchor + (offset + neural_offset) * s[0:3]) (:285-293) — as one marking
+ * pass, the filter's compaction scan and one writing pass.
+ *   visible_indices [n_vis] ascending anchor rows (gsvc_rast_visible_filter_compact), or NULL when the per-anchor
+ *       inputs are already gathered ([n_vis, ...]);
+ *   anchor [N,3], grid_offsets [N,K,3], grid_scaling [N,6], masks [N,K]: the model's (activated) per-anchor tensors;
+ *   neural_opacity [n_vis,K], color [n_vis,K*3], scale_rot [n_vis,K*7], neural_offset [n_vis,K*3]: the MLP outputs;
+ *   bound_min / bound_max [3] (device): the clamp of guassian.py:293.
+ * Outputs, rows in the reference's order (anchor-major, offset-minor, selected ones only), each with room for
+ * n_vis*K rows: xyz [.,3], color_out [.,3], opacity_out [.], scaling_out [.,3], rot_out [.,4]; plus, per (anchor,
+ * offset): neural_opacity_full [n_vis*K] (= opacity * mask, what the reference returns as `neural_opacity`),
+ * selection_mask [n_vis*K] (uint8, its `mask`) and rank [n_vis*K] (compact row or -1; the backward reads it).
+ * The number of selected Gaussians is published like num_rendered: ticket << 40 | count in count_slot_host
+ * (gsvc_rast_wait_count).  scratch: gsvc_gen_epilogue_scratch_bytes(n_vis, K) bytes.
+ *
+ * gsvc_gen_epilogue_backward: gradients w.r.t. the MLP outputs ([n_vis,...] like the inputs) and, per VISIBLE anchor,
+ * w.r.t. anchor [n_vis,3], grid_offsets [n_vis,K,3], grid_scaling [n_vis,6], masks [n_vis,K] (the caller scatters
+ * these rows to the full tensors: the gather's backward).  dL_dnop_full may be NULL.  One pass, no atomics.
+ */
+GSVC_RAST_API size_t gsvc_gen_epilogue_scratch_bytes(int32_t n_vis, int32_t K);
+GSVC_RAST_API int gsvc_gen_epilogue_forward(int32_t n_vis, int32_t K, const int32_t *visible_indices, const float *anchor,
+                                            const float *grid_offsets, const float *grid_scaling, const float *masks,
+                                            const float *neural_opacity, const float *color, const float *scale_rot,
+                                            const float *neural_offset, const float *bound_min, const float *bound_max,
+                                            float *xyz, float *color_out, float *opacity_out, float *scaling_out,
+                                            float *rot_out, float *neural_opacity_full, uint8_t *selection_mask,
+                                            int32_t *rank, void *scratch, uint64_t *count_slot_host, uint32_t ticket,
+                                            void *stream);
+GSVC_RAST_API int gsvc_gen_epilogue_backward(int32_t n_vis, int32_t K, const int32_t *visible_indices, const float *anchor,
+                                             const float *grid_offsets, const float *grid_scaling, const float *masks,
+                                             const float *neural_opacity, const float *scale_rot,
+                                             const float *neural_offset, const float *bound_min, const float *bound_max,
+                                             const int32_t *rank, const float *dL_dxyz, const float *dL_dcolor,
+                                             const float *dL_dopacity, const float *dL_dscaling, const float *dL_drot,
+                                             const float *dL_dnop_full, float *d_neural_opacity, float *d_color,
+                                             float *d_scale_rot, float *d_neural_offset, float *d_anchor,
+                                             float *d_grid_offsets, float *d_grid_scaling, float *d_masks, void *stream);
 
 #ifdef __cplusplus
 }

@@ -89,14 +89,26 @@ def grad_stats(a, b):
                 row_worst=float(ratio.max()), scale=scale, n=int(a.shape[0]))
 
 
-def check_grads(fo, go, got, names=None, rel_tol=GRAD_RTOL, row_fail_max=ROW_FAIL_MAX, row_hard=ROW_HARD, what=""):
+SMALL_SCENE = 50         # below this many visible Gaussians a tensor may be judged at the cancellation-aware bar
+
+
+def check_grads(fo, go, got, names=None, rel_tol=GRAD_RTOL, row_fail_max=ROW_FAIL_MAX, row_hard=ROW_HARD, what="",
+                cancel_ref=None):
     """`got`: name -> tensor / array with P rows (gradients for a masked_dL seed); `go`: oracle_backward result.
     Every visible Gaussian is compared.  Asserts the bars in the module docstring; returns dict(compared, rel,
-    row_fail, row_worst) (worst over the tensors) for the sweep records."""
+    row_fail, row_worst) (worst over the tensors) for the sweep records.
+
+    `cancel_ref` (randomised sweeps only): a callable returning the oracle backward for |dL|.  A scene of a handful
+    of Gaussians has no "largest gradient" to normalise by — each entry is a sum of signed per-pixel terms that can
+    cancel to far below any one of them, and then 1e-4 of the RESULT is below the fp32 rounding of its terms.  For
+    scenes with fewer than SMALL_SCENE visible Gaussians a tensor that misses the bars is re-judged against the same
+    gradient taken with |dL| (no cancellation over pixels): |a-b| <= 1e-5 of its largest entry.  Counted in
+    out["cancelled"] and reported by the sweeps; never used by the fixed-scene tests."""
     vis = fo["radii"] > 0
     P = vis.shape[0]
     names = tuple(got.keys()) if names is None else names
-    out = dict(compared=1.0, n=int(vis.sum()), rel=0.0, row_fail=0.0, row_worst=0.0)
+    out = dict(compared=1.0, n=int(vis.sum()), rel=0.0, row_fail=0.0, row_worst=0.0, cancelled=0)
+    go_abs = None
     for k in names:
         a = got[k].detach().cpu().numpy() if hasattr(got[k], "detach") else np.asarray(got[k])
         a = a.reshape(P, -1).astype(np.float64)
@@ -106,6 +118,14 @@ def check_grads(fo, go, got, names=None, rel_tol=GRAD_RTOL, row_fail_max=ROW_FAI
         if not vis.any():
             continue
         s = grad_stats(a[vis], b[vis])
+        if (cancel_ref is not None and int(vis.sum()) < SMALL_SCENE and
+                (s["rel"] > rel_tol or s["row_fail"] > row_fail_max or s["row_worst"] > row_hard)):
+            go_abs = go_abs if go_abs is not None else cancel_ref()
+            ref = float(np.abs(np.asarray(go_abs[k], np.float64).reshape(P, -1)[vis]).max(initial=0.0))
+            err = float(np.abs(a[vis] - b[vis]).max())
+            assert err <= 1e-5 * ref, f"{what}{k}: error {err:.3e} > 1e-5 of the uncancelled gradient {ref:.3e}"
+            out["cancelled"] += 1
+            continue
         assert s["rel"] <= rel_tol, f"{what}{k}: max-normalised error {s['rel']:.3e} > {rel_tol:.0e}"
         assert s["row_fail"] <= row_fail_max, (f"{what}{k}: {s['row_fail']:.4f} of {s['n']} Gaussians miss "
                                                f"|a-b| <= {ROW_RTOL:.0e}|b_row| + {ROW_ATOL:.0e} max|b|")

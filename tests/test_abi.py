@@ -22,14 +22,14 @@ def lib():
 
 def declared_symbols():
     src = open(HEADER).read()
-    return sorted(set(re.findall(r"GSVC_RAST_API\s+[\w\s\*]+?\b(gsvc_rast_\w+)\s*\(", src)))
+    return sorted(set(re.findall(r"GSVC_RAST_API\s+[\w\s\*]+?\b(gsvc_(?:rast|gen)_\w+)\s*\(", src)))
 
 
 def test_header_symbols_are_exported_and_bound(lib):
     names = declared_symbols()
     assert len(names) >= 15
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
-    exported = set(re.findall(r"\bT (gsvc_rast_\w+)", out))
+    exported = set(re.findall(r"\bT (gsvc_(?:rast|gen)_\w+)", out))
     assert set(names) == exported, (set(names) ^ exported)
     assert set(names) == set(_lib.SIGNATURES), (set(names) ^ set(_lib.SIGNATURES))
     for n in names:
@@ -44,7 +44,7 @@ def test_no_torch_or_python_dependency_in_the_abi():
 
 
 def test_abi_version_and_sizes(lib):
-    assert lib.gsvc_rast_abi_version() == _lib.ABI_VERSION == 3
+    assert lib.gsvc_rast_abi_version() == _lib.ABI_VERSION == 4
     g1, g2 = lib.gsvc_rast_geom_bytes(1000, 0), lib.gsvc_rast_geom_bytes(2000, 0)
     assert 56 * 1000 <= g1 < g2 <= 2 * g1 + 4096
     assert lib.gsvc_rast_geom_bytes(1000, 16) > g1                       # SH clamp flags
