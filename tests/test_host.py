@@ -336,3 +336,101 @@ def test_slab_index_range_never_drops_an_anchor_inside_the_slab():
                 assert float((kept - zf).abs().max()) <= thr + 3 * interval + 1e-6
     with pytest.raises(ValueError):
         z_interval_table(torch.tensor([0.2, 0.1]))
+
+
+# ---- row f3: synchronised densification of the data-parallel loop (gsvc_b200.dp_train), world_size 2 on gloo ----------
+def _dp_model(seed=5, N=400):
+    from gsvc_b200.dp_train import AnchorModel
+    g = torch.Generator().manual_seed(seed)
+    anchor = torch.rand(N, 3, generator=g) * torch.tensor([1.0, 0.6, 0.2])
+    m = AnchorModel(anchor, n_offsets=4, feat_dim=6, voxel_size=0.01, seed=seed, lr=1e-3)
+    m.p["offset"] = 6.0 * torch.randn(N, 4, 3, generator=g)        # Gaussians that left their anchor's voxel: growth candidates
+    return m
+
+
+def _dp_fake_iteration(model, rank, it):
+    """What one rank's views of an iteration would contribute: its own gradients and its own statistic deltas
+    (different on every rank — here seeded noise instead of a render, which needs a GPU)."""
+    from gsvc_b200.dp_train import PARAM_NAMES
+    N, K = model.n_anchors, model.K
+    g = torch.Generator().manual_seed(1000 * it + rank)
+    grads = {k: 1e-2 * torch.randn(model.p[k].shape, generator=g) for k in PARAM_NAMES}
+    seen = (torch.rand(N, 1, generator=g) < 0.8).float()                     # anchors visible in this rank's views
+    d_dem = 2.0 * seen
+    d_op = d_dem * torch.rand(N, 1, generator=g) * (torch.rand(N, 1, generator=g) > 0.15).float() * 0.5
+    drawn = (torch.rand(N * K, 1, generator=g) < 0.7).float() * seen.repeat_interleave(K, dim=0)
+    d_den = 2.0 * drawn
+    d_acc = d_den * torch.rand(N * K, 1, generator=g) * 1e-3
+    return grads, [d_op, d_dem, d_acc, d_den]
+
+
+def _dp_worker(rank, world, port, out_dir):
+    from gsvc_b200.dp_train import allreduce_iteration
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    model = _dp_model()
+    history = []
+    for it in range(1, 41):
+        grads, deltas = _dp_fake_iteration(model, rank, it)
+        g_avg = allreduce_iteration(model, grads, deltas, n_views_total=4, world=world)
+        model.optimizer_step(g_avg)
+        if it % 4 == 0:                                                      # ten densification rounds
+            gen = torch.Generator().manual_seed(77 + it)                     # the same seed on every rank
+            added, pruned = model.adjust_anchor(gen, check_interval=4, success_threshold=0.8, grad_threshold=4e-4,
+                                                min_opacity=0.05)
+            history.append((added, pruned, model.n_anchors))
+    torch.save((history, model.state_hash(), model.p["anchor"], model.offset_denom.shape[0]),
+               os.path.join(out_dir, f"dp{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_dp_densification_is_identical_on_every_rank(tmp_path):
+    """scene/gaussian_model.py:1302-1314 + 1362-1505 under data parallelism: every rank contributes its own views'
+    gradients and statistic deltas, ONE all-reduce per iteration carries both, adjust_anchor draws its random thinning
+    (torch.rand_like at :1369) from an identically seeded generator — after ten grow / prune rounds both ranks hold
+    bit-identical anchors, features, MLP weights and accumulators, and anchors were both added and pruned."""
+    port = _free_port()
+    mp.spawn(_dp_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    (h0, s0, a0, n0), (h1, s1, a1, n1) = torch.load(tmp_path / "dp0.pt"), torch.load(tmp_path / "dp1.pt")
+    assert h0 == h1 and torch.equal(s0, s1) and torch.equal(a0, a1) and n0 == n1 == a0.shape[0] * 4
+    assert sum(h[0] for h in h0) > 0 and sum(h[1] for h in h0) > 0, h0      # grew and pruned
+    assert a0.shape[0] != 400
+
+
+def test_dp_view_assignment_and_single_rank_statistics():
+    """train.py:353-387: the four views of an iteration, dealt to 1 / 2 / 4 ranks; and the statistic deltas of a view
+    against the reference's masked-scatter expression (scene/gaussian_model.py:1298-1314)."""
+    from gsvc_b200.dp_train import AnchorModel, views_for_rank, views_of_iteration
+    v = views_of_iteration(7)
+    assert v == [(7, False), (7, True), (8, False), (8, True)]
+    assert views_for_rank(v, 0, 1) == v and views_for_rank(v, 1, 2) == [(7, True), (8, True)]
+    assert [views_for_rank(v, r, 4) for r in range(4)] == [[x] for x in v]
+    N, K = 50, 3
+    g = torch.Generator().manual_seed(3)
+    vis_mask = torch.rand(N, generator=g) < 0.5
+    idx = torch.nonzero(vis_mask).flatten().to(torch.int32)
+    n = idx.numel()
+    nop = torch.randn(n * K, 1, generator=g)
+    sel = (nop > 0).view(-1)
+    M = int(sel.sum())
+    radii = (torch.rand(M, generator=g) < 0.7).int() * 5
+    m2g = torch.randn(M, 3, generator=g)
+    deltas = [torch.zeros(N, 1), torch.zeros(N, 1), torch.zeros(N * K, 1), torch.zeros(N * K, 1)]
+    AnchorModel.statistics_of_view(deltas, N, K, idx, nop, sel, radii, m2g)
+    # the reference expression
+    opacity_accum, anchor_demon = torch.zeros(N, 1), torch.zeros(N, 1)
+    acc, den = torch.zeros(N * K, 1), torch.zeros(N * K, 1)
+    temp = nop.clone().view(-1)
+    temp[temp < 0] = 0
+    opacity_accum[vis_mask] += temp.view(-1, K).sum(dim=1, keepdim=True)
+    anchor_demon[vis_mask] += 1
+    avm = vis_mask.unsqueeze(1).repeat(1, K).view(-1)
+    combined = torch.zeros(N * K, dtype=torch.bool)
+    combined[avm] = sel
+    tmp = combined.clone()
+    update_filter = radii > 0
+    combined[tmp] = update_filter
+    acc[combined] += torch.norm(m2g[update_filter, :2], dim=-1, keepdim=True)
+    den[combined] += 1
+    for a, b in zip(deltas, (opacity_accum, anchor_demon, acc, den)):
+        assert torch.allclose(a, b, atol=1e-6)
