@@ -67,7 +67,14 @@ def main():
     ext = torch.tensor([-2.2 * geom.x_min, -2.2 * geom.y_min, geom.z_of(F - 1) - geom.z_of(0) + 3 * thr])
     org = torch.tensor([1.1 * geom.x_min, 1.1 * geom.y_min, geom.z_of(0) - 1.5 * thr])
     anchors = (org + ext * torch.rand(args.anchors, 3, generator=g)).to(dev)
-    model = AnchorModel(anchors, n_offsets=4, feat_dim=8, voxel_size=2.0 / geom.scale, seed=5, lr=2e-3)
+    # voxel_size 0.4 px: the three growth levels of anchor_growing are 6.4 / 1.6 / 0.4 px voxels (a level only runs if
+    # the coarser one added anchors — scene/gaussian_model.py:1374-1377 — so the coarsest must be finer than the
+    # initial anchor spacing); Gaussians start 2 px wide
+    model = AnchorModel(anchors, n_offsets=4, feat_dim=8, voxel_size=0.4 / geom.scale, seed=5, lr=2e-3,
+                        init_scale=2.0 / geom.scale)
+    # the K Gaussians of an anchor start spread over its neighbourhood (the reference starts them at the anchor and
+    # lets the optimizer push them out over thousands of iterations; growth needs Gaussians that left their voxel)
+    model.p["offset"] = (1.5 * torch.randn(args.anchors, 4, 3, generator=g)).to(dev)
     trainer = DPTrainer(model, settings, target, rank=rank, world=world, seed=99, update_interval=args.interval,
                         grad_threshold=2e-5, min_opacity=0.02)
     frame_rng = torch.Generator().manual_seed(17)                   # the same frame draw on every rank (train.py:337)

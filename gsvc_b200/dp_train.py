@@ -47,7 +47,7 @@ class AnchorModel:
     (cat_tensors_to_optimizer / prune_anchor)."""
 
     def __init__(self, anchor: torch.Tensor, n_offsets: int = 4, feat_dim: int = 8, voxel_size: float = 0.01,
-                 seed: int = 0, lr: float = 2e-3):
+                 seed: int = 0, lr: float = 2e-3, init_scale: Optional[float] = None):
         dev = anchor.device
         g = torch.Generator().manual_seed(seed)
         N, K, F = int(anchor.shape[0]), int(n_offsets), int(feat_dim)
@@ -56,7 +56,7 @@ class AnchorModel:
         self.p: Dict[str, torch.Tensor] = {
             "anchor": anchor.detach().clone().float(),
             "offset": torch.zeros(N, K, 3, device=dev),
-            "scaling": torch.full((N, 6), math.log(voxel_size), device=dev),
+            "scaling": torch.full((N, 6), math.log(voxel_size if init_scale is None else init_scale), device=dev),
             "rotation": torch.tensor([1.0, 0.0, 0.0, 0.0], device=dev).repeat(N, 1),
             "anchor_feat": (0.5 * torch.randn(N, F, generator=g)).to(dev),
             "mlp_w": (0.5 * torch.randn(F + 1, 14 * K, generator=g) / math.sqrt(F + 1)).to(dev),
