@@ -84,7 +84,7 @@ __device__ void sh_backward(int deg, int M, const float* sh, float* dsh, const f
     dmean[2] += (ddz - z * dot) / len;
 }
 
-__global__ void __launch_bounds__(256, 3) preprocess_backward_kernel(DevSettings s, PreInputs in,
+__global__ void __launch_bounds__(256,2) preprocess_backward_kernel(DevSettings s, PreInputs in,
                                                                   const int32_t* __restrict__ radii, GeomView geo,
                                                                   const float4* __restrict__ acc, BwdOutputs out)
 {
@@ -258,7 +258,7 @@ cudaError_t launch_preprocess_backward(const DevSettings& s, const PreInputs& in
 {
     if (in.P <= 0) return cudaSuccess;
     count_launch();
-    return launch_pdl(preprocess_backward_kernel, dim3((in.P + 255) / 256), dim3(256), st, s, in, radii, g, acc, out);
+    return launch_pdl(preprocess_backward_kernel, dim3((in.P + 127) / 128), dim3(128), st, s, in, radii, g, acc, out);
 }
 
 // Densification statistic at the rasterizer boundary (scene/gaussian_model.py:1298-1314 `training_statis`, called

@@ -394,6 +394,17 @@ render_backward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, u
     // so by capacity_ok() — hence every tile leaves before it reads a list entry.
     if ((unsigned long long)rg.y > cap || im.hdr->overflow != 0u) return;
 
+    // The tile's start-up is a chain of dependent memory round trips: ranges -> n_contrib (-> deepest contributor) ->
+    // point list -> per-Gaussian records -> shared memory.  Where the replay starts depends on n_contrib, but for most
+    // tiles it starts at the end of the list (nothing saturated): the ids of the last BATCH entries are fetched
+    // speculatively right away, in parallel with the pixel state, which takes one round trip out of the chain.
+    unsigned int spec_id[BATCH / BLEND_THREADS];
+#pragma unroll
+    for (int r = 0; r < BATCH / BLEND_THREADS; r++) {
+        const int kp = n - 1 - (tid + r * BLEND_THREADS);
+        spec_id[r] = kp >= 0 ? __ldg(bin.point_list + rg.x + kp) : 0u;
+    }
+
     const float bg0 = __ldg(s.bg), bg1 = __ldg(s.bg + 1), bg2 = __ldg(s.bg + 2);
     PairBwd S{};
     {
@@ -432,7 +443,7 @@ render_backward_kernel(DevSettings s, GeomView geo, ImageView im, BinView bin, u
             const int slot = tid + r * BLEND_THREADS;
             const int kpos = m_len - 1 - (base + slot);  // list position staged in this slot
             if (kpos >= 0) {
-                const unsigned int id = bin.point_list[rg.x + kpos];
+                const unsigned int id = (base == 0 && m_len == n) ? spec_id[r] : bin.point_list[rg.x + kpos];
                 stage(s_feat, slot, geo, id);
             }
         }
