@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(int T, ImageVie
                 const unsigned long long R = prefix + total;
                 im.hdr->num_rendered = R;
                 im.hdr->overflow = 0u;
+                im.hdr->n_heavy = 0u;
                 if (host_slot) *host_slot = ((unsigned long long)ticket << 40) | (R < (1ull << 40) ? R : (1ull << 40) - 1);
             }
         }
@@ -295,6 +296,139 @@ __device__ __forceinline__ void sort_bucket_regs(const unsigned long long* __res
     }
 }
 
+// The same, reading and writing the bucket IN PLACE as (depth key, id) pairs split over two arrays: what the range
+// split of a heavy bucket leaves behind (below).
+template <int R, int LG>
+__device__ __forceinline__ void sort_bucket_regs_soa(unsigned int* __restrict__ ids, unsigned int* __restrict__ keys,
+                                                     int n, int lane)
+{
+    unsigned long long v[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int e = lane * R + r;
+        v[r] = e < n ? (((unsigned long long)keys[e] << 32) | ids[e]) : ~0ull;
+    }
+    __syncwarp();
+    BitonicMerges<R, 1, LG>::run(v, lane);
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int e = lane * R + r;
+        if (e < n) {
+            ids[e] = (unsigned int)v[r];
+            keys[e] = (unsigned int)(v[r] >> 32);
+        }
+    }
+}
+
+template <bool BIG>
+__device__ __forceinline__ void sort_sub_bucket_warp(unsigned int* ids, unsigned int* keys, int n, int lane)
+{
+    if (n <= 32) sort_bucket_regs_soa<1, 5>(ids, keys, n, lane);
+    else if (n <= 64) sort_bucket_regs_soa<2, 6>(ids, keys, n, lane);
+    else if (n <= 128) sort_bucket_regs_soa<4, 7>(ids, keys, n, lane);
+    else if (!BIG || n <= 256) sort_bucket_regs_soa<8, 8>(ids, keys, n, lane);
+    else sort_bucket_regs_soa<16, 9>(ids, keys, n, lane);
+}
+
+// Heavy buckets (more entries than the CTA's shared-memory sort holds: thousands of instances on one tile).  One more
+// MSD step, shaped to the data again: the depth keys of a tile are spread over its slab, so the bucket is split by a
+// MONOTONE map of the depth key onto SPLIT_BINS ranges (counting sort inside the CTA: shared-memory histogram, scan,
+// scatter into the output arrays used as scratch), and the ranges — a few hundred entries each — are sorted by the
+// warps in registers like ordinary buckets.  A range that is still too large for a warp (thousands of equal depths)
+// goes through the CTA's shared-memory network, and only a range beyond THAT falls back to the in-place global
+// network the whole bucket used to take (O(n log^2 n) global-memory passes with a block barrier each: a 50k-entry
+// tile serialised the chain for milliseconds).
+constexpr int SPLIT_BINS = 1024;
+
+template <bool BIG>
+__device__ __forceinline__ void sort_heavy_bucket(unsigned long long* __restrict__ src, unsigned int* __restrict__ ids,
+                                  unsigned int* __restrict__ keys, int nb, unsigned long long* s_items, int tid)
+{
+    constexpr int WARP_ITEMS = BIG ? SORT_WARP_ITEMS_BIG : SORT_WARP_ITEMS;
+    unsigned int* s_off = reinterpret_cast<unsigned int*>(s_items);          // [SPLIT_BINS + 1] range starts
+    unsigned int* s_cur = s_off + SPLIT_BINS + 1;                             // [SPLIT_BINS] counters, then cursors
+    unsigned int* s_red = s_cur + SPLIT_BINS;                                 // [2 * SORT_WARPS] min / max, then a list
+    const int lane = tid & 31, warp = tid >> 5;
+    // 1. depth-key range of the bucket
+    unsigned int kmin = 0xffffffffu, kmax = 0u;
+    for (int i = tid; i < nb; i += SORT_THREADS) {
+        const unsigned int k = (unsigned int)(src[i] >> 32);
+        kmin = min(kmin, k); kmax = max(kmax, k);
+    }
+    kmin = __reduce_min_sync(0xffffffffu, kmin); kmax = __reduce_max_sync(0xffffffffu, kmax);
+    if (lane == 0) { s_red[warp] = kmin; s_red[SORT_WARPS + warp] = kmax; }
+    for (int i = tid; i < SPLIT_BINS; i += SORT_THREADS) s_cur[i] = 0u;
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; w++) { kmin = min(kmin, s_red[w]); kmax = max(kmax, s_red[SORT_WARPS + w]); }
+    // ranges of ~128 entries on average (a warp sorts one in registers in ~2 us; thousands of 30-entry ranges would
+    // be bound by their load -> sort -> store latency instead)
+    int nbins = 64;
+    while (nbins < SPLIT_BINS && nbins * 128 < nb) nbins <<= 1;
+    // monotone (non-decreasing) in k: conversions, a product with a positive constant and a truncation all are
+    const float scale = (float)nbins / ((float)(kmax - kmin) + 1.0f);
+    auto bin_of = [&](unsigned int k) { return min(nbins - 1, (int)((float)(k - kmin) * scale)); };
+    // 2. histogram, exclusive scan
+    for (int i = tid; i < nb; i += SORT_THREADS) atomicAdd(&s_cur[bin_of((unsigned int)(src[i] >> 32))], 1u);
+    __syncthreads();
+    {
+        // SPLIT_BINS / SORT_THREADS consecutive bins per thread, warp scan of the thread sums, then across warps
+        constexpr int PER = SPLIT_BINS / SORT_THREADS;
+        unsigned int c[PER], sum = 0u;
+#pragma unroll
+        for (int j = 0; j < PER; j++) { c[j] = s_cur[tid * PER + j]; sum += c[j]; }
+        unsigned int incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned int o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        __syncthreads();                       // everyone has read its counters and s_red
+        if (lane == 31) s_red[warp] = incl;
+        __syncthreads();
+        unsigned int before = incl - sum;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; w++)
+            if (w < warp) before += s_red[w];
+#pragma unroll
+        for (int j = 0; j < PER; j++) { s_off[tid * PER + j] = before; s_cur[tid * PER + j] = before; before += c[j]; }
+        if (tid == SORT_THREADS - 1) s_off[SPLIT_BINS] = before;
+    }
+    __syncthreads();
+    // 3. scatter into the output arrays (in range order; unordered inside a range)
+    for (int i = tid; i < nb; i += SORT_THREADS) {
+        const unsigned long long v = src[i];
+        const unsigned int pos = atomicAdd(&s_cur[bin_of((unsigned int)(v >> 32))], 1u);
+        ids[pos] = (unsigned int)v;
+        keys[pos] = (unsigned int)(v >> 32);
+    }
+    __syncthreads();
+    // 4. ranges a warp can hold: in registers, 8 ranges at a time; larger ones are noted for the CTA
+    int n_large = 0;
+    for (int b = warp; b < nbins; b += SORT_WARPS) {
+        const int o = (int)s_off[b], n = (int)s_off[b + 1] - o;
+        if (n > 1 && n <= WARP_ITEMS) sort_sub_bucket_warp<BIG>(ids + o, keys + o, n, lane);
+    }
+    __syncthreads();
+    for (int b = 0; b < nbins; b++) {                         // block-uniform scan for the (rare) large ranges
+        const int o = (int)s_off[b], n = (int)s_off[b + 1] - o;
+        if (n <= WARP_ITEMS) continue;
+        n_large++;
+        // the split tables live in s_items: a large range borrows the bucket's own (now free) source area instead
+        unsigned long long* tmp = src + o;
+        for (int i = tid; i < n; i += SORT_THREADS) tmp[i] = ((unsigned long long)keys[o + i] << 32) | ids[o + i];
+        __syncthreads();
+        bitonic_sort<true>(tmp, n, tid, SORT_THREADS);        // global memory, block barriers: ranges of equal depths only
+        for (int i = tid; i < n; i += SORT_THREADS) {
+            const unsigned long long v = tmp[i];
+            ids[o + i] = (unsigned int)v;
+            keys[o + i] = (unsigned int)(v >> 32);
+        }
+        __syncthreads();
+    }
+    (void)n_large;
+}
+
 // BIG = false: buckets up to 256 entries in registers (32 registers per thread, 8 CTAs per SM) — the common case.
 // BIG = true: up to 512 (dense scenes, e.g. 1 M Gaussians at 1080p = ~360 per tile); chosen by the launcher from
 // the expected bucket size.  Either kernel sorts any bucket correctly (CTA-wide fallbacks beyond its register path).
@@ -342,15 +476,30 @@ __global__ void __launch_bounds__(SORT_THREADS, 4) sort_tiles_kernel(int T, Imag
                 bin.point_list[rb.x + i] = (unsigned int)v;
                 bin.depth_keys[rb.x + i] = (unsigned int)(v >> 32);
             }
-        } else {
-            bitonic_sort<true>(src, nb, tid, SORT_THREADS);  // in place in global memory; block barriers order it
-            for (int i = tid; i < nb; i += SORT_THREADS) {
-                const unsigned long long v = src[i];
-                bin.point_list[rb.x + i] = (unsigned int)v;
-                bin.depth_keys[rb.x + i] = (unsigned int)(v >> 32);
-            }
+        } else if (tid == 0) {
+            // thousands of instances on one tile: left to sort_heavy_kernel (its own launch, so that its registers and
+            // its run time are not this kernel's)
+            im.heavy_tiles[atomicAdd(&im.hdr->n_heavy, 1u)] = (unsigned int)tb;
         }
         __syncthreads();
+    }
+}
+
+// The tiles the sort kernel left: a small persistent grid walks the list (empty for ordinary frames: every CTA reads
+// one word and leaves), one CTA per heavy tile at a time.
+constexpr int HEAVY_CTAS = 148;
+__global__ void __launch_bounds__(SORT_THREADS) sort_heavy_kernel(ImageView im, BinView bin, unsigned long long cap)
+{
+    __shared__ unsigned long long s_items[SORT_SMEM_ITEMS];
+    pdl_prologue();
+    const unsigned int n_heavy = im.hdr->n_heavy;
+    for (unsigned int i = blockIdx.x; i < n_heavy; i += gridDim.x) {
+        const unsigned int t = im.heavy_tiles[i];
+        const uint2 rb = im.ranges[t];
+        if ((unsigned long long)rb.y > cap) continue;
+        __syncthreads();
+        sort_heavy_bucket<true>(bin.inst + rb.x, bin.point_list + rb.x, bin.depth_keys + rb.x, (int)(rb.y - rb.x), s_items,
+                                (int)threadIdx.x);
     }
 }
 
@@ -358,11 +507,14 @@ cudaError_t launch_sort_tiles(const DevSettings& s, ImageView im, BinView b, lon
 {
     const int T = s.gx * s.gy * s.n_views;
     if (T <= 0) return cudaSuccess;
-    count_launch();
+    count_launch(2);
     // expected bucket size from the instance capacity (1.25 x the last num_rendered seen for this shape)
     const bool dense = cap / T > 160;
-    return launch_pdl(dense ? sort_tiles_kernel<true> : sort_tiles_kernel<false>, dim3((T + SORT_WARPS - 1) / SORT_WARPS),
-                      dim3(SORT_THREADS), st, T, im, b, (unsigned long long)cap);
+    cudaError_t e = launch_pdl(dense ? sort_tiles_kernel<true> : sort_tiles_kernel<false>,
+                               dim3((T + SORT_WARPS - 1) / SORT_WARPS), dim3(SORT_THREADS), st, T, im, b,
+                               (unsigned long long)cap);
+    if (e != cudaSuccess) return e;
+    return launch_pdl(sort_heavy_kernel, dim3(HEAVY_CTAS), dim3(SORT_THREADS), st, im, b, (unsigned long long)cap);
 }
 
 // ---- export for the bit-exact stage tests --------------------------------------------------------

@@ -61,7 +61,8 @@ struct GeomView {
 struct ImageHeader {
     unsigned long long num_rendered;  // R = sum of tile counts
     unsigned int overflow;            // set by the scatter kernel when capacity was exceeded
-    unsigned int pad[29];
+    unsigned int n_heavy;             // tiles whose bucket the sort kernel left to sort_heavy_kernel (reset by the scan)
+    unsigned int pad[28];
 };
 struct ImageView {
     ImageHeader* hdr;
@@ -72,6 +73,7 @@ struct ImageView {
     unsigned int* tile_offset;  // [T] exclusive scan of tile_count
     unsigned int* tile_cursor;  // [T] scatter cursors
     uint2* ranges;              // [T] (start,end) — (0,0) for untouched tiles, as identifyTileRanges leaves them
+    unsigned int* heavy_tiles;  // [T] tiles with more instances than the sort kernel's shared-memory path holds
     float* final_T;             // [H*W]
     unsigned int* n_contrib;    // [H*W]
 };
@@ -124,6 +126,7 @@ inline ImageView image_view(void* buf, int W, int H, int n_views = 1)
     v.tile_offset = carve<unsigned int>(p, T);
     v.tile_cursor = carve<unsigned int>(p, T);
     v.ranges = carve<uint2>(p, T);
+    v.heavy_tiles = carve<unsigned int>(p, T);
     v.final_T = carve<float>(p, N);
     v.n_contrib = carve<unsigned int>(p, N);
     return v;
@@ -134,7 +137,8 @@ inline size_t image_bytes(int W, int H, int n_views = 1)
     size_t T = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE) * n_views;
     size_t N = (size_t)W * H * n_views;
     carve<ImageHeader>(p, 1); carve<unsigned int>(p, T); carve<unsigned long long>(p, T / 1024 + 2);
-    carve<unsigned int>(p, T); carve<unsigned int>(p, T); carve<uint2>(p, T); carve<float>(p, N); carve<unsigned int>(p, N);
+    carve<unsigned int>(p, T); carve<unsigned int>(p, T); carve<uint2>(p, T); carve<unsigned int>(p, T); carve<float>(p, N);
+    carve<unsigned int>(p, N);
     return (size_t)p + 256;
 }
 inline BinView bin_view(void* buf, long long cap)

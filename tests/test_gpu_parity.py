@@ -810,3 +810,36 @@ def test_rotations_at_any_float_alignment(cuda_device, P):
             assert (a - b).abs().max() <= ATOMIC_RTOL * b.abs().max()
         f = rast.visible_filter(means3D=p["means3D"], scales=p["scales"], rotations=p["rotations"], cov3D_precomp=None)
         assert torch.equal(f, r0)
+
+
+def _skewed_scene(P_hot=50000, P_rest=20000, seed=77, ties=False):
+    """One hot tile: P_hot small Gaussians whose centres fall into a single 16x16 tile of a 256x256 image (about two
+    thirds survive the slab cull), the rest spread as usual."""
+    scene = make_scene(P=P_hot + P_rest, W=256, H=256, F=256, seed=seed)
+    gs, fr = scene["gaussians"], scene["frame"]
+    g = torch.Generator().manual_seed(seed)
+    # tile (7, 9): pixels x in [112, 128), y in [144, 160); pix = (p - min) * scale - 0.5
+    gs["means3D"][:P_hot, 0] = fr.x_min + (112.5 + 15.0 * torch.rand(P_hot, generator=g) + 0.5) / fr.scale
+    gs["means3D"][:P_hot, 1] = fr.y_min + (144.5 + 15.0 * torch.rand(P_hot, generator=g) + 0.5) / fr.scale
+    gs["scales"][:P_hot] = 0.25 / fr.scale                       # radius 2-3 px: the instances stay in the tile and its neighbours
+    gs["opacities"][:P_hot] = 0.01 + 0.02 * torch.rand(P_hot, 1, generator=g)
+    if ties:
+        gs["means3D"][:P_hot:3, 2] = gs["means3D"][0, 2]         # a third of them at exactly one depth
+    return scene
+
+
+@pytest.mark.parametrize("ties", [False, True])
+def test_one_hot_tile_of_tens_of_thousands_is_sorted_exactly(cuda_device, ties):
+    """> 30 000 instances on ONE tile (the sort kernel's shared-memory path holds 2 048) go through
+    the range split of sort_heavy_kernel; with `ties`, ten thousand of them share one depth (a range no warp can hold:
+    the last-resort network).  Sorted keys, point list and tile ranges stay bit-exact against the oracle."""
+    from gsvc_b200.rasterizer import RasterState
+    scene = _skewed_scene(ties=ties)
+    fo = _oracle_forward(scene)
+    lens = fo["bin"]["ranges"][:, 1].astype(np.int64) - fo["bin"]["ranges"][:, 0]
+    assert lens.max() > 30000
+    g = _to_dev(scene["gaussians"], cuda_device)
+    state = RasterState(product_settings(scene, cuda_device), g["means3D"], g["opacities"],
+                        colors_precomp=g["colors_precomp"], scales=g["scales"], rotations=g["rotations"])
+    _check_stages(scene, fo, state)
+    _check_forward(fo, state.color, max_fragile=2e-2)       # tens of thousands of contributors per pixel at alpha ~ 1/255
