@@ -21,9 +21,14 @@ replicated on the devices but the HOST state is sharded by rows — rank r uploa
 [r·P/G, (r+1)·P/G) of each parameter segment and the devices all-gather the rest over NVLink; the
 gradients are reduce-scattered and rank r reads back only its rows.  PCIe then carries 1/G of the bytes
 per rank (the host link, not the GPUs, is what G replicated uploads would saturate).
-The collectives run beside the blend kernels, which keep every SM full: start the process group with
-TORCH_NCCL_HIGH_PRIORITY=1 (bench.py and examples/fit_window.py do) so that NCCL's CTAs are scheduled ahead of the
-blend grid's pending ones instead of in its tail.
+Both exchanges are taken OFF THE SMs (`peer_copies=True`, the default when the ranks can map each other's memory):
+the upload buffer and the gradient buffer of every slot live in symmetric memory (torch.distributed._symmetric_memory:
+CUDA virtual-memory allocations every rank maps), each rank PULLS the other ranks' rows with plain device-to-device
+copies — copy engines over NVLink, no CTA anywhere — between two signal-pad barriers, and sums the N row blocks it
+pulled with one small kernel.  The blend kernels keep every SM full, so NCCL's all-gather / reduce-scatter kernels
+(the fallback, `peer_copies=False` or when the mapping is refused) were only scheduled in the tails of the blend
+grids while the peers' CTAs spun: 30-50 us exposed per step at 2-4 GPUs even on high-priority streams
+(TORCH_NCCL_HIGH_PRIORITY=1, which bench.py and examples/fit_window.py still set for the fallback).
 """
 from __future__ import annotations
 
@@ -38,7 +43,8 @@ from .views import ViewBatch, rasterize_views
 
 
 class HostStepPipeline:
-    def __init__(self, P: int, device, slots: int = 2, use_graphs: bool = True, sharded: bool = False):
+    def __init__(self, P: int, device, slots: int = 2, use_graphs: bool = True, sharded: bool = False,
+                 peer_copies: bool = True):
         """`use_graphs`: after one eager step per slot (which sizes the binning buffer), the slot's forward +
         backward (8 kernels) is captured in a CUDA graph and replayed, so a step costs the host one graph launch
         instead of ~10 launches and the autograd bookkeeping; `capacity_ok()` reports whether the instance capacity
@@ -53,7 +59,10 @@ class HostStepPipeline:
         self.dev_flat = [torch.empty(GRAD_WIDTH * P, **f32) for _ in range(slots)]
         self.dev_grads = [torch.empty((P, GRAD_WIDTH), **f32) for _ in range(slots)]
         self.host_grads = [torch.empty((P, GRAD_WIDTH), dtype=torch.float32).pin_memory() for _ in range(slots)]
-        self.s_h2d, self.s_d2h = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
+        # high priority: the few tiny kernels these streams launch between copies (signal-pad barriers, the sum of the
+        # pulled gradient blocks) must not queue behind the 16 000-CTA blend grids of the step that is running
+        self.s_h2d = torch.cuda.Stream(self.device, priority=-1)
+        self.s_d2h = torch.cuda.Stream(self.device, priority=-1)
         self.in_ready = [None] * slots       # H2D of the slot finished
         self.compute_done = [None] * slots   # forward+backward that read the slot's parameters finished
         self.d2h_done = [None] * slots       # the slot's gradients are in host memory
@@ -73,11 +82,44 @@ class HostStepPipeline:
                     raise RasterizerError(f"sharded host state needs P ({P}) divisible by the world size ({self.world})")
         self.rows = P // self.world
         self.r0, self.r1 = self.rank * self.rows, (self.rank + 1) * self.rows
+        self.peer = None
         if self.world > 1:
             self.dev_shard = [[torch.empty(self.rows * w, **f32) for _, w in GRAD_LAYOUT] for _ in range(slots)]
             self.dev_gshard = [torch.empty((self.rows, GRAD_WIDTH), **f32) for _ in range(slots)]
+            if peer_copies:
+                self._setup_peer_copies(f32)
         self.h2d_bytes = GRAD_WIDTH * self.rows * 4     # per rank
         self.d2h_bytes = GRAD_WIDTH * self.rows * 4
+
+    def _setup_peer_copies(self, f32) -> None:
+        """Symmetric upload / gradient buffers + their handles; on any failure the NCCL path stays in place."""
+        import torch.distributed as dist
+        try:
+            import torch.distributed._symmetric_memory as symm
+            group = dist.group.WORLD
+            P, rows, slots = self.P, self.rows, self.slots
+            shard = [symm.empty(rows * GRAD_WIDTH, **f32) for _ in range(slots)]
+            grads = [symm.empty(P * GRAD_WIDTH, **f32) for _ in range(slots)]
+            h_shard = [symm.rendezvous(t, group) for t in shard]
+            h_grads = [symm.rendezvous(t, group) for t in grads]
+            self.peer = dict(shard=shard, grads=grads, h_shard=h_shard, h_grads=h_grads,
+                             pulled=[torch.empty((self.world, rows, GRAD_WIDTH), **f32) for _ in range(slots)],
+                             staged=[torch.empty((self.world, rows * GRAD_WIDTH), **f32) for _ in range(slots)])
+            # every rank's buffers as this rank sees them (peer-mapped tensors, made once)
+            self.peer["shard_of"] = [[h.get_buffer(q, (rows * GRAD_WIDTH,), torch.float32) for q in range(self.world)]
+                                     for h in h_shard]
+            self.peer["my_rows_of"] = [[h.get_buffer(q, (rows, GRAD_WIDTH), torch.float32, self.r0 * GRAD_WIDTH)
+                                        for q in range(self.world)] for h in h_grads]
+            # the backward writes its packed gradients straight into the symmetric buffer
+            self.dev_grads = [g.view(P, GRAD_WIDTH) for g in grads]
+            # segment offsets inside a rank's shard: [means3D rows | colours rows | opacity rows | scales rows | rotation rows]
+            self.shard_off, o = [], 0
+            for _, w in GRAD_LAYOUT:
+                self.shard_off.append(o)
+                o += rows * w
+        except Exception as e:       # no peer mapping on this box / build: NCCL all-gather + reduce-scatter
+            self.peer = None
+            self.peer_error = f"{type(e).__name__}: {e}"
 
     def views(self, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
         out, o, P = {}, 0, self.P
@@ -99,6 +141,32 @@ class HostStepPipeline:
                 self.s_h2d.wait_event(self.compute_done[b])   # the step that read this slot has finished
             if self.world == 1:
                 self.dev_flat[b].copy_(host_flat.view(-1), non_blocking=True)
+            elif self.peer is not None:
+                # this rank's rows of every segment over PCIe into ITS symmetric shard; then, between two barriers of
+                # the copy stream, every rank pulls every rank's rows into place with device-to-device copies (copy
+                # engines over NVLink).  The shard of a slot is rewritten two prefetches later, after the barrier of
+                # the prefetch in between — which no rank passes before it has finished these pulls.
+                pr, hf, off = self.peer, host_flat.view(-1), 0
+                mine = pr["shard"][b]
+                for i, (_, w) in enumerate(GRAD_LAYOUT):
+                    mine[self.shard_off[i]:self.shard_off[i] + self.rows * w].copy_(
+                        hf[off + self.r0 * w:off + self.r1 * w], non_blocking=True)
+                    off += w * self.P
+                h = pr["h_shard"][b]
+                h.barrier(channel=0)
+                # one contiguous pull per rank (copy engine), then five strided device copies put the segments in
+                # place: N + 5 calls per step instead of 5 N (the host loop, not the link, is what 40 small copies per
+                # step would saturate at 8 ranks)
+                staged = pr["staged"][b]
+                for step_ in range(self.world):
+                    q = (self.rank - step_) % self.world
+                    staged[q].copy_(pr["shard_of"][b][q], non_blocking=True)
+                off = 0
+                for i, (_, w) in enumerate(GRAD_LAYOUT):
+                    n = self.rows * w
+                    self.dev_flat[b][off:off + w * self.P].view(self.world, n).copy_(
+                        staged[:, self.shard_off[i]:self.shard_off[i] + n], non_blocking=True)
+                    off += w * self.P
             else:
                 # this rank's rows of every segment over PCIe, everybody else's over NVLink
                 import torch.distributed as dist
@@ -152,7 +220,9 @@ class HostStepPipeline:
             self.last_num_rendered = self._compute(b, rast, dL)
             self.eager_seen[b] = key
         work = None
-        if self.world > 1:
+        if self.world > 1 and self.peer is not None:
+            pass        # the gradients are exchanged on the copy-out stream below, without a collective kernel
+        elif self.world > 1:
             # sum over ranks, each rank keeps (and reads back) its own rows
             import torch.distributed as dist
             work = dist.reduce_scatter_tensor(self.dev_gshard[b], self.dev_grads[b], op=dist.ReduceOp.SUM,
@@ -164,6 +234,19 @@ class HostStepPipeline:
             self.s_d2h.wait_event(self.compute_done[b])
             if work is not None:
                 work.wait()                                   # stream-level: the copy stream waits for the collective
+            if self.world > 1 and self.peer is not None:
+                # reduce-scatter without a collective kernel: barrier (every rank's backward of this step has landed in
+                # its symmetric gradient buffer), pull this rank's rows of every rank's buffer with copy engines, sum
+                # the N blocks with one small kernel, barrier again (nobody overwrites a buffer that is still being
+                # read: the next compute on this slot waits for d2h_done, recorded after it)
+                pr = self.peer
+                h = pr["h_grads"][b]
+                h.barrier(channel=0)
+                for step_ in range(self.world):
+                    q = (self.rank - step_) % self.world
+                    pr["pulled"][b][q].copy_(pr["my_rows_of"][b][q], non_blocking=True)
+                torch.sum(pr["pulled"][b], dim=0, out=self.dev_gshard[b])
+                h.barrier(channel=1)
             src = self.dev_gshard[b] if self.world > 1 else self.dev_grads[b]
             self.host_grads[b][self.r0:self.r1].copy_(src, non_blocking=True)
             self.d2h_done[b] = self.s_d2h.record_event()

@@ -51,5 +51,7 @@ for i, o in enumerate(outs):
 assert pipe.graphs[0] is not None and pipe.capacity_ok(toasts[rank])
 dist.barrier()
 if rank == 0:
-    print(f"sharded pipeline ok on {world} ranks: rows per rank {pipe.rows}, max rel err {err:.2e}")
+    how = "peer copies over symmetric memory (no collective kernels)" if pipe.peer is not None else \
+        f"NCCL all-gather / reduce-scatter (peer mapping unavailable: {getattr(pipe, 'peer_error', 'disabled')})"
+    print(f"sharded pipeline ok on {world} ranks: rows per rank {pipe.rows}, max rel err {err:.2e}; exchange: {how}")
 dist.destroy_process_group()

@@ -1,10 +1,13 @@
 """Extract per-kernel DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum, per launch) and a few
 other per-launch figures from an `ncu --set full` report into a small JSON that bench.py reads for
 roofline.traffic.  Usage: python scripts/ncu_traffic.py gpurun_out/prof.ncu-rep profiles/traffic.json"""
-import csv, json, subprocess, sys
+import csv, json, os, subprocess, sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gsvc_b200.build import _digest
 
 UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-STAGE = {"preprocess_kernel<0>": "preprocess", "preprocess_kernel<1>": "visible_filter", "tile_scan_kernel": "tile_scan",
+STAGE = {"sort_heavy_kernel": "sort_heavy", "preprocess_kernel<0>": "preprocess", "preprocess_kernel<1>": "visible_filter", "tile_scan_kernel": "tile_scan",
          "scatter_kernel": "scatter", "sort_tiles_kernel": "sort_tiles", "render_forward_kernel": "render_forward",
          "render_backward_kernel": "render_backward", "preprocess_backward_kernel": "preprocess_backward"}
 raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -30,6 +33,9 @@ for rec in out.values():
     for k in list(rec):
         rec[k] = rec[k] / n
     rec["launches_averaged"] = n
-json.dump({"source": sys.argv[1], "note": "per-launch means from one ncu --set full capture (cold cache, serialised)", "kernels": out},
+# the digest of the kernel sources the capture was made from: bench.py refuses a profile whose digest is not the one
+# of the library it is timing (a stale profile would silently quote the traffic of older kernels)
+json.dump({"source": sys.argv[1], "csrc_digest": _digest(),
+           "note": "per-launch means from one ncu --set full capture (cold cache, serialised)", "kernels": out},
           open(sys.argv[2], "w"), indent=1)
 print(json.dumps(out, indent=1))
