@@ -44,7 +44,7 @@ from .views import ViewBatch, rasterize_views
 
 class HostStepPipeline:
     def __init__(self, P: int, device, slots: int = 2, use_graphs: bool = True, sharded: bool = False,
-                 peer_copies: bool = True):
+                 peer_copies: Optional[bool] = None):
         """`use_graphs`: after one eager step per slot (which sizes the binning buffer), the slot's forward +
         backward (8 kernels) is captured in a CUDA graph and replayed, so a step costs the host one graph launch
         instead of ~10 launches and the autograd bookkeeping; `capacity_ok()` reports whether the instance capacity
@@ -86,7 +86,11 @@ class HostStepPipeline:
         if self.world > 1:
             self.dev_shard = [[torch.empty(self.rows * w, **f32) for _, w in GRAD_LAYOUT] for _ in range(slots)]
             self.dev_gshard = [torch.empty((self.rows, GRAD_WIDTH), **f32) for _ in range(slots)]
-            if peer_copies:
+            # measured on one 8xB200 box (scripts/probe_hostpipe.py, 100 steps, ms per e2e step, peer / NCCL):
+            #   2 GPUs 0.469 / 0.469, 4 GPUs 0.455 / 0.473, 8 GPUs 0.447 / 0.456  (compute alone: 0.449)
+            # the three barriers of the peer path make its start-up and drain longer, which a 20-step window at 2 GPUs
+            # sees: the default is the peer path from 4 ranks up
+            if peer_copies if peer_copies is not None else self.world >= 4:
                 self._setup_peer_copies(f32)
         self.h2d_bytes = GRAD_WIDTH * self.rows * 4     # per rank
         self.d2h_bytes = GRAD_WIDTH * self.rows * 4
