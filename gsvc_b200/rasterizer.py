@@ -176,7 +176,27 @@ class _NativeSettings:
 
 
 def _stream_ptr(device) -> int:
-    return torch.cuda.current_stream(device).cuda_stream
+    # the raw handle of the current stream without building a torch.cuda.Stream object (6 us per call otherwise,
+    # twice per forward + backward of a 250 us step)
+    return torch._C._cuda_getCurrentRawStream(device.index if device.index is not None else torch.cuda.current_device())
+
+
+class _on_device:
+    """`with torch.cuda.device(device)` only when `device` is not already current (the context manager costs ~5 us
+    per use; the reference runs one device per process, utils/general_utils.py:153)."""
+    __slots__ = ("ctx",)
+
+    def __init__(self, device):
+        self.ctx = None if device.index is None or device.index == torch.cuda.current_device() else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            return self.ctx.__exit__(*exc)
+        return False
 
 
 def _bytes(n: int, device) -> torch.Tensor:
@@ -257,7 +277,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         _require_cuda(means3D, "means3D")
         device = means3D.device
         rs = raster_settings
-        with torch.cuda.device(device):
+        with _on_device(device):
             ns = _NativeSettings(rs, device)
             P = means3D.shape[0]
             means3D_c = _dev_f32(means3D, device, "means3D")
@@ -353,7 +373,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         n_geom, n_img, n_acc = ctx.offsets
         base = state.data_ptr()
         bin_p = binning.data_ptr() if binning is not None else base + n_geom + n_img + n_acc
-        with torch.cuda.device(device):
+        with _on_device(device):
             ns = ctx.ns
             g_out = _dev_f32(grad_out_color, device, "grad_out_color")
             # frame-sharded training: write (means3D, colours, opacity, scales, rotation) gradients straight into
