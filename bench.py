@@ -869,16 +869,16 @@ def run_product_arm(args, rank, local_rank, world):
         peak, peak_src = load_peaks()
         alg = algorithmic_bytes(P, V, num_rendered, N, T, NV)
         # per-launch DRAM traffic and issue utilisation of each kernel from the committed ncu --set full capture of
-        # this same command (profiles/r1_traffic.json, made by scripts/ncu_traffic.py); None if it is absent
-        prof, prof_note = {}, "profiles/r3_traffic.json absent"
+        # this same command (profiles/traffic.json, made by scripts/ncu_traffic.py); None if it is absent
+        prof, prof_note = {}, "profiles/traffic.json absent"
         try:
             from gsvc_b200.build import _digest
-            with open(os.path.join(ROOT, "profiles", "r3_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
                 pj = json.load(f)
             if pj.get("csrc_digest") == _digest():
-                prof, prof_note = pj["kernels"], "profiles/r3_traffic.json (ncu --set full of scripts/prof_step.py; digest of the kernel sources matches)"
+                prof, prof_note = pj["kernels"], "profiles/traffic.json (ncu --set full of scripts/prof_step.py; digest of the kernel sources matches)"
             else:
-                prof_note = "profiles/r3_traffic.json REFUSED: captured from other kernel sources than the library being timed"
+                prof_note = "profiles/traffic.json REFUSED: captured from other kernel sources than the library being timed"
         except Exception:
             pass
         dom = max(stage_avg, key=stage_avg.get)
@@ -955,7 +955,7 @@ def run_product_arm(args, rank, local_rank, world):
             # what actually bounds the dominant kernel: issued warp-instructions per second against the SMs' issue rate
             # (4 schedulers x 1 instruction per clock per SM); instruction count per launch from the committed ncu capture
             "issue_roofline": (lambda inst: None if not inst else {
-                "kernel": dom, "warp_instructions_per_launch": inst, "source": "profiles/r3_traffic.json (ncu smsp__inst_executed.sum)",
+                "kernel": dom, "warp_instructions_per_launch": inst, "source": "profiles/traffic.json (ncu smsp__inst_executed.sum)",
                 "achieved_Ginstr_per_s": inst / (stage_avg[dom] * 1e-3) / 1e9,
                 "peak_Ginstr_per_s": 148 * 4 * (clk.get("sm_mhz") or 1965.0) * 1e6 / 1e9,
                 "frac": inst / (stage_avg[dom] * 1e-3) / (148 * 4 * (clk.get("sm_mhz") or 1965.0) * 1e6)})(
