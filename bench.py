@@ -599,11 +599,25 @@ def run_product_arm(args, rank, local_rank, world):
         mine = [f for i, f in enumerate(frames3) if i % world == rank]
         batch3 = ViewBatch.toasts([(settings_for(geom, f, device), settings_for(geom, f, device, back=True)) for f in mine])
         dL3 = torch.randn((len(mine), 3, H, W), generator=torch.Generator().manual_seed(300 + rank)).to(device)
-        buf3 = torch.empty((c3["P"], 14), dtype=torch.float32, device=device)
-        # (this all-reduce is exposed by construction — nothing overlaps it — so NCCL, which drives NVLink from SMs at
-        # full rate, is the right tool: 118 us against 157 us for the copy-engine PeerAllReduce at 4 GPUs.  The
-        # peer version is for the overlapped all-reduce of the training step above.)
-        ar3 = None
+        # This all-reduce is exposed by construction — the window ends with it, nothing overlaps it — so it should move the
+        # 28 MB as fast as the links allow: gsvc_b200.sharding.SwitchAllReduce, ONE kernel of this library per rank
+        # (csrc/collective.cu): multimem.ld_reduce / multimem.st through the NVSwitch from 4 ranks up, peer loads and
+        # stores for 2 (measured at 28 MB, 2 / 8 GPUs: 61 / 86 us against 76 / 143 us for NCCL and 110 / 206 us for the
+        # copy-engine PeerAllReduce, which is built for the OVERLAPPED all-reduce of the training step above).
+        ar3, ar3_note = None, "NCCL all_reduce"
+        buf3 = None
+        if world > 1 and os.environ.get("GSVC_BENCH_C3_NCCL", "0") != "1":
+            try:
+                from gsvc_b200.sharding import SwitchAllReduce
+                ar3 = SwitchAllReduce(c3["P"] * 14, device)
+                buf3 = ar3.buffer().view(c3["P"], 14)
+                ar3_note = (f"sharding.SwitchAllReduce ({ar3.mode}: " +
+                            ("multimem.ld_reduce / multimem.st through the NVSwitch" if ar3.mode == "multicast"
+                             else "peer loads + stores over NVLink") + f", one kernel, {ar3.n_ctas} CTAs)")
+            except Exception as e:   # no symmetric memory on this box: NCCL
+                ar3, ar3_note = None, f"NCCL all_reduce (switch path unavailable: {type(e).__name__}: {e})"
+        if buf3 is None:
+            buf3 = torch.empty((c3["P"], 14), dtype=torch.float32, device=device)
         for _ in range(2):
             rasterize_views(batch3, means3D=g3["means3D"], opacities=g3["opacities"], colors_precomp=g3["colors_precomp"],
                             scales=g3["scales"], rotations=g3["rotations"])
@@ -621,7 +635,7 @@ def run_product_arm(args, rank, local_rank, world):
         def c3_step():
             c3_compute()
             if ar3 is not None:
-                ar3.start(0).wait()                              # the step ends when the reduced buffer is in place
+                ar3.run()                                        # on the compute stream: the step ends when it has
             elif world > 1:
                 dist.all_reduce(buf3, op=dist.ReduceOp.SUM)      # on the compute stream: the step ends when it has
 
@@ -632,13 +646,12 @@ def run_product_arm(args, rank, local_rank, world):
         w_ms = min(timed(c3_step, n3)[0] for _ in range(REPEATS))
         c_ms = min(timed(c3_compute, n3)[0] for _ in range(REPEATS)) if world > 1 else w_ms
         config3 = {"workload": "500k Gaussians, 8-frame TSW window (16 views) of a 600-frame 1080p video, frames dealt "
-                               "round-robin to the ranks, NCCL fp32 sum all-reduce of [P,14] per window (BASELINE.json configs[2])",
+                               "round-robin to the ranks, fp32 sum all-reduce of [P,14] per window (BASELINE.json configs[2])",
                    "P": c3["P"], "scaling": "strong", "n_gpus": world, "views_per_rank": 2 * len(mine),
                    "window_ms": w_ms / n3, "windows_per_s": 1000.0 * n3 / w_ms, "view_iters_per_s": 16000.0 * n3 / w_ms,
                    "compute_only_window_ms": c_ms / n3, "exposed_collective_us": 1000.0 * (w_ms - c_ms) / n3,
                    "allreduce_bytes": c3["P"] * 14 * 4 if world > 1 else 0,
-                   "allreduce": None if world == 1 else ("sharding.PeerAllReduce (copy-engine pulls, no collective kernel)"
-                                                         if ar3 is not None else "NCCL all_reduce"),
+                   "allreduce": None if world == 1 else ar3_note,
                    "timing": "max over ranks; the all-reduce is issued on the compute stream after the backward and the "
                              "step's end event follows it"}
         del g3, step3, buf3, dL3, ar3

@@ -10,7 +10,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libgsvc_rast.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # gsvc_rast_status
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_OVERFLOW = 0, -1, -2, -3, -4
@@ -74,6 +74,7 @@ SIGNATURES = {
     "gsvc_rast_export_geom": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsvc_rast_export_image": (C.c_int, [_SP, _i32, _vp, _vp, _vp, _vp]),
     "gsvc_rast_densify_stats": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "gsvc_rast_switch_allreduce": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _i32, _vp]),
     "gsvc_rast_count_overflows": (C.c_int, [_i32]),
     "gsvc_rast_overflow_events": (_i64, [_i32, _vp]),
     "gsvc_rast_launch_count": (_i64, [_i32]),

@@ -178,6 +178,24 @@ int gsvc_rast_densify_stats(int32_t n_views, int32_t P, const float* dL_dmeans2D
     return GSVC_RAST_OK;
 }
 
+int gsvc_rast_switch_allreduce(void* multicast, void* buffers, void* signal_pads, void* state, int32_t rank,
+                               int32_t world, int64_t numel, int32_t n_ctas, void* stream_)
+{
+    if (world < 1 || rank < 0 || rank >= world) return fail(GSVC_RAST_ERR_INVALID, "rank %d outside world %d", rank, world);
+    if (numel < 0 || (numel & 3)) return fail(GSVC_RAST_ERR_INVALID, "numel must be a non-negative multiple of 4");
+    if (n_ctas < 1 || n_ctas > 592) return fail(GSVC_RAST_ERR_INVALID, "n_ctas must be in 1..592 (co-resident CTAs)");
+    if (!signal_pads || !state) return fail(GSVC_RAST_ERR_INVALID, "signal_pads / state must be non-NULL");
+    if (!multicast && !buffers) return fail(GSVC_RAST_ERR_INVALID, "one of multicast / buffers must be non-NULL");
+    if (!multicast && world != 1 && world != 2 && world != 4 && world != 8)
+        return fail(GSVC_RAST_ERR_INVALID, "the peer-load path is built for 1, 2, 4 or 8 ranks, got %d", world);
+    if (reinterpret_cast<uintptr_t>(multicast) & 15) return fail(GSVC_RAST_ERR_INVALID, "multicast address must be 16-byte aligned");
+    cudaError_t e = launch_switch_allreduce(static_cast<float*>(multicast), static_cast<void* const*>(buffers),
+                                            static_cast<unsigned int* const*>(signal_pads), static_cast<unsigned int*>(state),
+                                            rank, world, (long long)numel, n_ctas, static_cast<cudaStream_t>(stream_));
+    if (e != cudaSuccess) return fail(GSVC_RAST_ERR_CUDA, "switch_allreduce: %s", cudaGetErrorString(e));
+    return GSVC_RAST_OK;
+}
+
 int gsvc_rast_count_overflows(int32_t enable)
 {
     g_count_overflows = enable != 0;

@@ -386,6 +386,8 @@ cudaError_t read_overflow_events(unsigned int* host_value, bool reset, cudaStrea
 cudaError_t launch_densify_stats(int n_views, int P, const float* dm2d, const int32_t* radii, float* stats,
                                  long long stride, bool accumulate, cudaStream_t st);
 
+cudaError_t launch_switch_allreduce(float* multicast, void* const* buffers, unsigned int* const* pads, unsigned int* state,
+                                    int rank, int world, long long numel, int n_ctas, cudaStream_t st);
 void count_launch(int n = 1);
 
 }  // namespace gsvc

@@ -139,6 +139,60 @@ class PeerAllReduce:
         return PeerAllReduce._Done(ev, self.device)
 
 
+class SwitchAllReduce:
+    """Sum all-reduce of the step's gradient buffer THROUGH THE NVSWITCH, one kernel of this library per rank
+    (csrc/collective.cu, `gsvc_rast_switch_allreduce`): rank r load-reduces its slice of the buffer through the
+    multicast mapping (the switch sums the ranks' copies) and stores the sums back through it (the switch writes
+    every rank).  For an all-reduce nothing overlaps — the window of BASELINE config 3 ends with it — this is the
+    fastest path on an NVSwitch box: each GPU's links carry the buffer once out and once in.  All ranks end up with
+    bit-identical sums.
+
+        ar = SwitchAllReduce(P * 14, device)          # raises if the ranks cannot map a multicast object
+        buf = ar.buffer().view(P, 14)                  # the backward writes here (packed_backward / GraphedStep)
+        ar.run()                                       # on the current stream, after the backward; every rank calls it
+    """
+
+    def __init__(self, numel: int, device, group=None, n_ctas: int = 0, mode: str = "auto"):
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        group = dist.group.WORLD if group is None else group
+        self.device = torch.device(device)
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if numel % 4:
+            raise ValueError(f"buffer of {numel} floats is not a multiple of 4 (16-byte vector accesses)")
+        self.numel = numel
+        self.t = symm.empty(numel, dtype=torch.float32, device=self.device)
+        self.h = symm.rendezvous(self.t, group)
+        mc = int(getattr(self.h, "multicast_ptr", 0) or 0)
+        # two ranks: a peer load of the other copy beats sending one's own copy through the switch and back
+        if mode == "auto":
+            mode = "multicast" if (mc and self.world > 2) else "peer"
+        if mode == "multicast" and not mc:
+            raise _lib.RasterizerError("the ranks of this group have no multicast mapping (no NVSwitch / fabric): "
+                                       "use mode='peer', allreduce_grads (NCCL) or PeerAllReduce")
+        if mode == "peer" and self.world not in (1, 2, 4, 8):
+            raise _lib.RasterizerError(f"the peer-load path is built for 1, 2, 4 or 8 ranks, got {self.world}")
+        self.mode = mode
+        self.mc = mc if mode == "multicast" else 0
+        self.bufs = int(self.h.buffer_ptrs_dev)
+        if self.world * 4 > int(symm.get_signal_pad_size()):
+            raise ValueError(f"{self.world} ranks do not fit the signal pad")
+        self.n_ctas = int(n_ctas) if n_ctas else 64
+        self.pads = int(self.h.signal_pad_ptrs_dev)
+        self.state = torch.zeros(2, dtype=torch.int32, device=self.device)   # where the CTAs of a launch meet
+        self._lib = _lib
+
+    def buffer(self) -> torch.Tensor:
+        return self.t
+
+    def run(self):
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        self._lib.check(self._lib.lib().gsvc_rast_switch_allreduce(self.mc or None, self.bufs, self.pads, self.state.data_ptr(), self.rank,
+                                                                   self.world, self.numel, self.n_ctas, st),
+                        "gsvc_rast_switch_allreduce")
+        return self.t
+
+
 STATS_WIDTH = 2   # per Gaussian: (sum over views of |dL/dmeans2D[:2]| where drawn, number of views it was drawn in)
 
 

@@ -35,7 +35,7 @@ extern "C" {
 #define GSVC_RAST_API
 #endif
 
-#define GSVC_RAST_ABI_VERSION 4
+#define GSVC_RAST_ABI_VERSION 5
 #define GSVC_RAST_TILE 16 /* tile edge in pixels; tile ids are row-major over ceil(W/16) x ceil(H/16) */
 #define GSVC_RAST_MAX_VIEWS 16 /* views per batched call (gsvc_rast_*_views) */
 
@@ -234,6 +234,33 @@ GSVC_RAST_API int gsvc_rast_backward_views(const gsvc_rast_settings *st, int32_t
  */
 GSVC_RAST_API int gsvc_rast_densify_stats(int32_t n_views, int32_t P, const float *dL_dmeans2D, const int32_t *radii,
                             float *stats, int64_t stride, int32_t accumulate, void *stream);
+
+/*
+ * Sum all-reduce of a rank-sharded step's fp32 buffer (the packed [P,14] parameter gradients, optionally followed by
+ * the [P,2] densification statistic) through the NVSwitch — the one exchange step of the frame-sharded training
+ * loop (what DistributedDataParallel's gradient all-reduce would be for /root/reference/pipeline/train.py:462; the
+ * reference itself trains on one GPU).  ONE kernel launch per rank, no NCCL.  Rank r owns the r-th slice of the
+ * buffer: it obtains the slice's sum over the ranks and writes it into every rank's buffer, either
+ *   - through the MULTICAST mapping of the buffers (multicast != NULL): multimem.ld_reduce / multimem.st — the
+ *     switch adds and replicates, each GPU's links carry the buffer once out and once in; or
+ *   - with peer loads and stores over NVLink (multicast == NULL, buffers != NULL; 2, 4 or 8 ranks).
+ *   multicast     the buffer's address in the multicast mapping of a symmetric allocation every rank of the node
+ *                 has made with the same size (e.g. torch.distributed._symmetric_memory: handle.multicast_ptr);
+ *                 16-byte aligned; NULL selects the peer path
+ *   buffers       device array of `world` pointers: buffers[q] = rank q's buffer as mapped into THIS process
+ *                 (handle.buffer_ptrs_dev); may be NULL when multicast is given
+ *   signal_pads   device array of `world` pointers: signal_pads[q] = rank q's zero-initialised signal pad as mapped
+ *                 into THIS process (handle.signal_pad_ptrs_dev), each at least world * 4 bytes
+ *   state         two zeroed 32-bit words of this rank's OWN device memory, private to this buffer (the CTAs of the
+ *                 launch meet there); zero again when the kernel has completed
+ *   numel         floats in the buffer, a multiple of 4
+ *   n_ctas        CTAs of the launch (all of them must be co-resident: <= 4 * SM count)
+ * On return of the kernel every rank's buffer holds the sum over the ranks, bit-identical on all of them (one adder
+ * per element).  Every rank must make the call (it is a collective); the pad words are back to zero afterwards, so
+ * the launch can be captured in a CUDA graph and replayed.
+ */
+GSVC_RAST_API int gsvc_rast_switch_allreduce(void *multicast, void *buffers, void *signal_pads, void *state, int32_t rank,
+                               int32_t world, int64_t numel, int32_t n_ctas, void *stream);
 
 /*
  * Stage exports for bit-exact parity tests (not used on the hot path).

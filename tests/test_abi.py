@@ -44,7 +44,7 @@ def test_no_torch_or_python_dependency_in_the_abi():
 
 
 def test_abi_version_and_sizes(lib):
-    assert lib.gsvc_rast_abi_version() == _lib.ABI_VERSION == 4
+    assert lib.gsvc_rast_abi_version() == _lib.ABI_VERSION == 5
     g1, g2 = lib.gsvc_rast_geom_bytes(1000, 0), lib.gsvc_rast_geom_bytes(2000, 0)
     assert 56 * 1000 <= g1 < g2 <= 2 * g1 + 4096
     assert lib.gsvc_rast_geom_bytes(1000, 16) > g1                       # SH clamp flags
