@@ -28,6 +28,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=250)
     ap.add_argument("--interval", type=int, default=5)
+    ap.add_argument("--switch", action="store_true", help="sum gradients + statistics with sharding.SwitchAllReduce")
     ap.add_argument("--width", type=int, default=320)
     ap.add_argument("--height", type=int, default=192)
     ap.add_argument("--frames", type=int, default=64)
@@ -75,8 +76,13 @@ def main():
     # the K Gaussians of an anchor start spread over its neighbourhood (the reference starts them at the anchor and
     # lets the optimizer push them out over thousands of iterations; growth needs Gaussians that left their voxel)
     model.p["offset"] = (1.5 * torch.randn(args.anchors, 4, 3, generator=g)).to(dev)
+    collective = None
+    if args.switch and world > 1:
+        # the iteration's one exchange through the library's own kernel; room for the anchors to grow 4x
+        from gsvc_b200.sharding import SwitchAllReduce
+        collective = SwitchAllReduce(4 * sum(n for _, n in model.flat_layout()) // 4 * 4, dev)
     trainer = DPTrainer(model, settings, target, rank=rank, world=world, seed=99, update_interval=args.interval,
-                        grad_threshold=2e-5, min_opacity=0.02)
+                        grad_threshold=2e-5, min_opacity=0.02, collective=collective)
     frame_rng = torch.Generator().manual_seed(17)                   # the same frame draw on every rank (train.py:337)
     first = last = None
     agree, rounds, added, pruned = True, 0, 0, 0
@@ -102,7 +108,9 @@ def main():
     if rank == 0:
         print(json.dumps({"world": world, "iterations": args.iters, "densification_rounds": rounds, "anchors_start": args.anchors,
                           "anchors_end": model.n_anchors, "added": added, "pruned": pruned,
-                          "loss_first10": first / 10, "loss_last10": last / 10, "ranks_agree_every_round": agree}))
+                          "loss_first10": first / 10, "loss_last10": last / 10, "ranks_agree_every_round": agree,
+                          "collective": "torch.distributed all_reduce" if collective is None else
+                          f"sharding.SwitchAllReduce ({collective.mode})"}))
     if world > 1:
         dist.destroy_process_group()
     return 0 if agree else 1

@@ -219,14 +219,17 @@ def views_for_rank(views: Sequence, rank: int, world: int) -> List:
 
 
 def allreduce_iteration(model: AnchorModel, grads: Dict[str, torch.Tensor], deltas, n_views_total: int,
-                        world: int) -> Dict[str, torch.Tensor]:
+                        world: int, collective=None) -> Dict[str, torch.Tensor]:
     """ONE collective per iteration: [parameter gradients | statistic deltas] summed over the ranks; gradients are then
     divided by the number of views (the reference sums the four views' losses; the mean keeps the step size
     independent of how many views an iteration has), statistics stay sums and are added into the accumulators."""
     layout = model.flat_layout()
     flat = torch.cat([grads[k].reshape(-1) for k in PARAM_NAMES] + [d.reshape(-1) for d in deltas])
     if world > 1:
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        if collective is not None:
+            collective.sum_(flat)          # sharding.SwitchAllReduce: this library's own exchange kernel (NVLink / NVSwitch)
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
     out, off = {}, 0
     for name, n in layout:
         out[name] = flat[off:off + n]
@@ -244,8 +247,9 @@ class DPTrainer:
 
     def __init__(self, model: AnchorModel, settings_fn, target_fn, rank: int = 0, world: int = 1, seed: int = 1234,
                  update_interval: int = 100, densify_from: int = 0, grad_threshold: float = 0.0002,
-                 min_opacity: float = 0.005, success_threshold: float = 0.8):
+                 min_opacity: float = 0.005, success_threshold: float = 0.8, collective=None):
         self.m, self.settings_fn, self.target_fn = model, settings_fn, target_fn
+        self.collective = collective        # None: torch.distributed all_reduce (NCCL / gloo)
         self.rank, self.world, self.seed = rank, world, seed
         self.update_interval, self.densify_from = update_interval, densify_from
         self.grad_threshold, self.min_opacity, self.success_threshold = grad_threshold, min_opacity, success_threshold
@@ -307,7 +311,7 @@ class DPTrainer:
                     m2g = torch.zeros_like(means2D) if m2g is None else m2g
                     AnchorModel.statistics_of_view(deltas, N, K, idx, g.neural_opacity, g.mask, radii, m2g)
         with torch.no_grad():
-            g_avg = allreduce_iteration(m, grads, deltas, len(views), self.world)
+            g_avg = allreduce_iteration(m, grads, deltas, len(views), self.world, self.collective)
             added = pruned = 0
             if self.iteration > self.densify_from and self.iteration % self.update_interval == 0:
                 gen = torch.Generator().manual_seed(self.seed + self.iteration)     # the same on every rank

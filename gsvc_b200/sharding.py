@@ -10,7 +10,7 @@ There is no other exchange on this path (forward-only decode needs none at all).
 from __future__ import annotations
 
 import contextlib
-from typing import Callable, Dict, List, Sequence
+from typing import Callable, Dict, List, Optional, Sequence
 
 import torch
 import torch.distributed as dist
@@ -160,9 +160,22 @@ class SwitchAllReduce:
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         if numel % 4:
             raise ValueError(f"buffer of {numel} floats is not a multiple of 4 (16-byte vector accesses)")
+        self._group, self._mode_req, self._lib = group, mode, _lib
+        if self.world * 4 > int(symm.get_signal_pad_size()):
+            raise ValueError(f"{self.world} ranks do not fit the signal pad")
+        self._allocate(numel)
+        # measured at 28 MB: the switch path is fastest with FEW CTAs (8 GPUs: 82 / 85 / 91 / 99 us at 16 / 32 / 64 / 128
+        # CTAs — more requests in flight only contend in the fabric), the peer path needs ~64 to cover the link latency
+        self.n_ctas = int(n_ctas) if n_ctas else ((16 if self.world >= 8 else 32) if self.mode == "multicast" else 64)
+        self.state = torch.zeros(2, dtype=torch.int32, device=self.device)   # where the CTAs of a launch meet
+
+    def _allocate(self, numel: int):
+        """(Re)allocate the symmetric buffer: a collective — every rank calls it with the same size."""
+        import torch.distributed._symmetric_memory as symm
+        _lib, mode = self._lib, self._mode_req
         self.numel = numel
         self.t = symm.empty(numel, dtype=torch.float32, device=self.device)
-        self.h = symm.rendezvous(self.t, group)
+        self.h = symm.rendezvous(self.t, self._group)
         mc = int(getattr(self.h, "multicast_ptr", 0) or 0)
         # two ranks: a peer load of the other copy beats sending one's own copy through the switch and back
         if mode == "auto":
@@ -175,22 +188,38 @@ class SwitchAllReduce:
         self.mode = mode
         self.mc = mc if mode == "multicast" else 0
         self.bufs = int(self.h.buffer_ptrs_dev)
-        if self.world * 4 > int(symm.get_signal_pad_size()):
-            raise ValueError(f"{self.world} ranks do not fit the signal pad")
-        self.n_ctas = int(n_ctas) if n_ctas else 64
         self.pads = int(self.h.signal_pad_ptrs_dev)
-        self.state = torch.zeros(2, dtype=torch.int32, device=self.device)   # where the CTAs of a launch meet
-        self._lib = _lib
 
     def buffer(self) -> torch.Tensor:
         return self.t
 
-    def run(self):
+    def run(self, numel: Optional[int] = None):
+        """Sum the buffer (or its first `numel` floats, a multiple of 4 and the same on every rank) over the ranks."""
+        n = self.numel if numel is None else int(numel)
+        if n % 4 or not 0 <= n <= self.numel:
+            raise ValueError(f"numel {n} must be a multiple of 4 within the buffer's {self.numel} floats")
         st = torch.cuda.current_stream(self.device).cuda_stream
         self._lib.check(self._lib.lib().gsvc_rast_switch_allreduce(self.mc or None, self.bufs, self.pads, self.state.data_ptr(), self.rank,
-                                                                   self.world, self.numel, self.n_ctas, st),
+                                                                   self.world, n, self.n_ctas, st),
                         "gsvc_rast_switch_allreduce")
         return self.t
+
+    def sum_(self, flat: torch.Tensor) -> torch.Tensor:
+        """In-place sum over the ranks of any flat fp32 tensor that fits the buffer (a copy in, the exchange, a copy out:
+        for buffers whose size changes from call to call, e.g. the anchor-level loop where anchors are grown and pruned —
+        a caller with a fixed size writes into buffer() directly)."""
+        n = flat.numel()
+        n4 = (n + 3) // 4 * 4
+        if n4 > self.numel:
+            # every rank sums the same number of floats, so every rank gets here in the same call
+            torch.cuda.current_stream(self.device).synchronize()
+            self._allocate(2 * n4)
+        self.t[:n].copy_(flat.reshape(-1))
+        if n4 > n:
+            self.t[n:n4].zero_()
+        self.run(n4)
+        flat.reshape(-1).copy_(self.t[:n])
+        return flat
 
 
 STATS_WIDTH = 2   # per Gaussian: (sum over views of |dL/dmeans2D[:2]| where drawn, number of views it was drawn in)
