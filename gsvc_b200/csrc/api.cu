@@ -3,6 +3,7 @@
 // pointers, sizes and a cudaStream_t.
 #include <atomic>
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 
@@ -398,8 +399,13 @@ static int forward_render_core(const gsvc_rast_settings* st, const DevSettings& 
     ImageView im = image_view(image, d.W, d.H, d.n_views);
     // the scatter cursors were consumed by a previous attempt: reset them
     CK(cudaMemsetAsync(im.tile_cursor, 0, (size_t)d.gx * d.gy * d.n_views * sizeof(unsigned int), stream), "cursor reset");
-    // ... and so was the overflow flag of that attempt (the blend backward refuses to replay an overflowed frame)
-    CK(cudaMemsetAsync(&im.hdr->overflow, 0, sizeof(unsigned int), stream), "overflow flag reset");
+    // ... and so were the overflow flag of that attempt (the blend backward refuses to replay an overflowed frame) and
+    // its list of heavy tiles: the sort of the first attempt may already have queued some, and a tile queued twice is
+    // sorted by two CTAs of sort_heavy_kernel at once (found by the randomised sweep: a 2 231-instance tile rendered
+    // after an overflowed first attempt came out with pixels off by 0.26)
+    static_assert(offsetof(ImageHeader, n_heavy) == offsetof(ImageHeader, overflow) + sizeof(unsigned int),
+                  "overflow and n_heavy are reset with one memset");
+    CK(cudaMemsetAsync(&im.hdr->overflow, 0, 2 * sizeof(unsigned int), stream), "overflow flag / heavy list reset");
     if (d.accumulate)
         CK(cudaMemsetAsync(out_color, 0, (size_t)n_out * 3 * d.W * d.H * sizeof(float), stream), "zero out_color");
     return render_stages(d, P, g, im, binning, capacity, out_color, stream, dbg);

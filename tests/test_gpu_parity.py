@@ -428,6 +428,33 @@ def test_heavy_tile_uses_global_sort_fallback(cuda_device):
     _check_forward(fo, state.color, max_fragile=5e-3)   # thousands of contributors per pixel at opacities 0.02-0.04
 
 
+def test_heavy_tile_after_an_overflowed_first_attempt(cuda_device):
+    """The capacity predicted from earlier calls falls short, the forward is re-enqueued on a larger buffer — and the
+    scene has a tile with more instances than the sort kernel's shared-memory path holds.  The first attempt's sort
+    may already have queued that tile for sort_heavy_kernel; the second attempt must start from an empty queue
+    (found by the randomised sweep: a tile queued twice was sorted by two CTAs at once, pixels off by 0.26)."""
+    from gsvc_b200 import rasterizer as R
+    small = make_scene(P=300, W=64, H=48, F=64, seed=5)
+    scene = make_scene(P=6000, W=64, H=48, F=64, seed=13)
+    gs = scene["gaussians"]
+    gs["means3D"][:, 0] = 0.02 * torch.randn(6000, generator=torch.Generator().manual_seed(1))
+    gs["means3D"][:, 1] = 0.02 * torch.randn(6000, generator=torch.Generator().manual_seed(2))
+    gs["means3D"][:, 2] = scene["frame"].z + 0.04 * (torch.rand(6000, generator=torch.Generator().manual_seed(3)) - 0.5)
+    gs["opacities"][:] = 0.02 + 0.02 * gs["opacities"]
+    fo = _oracle_forward(scene)
+    lens = fo["bin"]["ranges"][:, 1].astype(np.int64) - fo["bin"]["ranges"][:, 0]
+    assert lens.max() > 2048
+    for attempt in range(3):
+        R._capacity_hint.clear(); R._density_hint.clear()
+        _run_product(small, cuda_device, requires_grad=False)        # leaves a density hint far below this scene's
+        before = R.capacity_stats["rerendered"]
+        _, _, color, radii, n = _run_product(scene, cuda_device, requires_grad=False)
+        assert R.capacity_stats["rerendered"] == before + 1, "the first attempt was meant to overflow"
+        assert n == fo["num_rendered"]
+        np.testing.assert_array_equal(radii.cpu().numpy(), fo["radii"])
+        _check_forward(fo, color, max_fragile=5e-3)
+
+
 def test_toast_two_view_composition(cuda_device):
     """A.5: image = (render(V) + flip_W(render(V_s))) / 2 — the back view is the x-mirror with reversed depth."""
     f = make_scene(P=8000, W=128, H=80, F=128, seed=17, back=False)
