@@ -3,7 +3,10 @@
 The reference renders every frame twice (front view, then the x-mirrored back view), flips the
 second image and averages the two (/root/reference/pipeline/train.py:353-387,
 utils/report_utils.py:303-314); a training iteration does that for two frames, i.e. FOUR complete
-rasterizer calls plus flip / add / scale passes on the SAME Gaussians.  Here a batch of up to 16
+rasterizer calls plus flip / add / scale passes.  Views that SHARE a Gaussian set can be batched (decode /
+evaluation of a fixed set; the front / back pair of one frame when the generator ran once for both — in training
+the reference regenerates the neural Gaussians per render() call, so there the per-call path is the comparable
+one).  Here a batch of up to 16
 views is ONE kernel chain (virtual Gaussian v*P+g, virtual tile v*T+t): one preprocess, one scan,
 one scatter, one sort, one blend forward, one blend backward, one per-Gaussian backward that SUMS
 the views' parameter gradients (what autograd accumulates across the reference's calls), and the
