@@ -347,7 +347,10 @@ __device__ __forceinline__ void sort_heavy_bucket(unsigned long long* __restrict
     constexpr int WARP_ITEMS = BIG ? SORT_WARP_ITEMS_BIG : SORT_WARP_ITEMS;
     unsigned int* s_off = reinterpret_cast<unsigned int*>(s_items);          // [SPLIT_BINS + 1] range starts
     unsigned int* s_cur = s_off + SPLIT_BINS + 1;                             // [SPLIT_BINS] counters, then cursors
-    unsigned int* s_red = s_cur + SPLIT_BINS;                                 // [2 * SORT_WARPS] min / max, then a list
+    // (one word of padding: s_off holds an odd number of words, and with s_red starting on an odd word the compiler
+    //  fetched s_red[0] together with s_cur[SPLIT_BINS - 1] in one 8-byte load — harmless, the extra word is dropped, but
+    //  it reads a counter another thread is writing: racecheck's one finding on this library)
+    unsigned int* s_red = s_cur + SPLIT_BINS + 1;                             // [2 * SORT_WARPS] min / max, then a list
     const int lane = tid & 31, warp = tid >> 5;
     // 1. depth-key range of the bucket
     unsigned int kmin = 0xffffffffu, kmax = 0u;
