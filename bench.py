@@ -622,6 +622,14 @@ def run_product_arm(args, rank, local_rank, world):
             rasterize_views(batch3, means3D=g3["means3D"], opacities=g3["opacities"], colors_precomp=g3["colors_precomp"],
                             scales=g3["scales"], rotations=g3["rotations"])
         step3 = GraphedStep(batch3, g3, dL3, packed=buf3) if graphs is not None else None
+        # From 4 ranks up the backward CARRIES the exchange (gsvc_rast_backward_views_exchange): the first CTAs of the
+        # per-Gaussian backward kernel sum the rows through the switch chunk by chunk while the others still compute
+        # (8 GPUs: window 0.991 -> 0.964 ms; with 2 ranks and peer loads the separate launch is faster: 3.413 vs 3.451).
+        step3x = None
+        if ar3 is not None and ar3.mode == "multicast" and world >= 4 and graphs is not None and \
+                os.environ.get("GSVC_BENCH_C3_FUSED", "1") == "1":
+            step3x = GraphedStep(batch3, g3, dL3, exchange=ar3)
+            ar3_note += "; carried by the per-Gaussian backward's own launch (gsvc_rast_backward_views_exchange)"
 
         def c3_compute():
             if step3 is not None:
@@ -633,6 +641,9 @@ def run_product_arm(args, rank, local_rank, world):
                 torch.autograd.grad(img, [p[k] for k, _ in GRAD_LAYOUT], grad_outputs=dL3)
 
         def c3_step():
+            if step3x is not None:
+                step3x()                                         # forward + backward + exchange, one graph
+                return
             c3_compute()
             if ar3 is not None:
                 ar3.run()                                        # on the compute stream: the step ends when it has
@@ -654,7 +665,7 @@ def run_product_arm(args, rank, local_rank, world):
                    "allreduce": None if world == 1 else ar3_note,
                    "timing": "max over ranks; the all-reduce is issued on the compute stream after the backward and the "
                              "step's end event follows it"}
-        del g3, step3, buf3, dL3, ar3
+        del g3, step3, step3x, buf3, dL3, ar3
 
 
     # ---- row f2, second half: the generator's epilogue between the MLPs and the rasterizer call

@@ -28,6 +28,15 @@ class Settings(C.Structure):
     ]
 
 
+class Exchange(C.Structure):
+    """struct gsvc_rast_exchange — the rank-to-rank exchange a backward launch may carry."""
+    _fields_ = [("multicast", C.c_void_p), ("buffers", C.c_void_p), ("signal_pads", C.c_void_p), ("state", C.c_void_p),
+                ("rank", C.c_int32), ("world", C.c_int32), ("n_ctas", C.c_int32), ("chunk_rows", C.c_int32)]
+
+
+EXCHANGE_MAX_CHUNKS = 62
+
+
 class View(C.Structure):
     """struct gsvc_rast_view — one view of a batched call (gsvc_rast_*_views)."""
     _fields_ = [
@@ -70,6 +79,8 @@ SIGNATURES = {
     "gsvc_rast_backward_views": (C.c_int, [_SP, _i32, _VP, _i32, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                            _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                            _vp]),
+    "gsvc_rast_backward_views_exchange": (C.c_int, [_SP, _i32, _VP, _i32, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                                    _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, C.POINTER(Exchange), _vp]),
     "gsvc_rast_export_keys": (C.c_int, [_SP, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsvc_rast_export_geom": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsvc_rast_export_image": (C.c_int, [_SP, _i32, _vp, _vp, _vp, _vp]),

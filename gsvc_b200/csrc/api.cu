@@ -465,7 +465,7 @@ static int backward_core(const gsvc_rast_settings* st, const DevSettings& d, int
                          const float* means3D, const float* shs, const float* colors_precomp, const float* scales,
                          const float* rotations, const float* cov3D_precomp, const int32_t* radii, const void* geom,
                          const void* image, const void* binning, void* scratch, int32_t scratch_is_zero,
-                         const float* dL_dout, BwdOutputs out, cudaStream_t stream)
+                         const float* dL_dout, BwdOutputs out, cudaStream_t stream, ExchangeArgs ex = ExchangeArgs{})
 {
     int rc = check_inputs(P, sh_M, st->sh_degree, means3D, shs, colors_precomp, reinterpret_cast<const float*>(1), scales,
                           rotations, cov3D_precomp, true);
@@ -483,7 +483,7 @@ static int backward_core(const gsvc_rast_settings* st, const DevSettings& d, int
     float4* acc = static_cast<float4*>(scratch);
     PreInputs in{P, means3D, shs, colors_precomp, nullptr, scales, rotations, cov3D_precomp, 0, P};
     { StageScope t(ST_RENDER_BWD, stream); CK(launch_render_backward(d, P, g, im, b, capacity, dL_dout, acc, scratch_is_zero != 0, stream), "render_backward"); }
-    { StageScope t(ST_PREPROCESS_BWD, stream); CK(launch_preprocess_backward(d, in, radii, g, acc, out, stream), "preprocess_backward"); }
+    { StageScope t(ST_PREPROCESS_BWD, stream); CK(launch_preprocess_backward(d, in, radii, g, acc, out, ex, stream), "preprocess_backward"); }
     return 0;
 }
 
@@ -521,6 +521,55 @@ int gsvc_rast_backward_views(const gsvc_rast_settings* st, int32_t n_views, cons
                    dL_packed};
     return backward_core(st, d, P, sh_M, capacity, means3D, shs, colors_precomp, scales, rotations, cov3D_precomp, radii,
                          geom, image, binning, scratch, scratch_is_zero, dL_dout, out, static_cast<cudaStream_t>(stream_));
+}
+
+int gsvc_rast_backward_views_exchange(const gsvc_rast_settings* st, int32_t n_views, const gsvc_rast_view* views_host,
+                                      int32_t n_out, int32_t P, int32_t sh_M, int64_t capacity, const float* means3D,
+                                      const float* shs, const float* colors_precomp, const float* scales,
+                                      const float* rotations, const float* cov3D_precomp, const int32_t* radii,
+                                      const void* geom, const void* image, const void* binning, void* scratch,
+                                      int32_t scratch_is_zero, const float* dL_dout, float* dL_dmeans2D,
+                                      float* dL_packed, const gsvc_rast_exchange* x, void* stream_)
+{
+    if (!x) return fail(GSVC_RAST_ERR_INVALID, "exchange is NULL");
+    if (!dL_packed) return fail(GSVC_RAST_ERR_INVALID, "the exchange sums the packed [P,14] rows: dL_packed is NULL");
+    if (x->world < 1 || x->rank < 0 || x->rank >= x->world)
+        return fail(GSVC_RAST_ERR_INVALID, "rank %d outside world %d", x->rank, x->world);
+    if (P < 2 || (P & 1)) return fail(GSVC_RAST_ERR_INVALID, "the exchange moves 16-byte words: P must be even and > 0");
+    if (!x->signal_pads || !x->state || (!x->multicast && !x->buffers))
+        return fail(GSVC_RAST_ERR_INVALID, "signal_pads / state and one of multicast / buffers must be non-NULL");
+    if (!x->multicast && x->world > 8) return fail(GSVC_RAST_ERR_INVALID, "the peer-load path holds up to 8 ranks");
+    if ((reinterpret_cast<uintptr_t>(x->multicast) | reinterpret_cast<uintptr_t>(dL_packed)) & 15)
+        return fail(GSVC_RAST_ERR_INVALID, "dL_packed (and its multicast address) must be 16-byte aligned");
+    const int n_compute = (P + 127) / 128;
+    int chunk_rows = x->chunk_rows > 0 ? x->chunk_rows : ((P / 4 + 127) / 128) * 128;
+    if (chunk_rows % 128) return fail(GSVC_RAST_ERR_INVALID, "chunk_rows must be a multiple of 128");
+    if (chunk_rows < 128) chunk_rows = 128;
+    int chunk_ctas = chunk_rows / 128;
+    int n_chunks = (n_compute + chunk_ctas - 1) / chunk_ctas;
+    if (n_chunks > GSVC_RAST_EXCHANGE_MAX_CHUNKS) {               // fewer, larger chunks
+        chunk_ctas = (n_compute + GSVC_RAST_EXCHANGE_MAX_CHUNKS - 1) / GSVC_RAST_EXCHANGE_MAX_CHUNKS;
+        n_chunks = (n_compute + chunk_ctas - 1) / chunk_ctas;
+    }
+    const int n_ex = x->n_ctas > 0 ? x->n_ctas : 65;                 // one coordinator + 64 movers
+    if (n_ex < 2) return fail(GSVC_RAST_ERR_INVALID, "the exchange role needs a coordinator and at least one mover: n_ctas >= 2");
+    if (n_ex > 296) return fail(GSVC_RAST_ERR_INVALID, "n_ctas must be <= 296 (the exchange CTAs must stay co-resident)");
+    ExchangeArgs ex{};
+    ex.mc = static_cast<float4*>(x->multicast);
+    ex.bufs = static_cast<float4* const*>(x->buffers);
+    ex.pads = static_cast<unsigned int* const*>(x->signal_pads);
+    ex.state = static_cast<unsigned int*>(x->state);
+    ex.rank = x->rank; ex.world = x->world; ex.n_ex = n_ex;
+    ex.chunk_ctas = chunk_ctas; ex.n_chunks = n_chunks; ex.n_compute = n_compute;
+    ex.chunk_f4 = (long long)chunk_ctas * 128 * 14 / 4;
+    ex.total_f4 = (long long)P * 14 / 4;
+    DevSettings d;
+    int rc = make_settings_views(st, n_views, views_host, n_out, shs ? sh_M : 0, d);
+    if (rc) return rc;
+    BwdOutputs out{nullptr, dL_dmeans2D, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, dL_packed};
+    return backward_core(st, d, P, sh_M, capacity, means3D, shs, colors_precomp, scales, rotations, cov3D_precomp, radii,
+                         geom, image, binning, scratch, scratch_is_zero, dL_dout, out, static_cast<cudaStream_t>(stream_),
+                         ex);
 }
 
 int gsvc_rast_export_keys(const gsvc_rast_settings* st, int32_t n_views, int64_t capacity, const void* image,

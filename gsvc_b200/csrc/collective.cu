@@ -9,79 +9,9 @@
 // in, no GPU receives N copies, and no SM adds anything.  Everything is ONE launch: the ranks handshake before (the
 // peers' producer kernels have finished) and after (their stores have landed) through one word per pair of ranks in
 // the symmetric signal pad.
-#include "common.cuh"
+#include "collective.cuh"
 
 namespace gsvc {
-
-constexpr int AR_THREADS = 512;
-
-// Handshake of this rank with every peer.  slot(owner, writer) is one word of `owner`'s pad that only `writer` raises
-// and only `owner` lowers: raise = wait until it is 0, set it to 1; lower = wait until it is 1, set
-// it back to 0.  Stateless (the pad is all zeros between two launches), so a CUDA graph can replay it.
-__device__ __forceinline__ unsigned int cas_release_sys(unsigned int* a, unsigned int cmp, unsigned int val)
-{
-    unsigned int old;
-    asm volatile("atom.release.sys.global.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(a), "r"(cmp), "r"(val) : "memory");
-    return old;
-}
-__device__ __forceinline__ unsigned int cas_acquire_sys(unsigned int* a, unsigned int cmp, unsigned int val)
-{
-    unsigned int old;
-    asm volatile("atom.acquire.sys.global.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(a), "r"(cmp), "r"(val) : "memory");
-    return old;
-}
-
-__device__ __forceinline__ void peer_handshake(unsigned int* const* pads, int rank, int world)
-{
-    if ((int)threadIdx.x < world) {
-        const int peer = (int)threadIdx.x;
-        unsigned int* theirs = pads[peer] + rank;      // I raise it, the peer lowers it
-        unsigned int* mine = pads[rank] + peer;        // the peer raises it, I lower it
-        while (cas_release_sys(theirs, 0u, 1u) != 0u) {}
-        while (cas_acquire_sys(mine, 1u, 0u) != 1u) {}
-    }
-}
-
-// ONE CTA of the launch talks to the peers (world words of pad traffic per rank and handshake, whatever the grid size;
-// with a handshake per CTA the 8-GPU exchange lost 15 us between 16 and 128 CTAs).  state = {go, done}: two words of
-// LOCAL device memory, zero between launches.
-//   begin: CTA 0 handshakes (every peer's producer kernels have finished), then opens `go` for the other CTAs.
-__device__ __forceinline__ void exchange_begin(unsigned int* const* pads, unsigned int* state, int rank, int world)
-{
-    if (blockIdx.x == 0) {
-        peer_handshake(pads, rank, world);
-        __syncthreads();
-        if (threadIdx.x == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(state), "r"(1u) : "memory");
-    } else {
-        if (threadIdx.x == 0) {
-            unsigned int v;
-            do {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(state) : "memory");
-            } while (v != 1u);
-        }
-        __syncthreads();
-    }
-}
-//   end: every CTA's stores are performed system-wide, then the LAST CTA to get here resets the state and handshakes
-//   (every peer's stores into this rank's buffer have landed before the kernel completes).
-__device__ __forceinline__ void exchange_end(unsigned int* const* pads, unsigned int* state, int rank, int world)
-{
-    __shared__ int s_last;
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned int prev;
-        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(prev) : "l"(state + 1), "r"(1u) : "memory");
-        s_last = prev == gridDim.x - 1;
-        if (s_last) {
-            state[0] = 0u;
-            state[1] = 0u;
-            __threadfence();
-        }
-    }
-    __syncthreads();
-    if (s_last) peer_handshake(pads, rank, world);
-}
 
 template <int AR_UNROLL>
 __global__ void __launch_bounds__(AR_THREADS)
@@ -95,36 +25,21 @@ switch_allreduce_kernel(float4* __restrict__ mc, unsigned int* const* __restrict
 #pragma unroll
         for (int u = 0; u < AR_UNROLL; u++) {
             const long long i = i0 + u * stride;
-            if (i < hi4)
-                asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
-                             : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "l"(mc + i) : "memory");
+            if (i < hi4) v[u] = mc_ld_reduce(mc + i);
         }
 #pragma unroll
         for (int u = 0; u < AR_UNROLL; u++) {
             const long long i = i0 + u * stride;
-            if (i < hi4)
-                asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
-                             ::"l"(mc + i), "f"(v[u].x), "f"(v[u].y), "f"(v[u].z), "f"(v[u].w) : "memory");
+            if (i < hi4) mc_st(mc + i, v[u]);
         }
     }
-    exchange_end(pads, state, rank, world);
+    exchange_end(pads, state, rank, world, gridDim.x);
 }
 
 // The same exchange without a multicast mapping (or for two ranks, where sending one's own copy through the switch
 // costs more than it saves): rank r reads its slice from every rank's buffer with peer loads (NVLink), adds the copies
 // in rank order — one adder per element, so every rank receives the SAME sum — and stores the result into every
 // rank's buffer with peer stores.
-__device__ __forceinline__ float4 ld_sys(const float4* p)
-{
-    float4 v;
-    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_sys(float4* p, float4 v)
-{
-    asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-
 template <int WORLD, int UNROLL>
 __global__ void __launch_bounds__(AR_THREADS)
 peer_allreduce_kernel(float4* const* __restrict__ bufs, unsigned int* const* __restrict__ pads, unsigned int* state, int rank,
@@ -157,7 +72,7 @@ peer_allreduce_kernel(float4* const* __restrict__ bufs, unsigned int* const* __r
             }
         }
     }
-    exchange_end(pads, state, rank, WORLD);
+    exchange_end(pads, state, rank, WORLD, gridDim.x);
 }
 
 cudaError_t launch_switch_allreduce(float* multicast, void* const* buffers, unsigned int* const* pads, unsigned int* state,

@@ -374,8 +374,20 @@ struct BwdOutputs {
     float* dL_dscales; float* dL_drotations; float* dL_dcov3D; float* dL_dshs;
     float* packed;  // optional [P,14] (means3D, colours, opacity, scales, rotation) replacing the five dense arrays
 };
+// the exchange a per-Gaussian backward launch may carry (collective.cuh: exchange_role)
+struct ExchangeArgs {
+    float4* mc;                        // the buffer through the multicast mapping (nullptr: peer loads / stores)
+    float4* const* bufs;               // [world] the ranks' buffers as mapped here
+    unsigned int* const* pads;         // [world] the ranks' signal pads as mapped here
+    unsigned int* state;               // [2 + n_chunks] zeroed words of local memory: go, done, chunk counters
+    int rank, world;
+    int n_ex;                          // CTAs of the exchange role (0: the launch carries no exchange)
+    int chunk_ctas, n_chunks;          // compute CTAs per chunk; chunks of the buffer
+    int n_compute;                     // compute CTAs of the launch
+    long long chunk_f4, total_f4;      // 16-byte words per chunk / in the buffer
+};
 cudaError_t launch_preprocess_backward(const DevSettings& s, const PreInputs& in, const int32_t* radii, GeomView g,
-                                       const float4* acc, BwdOutputs out, cudaStream_t st);
+                                       const float4* acc, BwdOutputs out, ExchangeArgs ex, cudaStream_t st);
 cudaError_t launch_export_keys(const DevSettings& s, ImageView im, BinView b, long long R,
                                unsigned long long* sorted_keys, unsigned int* point_list, unsigned int* ranges,
                                cudaStream_t st);

@@ -4,7 +4,7 @@
 // Under the orthographic camera the pixel position enters nothing but `pix`, so unlike the
 // perspective rasterizer there is no mean → cov2D term.
 // Pure stream over P Gaussians: HBM-bound (reads 4 P + ~100 V, writes 68 P bytes).
-#include "common.cuh"
+#include "collective.cuh"
 
 namespace gsvc {
 
@@ -84,13 +84,10 @@ __device__ void sh_backward(int deg, int M, const float* sh, float* dsh, const f
     dmean[2] += (ddz - z * dot) / len;
 }
 
-__global__ void __launch_bounds__(256,2) preprocess_backward_kernel(DevSettings s, PreInputs in,
-                                                                  const int32_t* __restrict__ radii, GeomView geo,
-                                                                  const float4* __restrict__ acc, BwdOutputs out)
+__device__ __forceinline__ void gaussian_backward(const DevSettings& s, const PreInputs& in,
+                                                  const int32_t* __restrict__ radii, const GeomView& geo,
+                                                  const float4* __restrict__ acc, const BwdOutputs& out, const int g)
 {
-    pdl_prologue();
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= in.P) return;
     float dmean[3] = {0.f, 0.f, 0.f}, dcol[3] = {0.f, 0.f, 0.f}, dop = 0.f;
     float dsc[3] = {0.f, 0.f, 0.f}, drot[4] = {0.f, 0.f, 0.f, 0.f}, dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (in.shs && out.dL_dshs) {
@@ -253,12 +250,40 @@ __global__ void __launch_bounds__(256,2) preprocess_backward_kernel(DevSettings 
     }
 }
 
+// One thread per Gaussian.  With an exchange (ex.n_ex > 0: the packed [P,14] rows are one rank's share of a
+// frame-sharded step and live in symmetric memory) the first ex.n_ex CTAs of the launch do not compute: they sum the rows
+// over the ranks chunk by chunk while the other CTAs are still producing the later chunks (collective.cuh), so the
+// launch ends with the all-reduced buffer in place and most of the transfer hidden under the computation.
+__global__ void __launch_bounds__(256,2) preprocess_backward_kernel(DevSettings s, PreInputs in,
+                                                                  const int32_t* __restrict__ radii, GeomView geo,
+                                                                  const float4* __restrict__ acc, BwdOutputs out,
+                                                                  ExchangeArgs ex)
+{
+    pdl_prologue();
+    if (ex.n_ex > 0 && (int)blockIdx.x < ex.n_ex) {
+        exchange_role(ex);
+        return;
+    }
+    const int cta = (int)blockIdx.x - ex.n_ex;
+    const int g = cta * blockDim.x + threadIdx.x;
+    if (g < in.P) gaussian_backward(s, in, radii, geo, acc, out, g);
+    if (ex.n_ex > 0) {
+        // device-scope only: a system-scope fence in each of the ~P/128 CTAs cost 100 us per launch.  The chain to the
+        // peers is closed by the coordinator CTA: it acquires the chunk's count (device scope), fences at system scope
+        // once per chunk and only then raises the chunk's flag in the peers' pads.
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(ex.state + 2 + cta / ex.chunk_ctas, 1u);
+    }
+}
+
 cudaError_t launch_preprocess_backward(const DevSettings& s, const PreInputs& in, const int32_t* radii, GeomView g,
-                                       const float4* acc, BwdOutputs out, cudaStream_t st)
+                                       const float4* acc, BwdOutputs out, ExchangeArgs ex, cudaStream_t st)
 {
     if (in.P <= 0) return cudaSuccess;
     count_launch();
-    return launch_pdl(preprocess_backward_kernel, dim3((in.P + 127) / 128), dim3(128), st, s, in, radii, g, acc, out);
+    const int n_compute = (in.P + 127) / 128;
+    return launch_pdl(preprocess_backward_kernel, dim3(n_compute + ex.n_ex), dim3(128), st, s, in, radii, g, acc, out, ex);
 }
 
 // Densification statistic at the rasterizer boundary (scene/gaussian_model.py:1298-1314 `training_statis`, called

@@ -30,10 +30,12 @@ from .views import ViewBatch, rasterize_views
 
 class GraphedStep:
     def __init__(self, rast, params: Dict[str, torch.Tensor], dL: Optional[torch.Tensor],
-                 packed: Optional[torch.Tensor] = None, warmup: int = 2):
+                 packed: Optional[torch.Tensor] = None, warmup: int = 2, exchange=None):
         """`rast`: a GaussianRasterizer (one view, dL [3,H,W]) or a views.ViewBatch (all its views in one chain,
         dL [n_out,3,H,W], gradients summed over the views).  `dL` None: forward only.  `packed`: optional [P,14]
-        buffer the backward writes (sharding.GRAD_LAYOUT); allocated here if omitted."""
+        buffer the backward writes (sharding.GRAD_LAYOUT); allocated here if omitted.  `exchange`: a
+        sharding.SwitchAllReduce over P*14 floats — the backward then writes into ITS buffer and carries the sum over the
+        ranks in its own launches (ViewBatch steps only; every rank builds and replays the same step)."""
         self.rast, self.params, self.dL = rast, params, dL
         self.batch = rast if isinstance(rast, ViewBatch) else None
         m = params["means3D"]
@@ -41,6 +43,13 @@ class GraphedStep:
             raise RasterizerError("GraphedStep needs CUDA tensors: gsvc_b200 has no CPU fallback")
         self.device, self.P = m.device, int(m.shape[0])
         self.backward = dL is not None
+        self.exchange = exchange
+        if exchange is not None:
+            if self.batch is None or not self.backward:
+                raise RasterizerError("a step carries the exchange in its batched-view backward: pass a ViewBatch and dL")
+            if packed is not None:
+                raise RasterizerError("with `exchange` the packed buffer is the exchange's own")
+            packed = exchange.buffer().view(self.P, GRAD_WIDTH)
         if self.backward and packed is None:
             packed = torch.empty((self.P, GRAD_WIDTH), dtype=torch.float32, device=self.device)
         self.packed = packed
@@ -68,7 +77,7 @@ class GraphedStep:
         leaves = {k: p[k].detach().requires_grad_(True) for k, _ in GRAD_LAYOUT}
         means2D = None if self.batch is not None else torch.zeros_like(leaves["means3D"], requires_grad=True)
         color, radii, n = self._call(leaves, means2D)
-        with packed_backward(self.packed):
+        with packed_backward(self.packed, exchange=self.exchange):
             torch.autograd.grad(color, [leaves[k] for k, _ in GRAD_LAYOUT], grad_outputs=self.dL)
         return color, radii, n
 

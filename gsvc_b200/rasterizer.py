@@ -112,16 +112,25 @@ class _PackedTarget:
     on another thread) gets ordinary dense gradients instead of silently overwriting the first one's."""
     buf = None
     taken = False
+    exchange = None        # sharding.SwitchAllReduce whose buffer `buf` is: the backward that takes buf carries the exchange
     lock = threading.Lock()
 
     def take(self, P, device, ok: bool):
+        return self.take_with_exchange(P, device, ok)[0]
+
+    def take_with_exchange(self, P, device, ok: bool):
+        """(buffer or None, exchange or None).  A backward that cannot carry the exchange (single-view entry point)
+        calls take(): the exchange is then left to the caller (SwitchAllReduce.run())."""
         with self.lock:
             b = self.buf
             if (b is None or self.taken or not ok or tuple(b.shape) != (P, 14) or b.device != device or
                     b.dtype != torch.float32 or not b.is_contiguous()):
-                return None
+                return None, None
             self.taken = True
-            return b
+            x = self.exchange
+            if x is not None:
+                x.fused_launches += 1
+            return b, x
 
 
 _packed_target = _PackedTarget()

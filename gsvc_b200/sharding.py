@@ -37,22 +37,31 @@ def pack_grads(grads: Dict[str, torch.Tensor], out: torch.Tensor = None) -> torc
 
 
 @contextlib.contextmanager
-def packed_backward(buf: torch.Tensor):
+def packed_backward(buf: torch.Tensor, exchange=None):
     """While active, the FIRST rasterizer backward that fits writes the GRAD_LAYOUT gradients directly into `buf`
     ([P,14] fp32, contiguous, on the rasterizer's device) and returns views of it, so the all-reduce needs no pack
     pass.  One context serves one backward: a second rasterizer backward inside it (the reference loop's four
     render() calls under one loss.backward()) returns ordinary dense gradients — batch the views of a step into one
-    call (views.rasterize_views) to get all of them into the buffer."""
+    call (views.rasterize_views) to get all of them into the buffer.
+
+    `exchange`: the SwitchAllReduce that owns `buf` (buf = exchange.buffer().view(P, 14)).  The batched-view backward
+    then CARRIES the all-reduce: the first CTAs of its per-Gaussian kernel sum the rows over the ranks chunk by chunk
+    while the others still compute (gsvc_rast_backward_views_exchange), and the buffer holds the sum over the ranks
+    when the backward's kernels have run — no separate collective launch.  Every rank must run the same backward;
+    `exchange.fused_launches` counts the launches that carried it (a backward that could not — a single-view call — leaves
+    the buffer un-reduced: call exchange.run())."""
     from . import rasterizer
     t = rasterizer._packed_target
+    if exchange is not None and (buf.data_ptr() != exchange.buffer().data_ptr() or buf.numel() != exchange.numel):
+        raise ValueError("packed_backward(buf, exchange): buf must be the exchange's whole buffer viewed as [P,14]")
     with t.lock:
-        prev = (t.buf, t.taken)
-        t.buf, t.taken = buf, False
+        prev = (t.buf, t.taken, t.exchange)
+        t.buf, t.taken, t.exchange = buf, False, exchange
     try:
         yield buf
     finally:
         with t.lock:
-            t.buf, t.taken = prev
+            t.buf, t.taken, t.exchange = prev
 
 
 def unpack_grads(buf: torch.Tensor) -> Dict[str, torch.Tensor]:
@@ -167,7 +176,10 @@ class SwitchAllReduce:
         # measured at 28 MB: the switch path is fastest with FEW CTAs (8 GPUs: 82 / 85 / 91 / 99 us at 16 / 32 / 64 / 128
         # CTAs — more requests in flight only contend in the fabric), the peer path needs ~64 to cover the link latency
         self.n_ctas = int(n_ctas) if n_ctas else ((16 if self.world >= 8 else 32) if self.mode == "multicast" else 64)
-        self.state = torch.zeros(2, dtype=torch.int32, device=self.device)   # where the CTAs of a launch meet
+        # where the CTAs of a launch meet: go, done, and the chunk counters of a backward that carries the exchange
+        self.state = torch.zeros(2 + _lib.EXCHANGE_MAX_CHUNKS, dtype=torch.int32, device=self.device)
+        self.fused_launches = 0
+        self._xstruct = None
 
     def _allocate(self, numel: int):
         """(Re)allocate the symmetric buffer: a collective — every rank calls it with the same size."""
@@ -192,6 +204,18 @@ class SwitchAllReduce:
 
     def buffer(self) -> torch.Tensor:
         return self.t
+
+    def exchange_struct(self, n_ctas: int = 0, chunk_rows: int = 0):
+        """struct gsvc_rast_exchange for gsvc_rast_backward_views_exchange (kept alive by this object)."""
+        import os
+        # measured (profiles/r4_notes.md): the switch path wants few movers (8 GPUs, 28 MB: 33 CTAs beat 65), the peer path
+        # many (2 GPUs: 129 beat 65; it still loses to the separate launch there, so bench.py does not use it for 2 ranks)
+        n_ctas = int(n_ctas) or int(os.environ.get("GSVC_EXCHANGE_CTAS", "0")) or (33 if self.mode == "multicast" else 129)
+        chunk_rows = int(chunk_rows) or int(os.environ.get("GSVC_EXCHANGE_CHUNK_ROWS", "0"))
+        x = self._lib.Exchange(self.mc or None, self.bufs, self.pads, self.state.data_ptr(), self.rank, self.world,
+                               n_ctas, chunk_rows)
+        self._xstruct = x
+        return x
 
     def run(self, numel: Optional[int] = None):
         """Sum the buffer (or its first `numel` floats, a multiple of 4 and the same on every rank) over the ranks."""

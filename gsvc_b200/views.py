@@ -226,7 +226,10 @@ class _RasterizeViews(torch.autograd.Function):
         bin_p = binning.data_ptr() if binning is not None else base + n_geom + n_img + n_acc
         with torch.cuda.device(device):
             g_out = _dev_f32(grad_out_color, device, "grad_out_color")
-            packed = R._packed_target.take(P, device, col is not None and sc is not None)
+            packed, exchange = R._packed_target.take_with_exchange(P, device, col is not None and sc is not None)
+            if exchange is not None and (P % 2 or sh is not None or cov is not None):
+                raise RasterizerError("a backward that carries the exchange needs an even P, colors_precomp and the "
+                                      "scale / rotation pair")
             widths = (3, 3 * V, 1, 3 if col is not None else 0, ctx.sh_M * 3 if sh is not None else 0,
                       3 if sc is not None else 0, 4 if rot is not None else 0, 6 if cov is not None else 0)
             n_scratch = 0 if n_acc else L.gsvc_rast_backward_scratch_bytes(P * V) // 4
@@ -240,11 +243,19 @@ class _RasterizeViews(torch.autograd.Function):
             off = (off + 63) & ~63
             scratch_p = base + n_geom + n_img if n_acc else flat.data_ptr() + 4 * off
             g_means3D, g_means2D, g_opac, g_col, g_sh, g_sc, g_rot, g_cov = outs
-            _lib.check(L.gsvc_rast_backward_views(
-                nv.ref, V, nv.views, n_out, P, ctx.sh_M, ctx.capacity, _ptr(means3D), _ptr(sh), _ptr(col), _ptr(sc),
-                _ptr(rot), _ptr(cov), _ptr(radii), base, base + n_geom, bin_p, scratch_p, acc_clean, _ptr(g_out),
-                _ptr(g_means3D), _ptr(g_means2D), _ptr(g_col), _ptr(g_opac), _ptr(g_sc), _ptr(g_rot), _ptr(g_cov),
-                _ptr(g_sh), _ptr(packed), _stream_ptr(device)), "gsvc_rast_backward_views")
+            if exchange is not None:
+                import ctypes
+                _lib.check(L.gsvc_rast_backward_views_exchange(
+                    nv.ref, V, nv.views, n_out, P, ctx.sh_M, ctx.capacity, _ptr(means3D), _ptr(sh), _ptr(col), _ptr(sc),
+                    _ptr(rot), _ptr(cov), _ptr(radii), base, base + n_geom, bin_p, scratch_p, acc_clean, _ptr(g_out),
+                    _ptr(g_means2D), _ptr(packed), ctypes.byref(exchange.exchange_struct()), _stream_ptr(device)),
+                    "gsvc_rast_backward_views_exchange")
+            else:
+                _lib.check(L.gsvc_rast_backward_views(
+                    nv.ref, V, nv.views, n_out, P, ctx.sh_M, ctx.capacity, _ptr(means3D), _ptr(sh), _ptr(col), _ptr(sc),
+                    _ptr(rot), _ptr(cov), _ptr(radii), base, base + n_geom, bin_p, scratch_p, acc_clean, _ptr(g_out),
+                    _ptr(g_means3D), _ptr(g_means2D), _ptr(g_col), _ptr(g_opac), _ptr(g_sc), _ptr(g_rot), _ptr(g_cov),
+                    _ptr(g_sh), _ptr(packed), _stream_ptr(device)), "gsvc_rast_backward_views")
         v = lambda t, *shape: None if t is None else t.view(*shape)
         if packed is not None:
             return (packed[:, 0:3], v(g_means2D, V, P, 3), None, packed[:, 3:6], packed[:, 6:7], packed[:, 7:10],

@@ -263,6 +263,39 @@ GSVC_RAST_API int gsvc_rast_switch_allreduce(void *multicast, void *buffers, voi
                                int32_t world, int64_t numel, int32_t n_ctas, void *stream);
 
 /*
+ * The backward of a batch of views WITH the exchange of a frame-sharded step in the same launches: the per-Gaussian
+ * backward writes the packed [P,14] rows (dL_packed, required) of THIS rank's frames, and the first `n_ctas` CTAs of
+ * that same kernel sum the rows over the ranks — chunk by chunk, while the other CTAs are still computing the later
+ * chunks — so the call ends with the all-reduced buffer in place on every rank (bit-identical) and most of the transfer
+ * hidden under the computation.  dL_packed must be this rank's part of a symmetric allocation as for
+ * gsvc_rast_switch_allreduce (same meaning of multicast / buffers / signal_pads / rank / world; the pads must hold
+ * world * (1 + chunks) words); P must be even.
+ *   state        2 + GSVC_RAST_EXCHANGE_MAX_CHUNKS zeroed 32-bit words of this rank's own device memory
+ *   n_ctas       CTAs of the exchange role (128 threads each: one coordinator + the movers; 0 selects 65)
+ *   chunk_rows   Gaussians per chunk, a multiple of 128 (0 selects ~1/4 of P); the same on every rank
+ * Every rank must make the call with the same P.  All other arguments as gsvc_rast_backward_views.
+ */
+#define GSVC_RAST_EXCHANGE_MAX_CHUNKS 62
+typedef struct gsvc_rast_exchange {
+    void *multicast;     /* dL_packed through the multicast mapping, or NULL: peer loads and stores */
+    void *buffers;       /* device array of `world` pointers: every rank's dL_packed as mapped here */
+    void *signal_pads;   /* device array of `world` pointers: every rank's signal pad as mapped here */
+    void *state;
+    int32_t rank;
+    int32_t world;
+    int32_t n_ctas;
+    int32_t chunk_rows;
+} gsvc_rast_exchange;
+
+GSVC_RAST_API int gsvc_rast_backward_views_exchange(const gsvc_rast_settings *st, int32_t n_views,
+                             const gsvc_rast_view *views_host, int32_t n_out, int32_t P, int32_t sh_M, int64_t capacity,
+                             const float *means3D, const float *shs, const float *colors_precomp, const float *scales,
+                             const float *rotations, const float *cov3D_precomp, const int32_t *radii, const void *geom,
+                             const void *image, const void *binning, void *scratch, int32_t scratch_is_zero,
+                             const float *dL_dout, float *dL_dmeans2D, float *dL_packed,
+                             const gsvc_rast_exchange *exchange, void *stream);
+
+/*
  * Stage exports for bit-exact parity tests (not used on the hot path).
  * keys: sorted_keys [R] = (tile << 32) | depth_key, point_list [R], ranges [T,2] (untouched tiles 0,0).
  * geom: depth [P], xy [P,2], conic_opacity [P,4], rgb [P,3], rect [P,4] int32 (minx,miny,maxx,maxy tiles).
