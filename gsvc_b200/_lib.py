@@ -35,6 +35,7 @@ class Exchange(C.Structure):
 
 
 EXCHANGE_MAX_CHUNKS = 62
+EXCHANGE_STATE_WORDS = 2 + EXCHANGE_MAX_CHUNKS + 1     # go, done, chunk counters, count of waits that gave up
 
 
 class View(C.Structure):

@@ -23,14 +23,44 @@ __device__ __forceinline__ unsigned int cas_acquire_sys(unsigned int* a, unsigne
     return old;
 }
 
-__device__ __forceinline__ void peer_handshake(unsigned int* const* pads, int rank, int world)
+// Every wait of the exchange is bounded: a rank that never arrives (a crashed peer process, a caller that skipped the
+// collective call) must not leave this GPU spinning for good.  After ~20 s (clock64 runs at the SM clock) the wait gives
+// up, counts itself in the sticky word state[EXCHANGE_TIMEOUT_WORD] and the kernel runs to its end — the buffer is then NOT
+// the sum over the ranks; the owner reads that word after a synchronisation (SwitchAllReduce.timeouts()).
+constexpr long long EXCHANGE_WAIT_CYCLES = 40000000000ll;
+constexpr int EXCHANGE_TIMEOUT_WORD = 2 + GSVC_RAST_EXCHANGE_MAX_CHUNKS;   // state = go, done, chunk counters, this word
+
+__device__ __forceinline__ long long sm_clock()
+{
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
+    return t;
+}
+
+struct SpinGuard {
+    long long t0;
+    unsigned int n;
+    unsigned int* sticky;
+    __device__ __forceinline__ explicit SpinGuard(unsigned int* state) : t0(sm_clock()), n(0u), sticky(state + EXCHANGE_TIMEOUT_WORD) {}
+    // true: keep waiting
+    __device__ __forceinline__ bool keep_waiting()
+    {
+        if ((++n & 0xfffu) != 0u) return true;                     // look at the clock every 4096 polls
+        if (sm_clock() - t0 < EXCHANGE_WAIT_CYCLES) return true;
+        atomicAdd(sticky, 1u);
+        return false;
+    }
+};
+
+__device__ __forceinline__ void peer_handshake(unsigned int* const* pads, unsigned int* state, int rank, int world)
 {
     if ((int)threadIdx.x < world) {
         const int peer = (int)threadIdx.x;
         unsigned int* theirs = pads[peer] + rank;      // I raise it, the peer lowers it
         unsigned int* mine = pads[rank] + peer;        // the peer raises it, I lower it
-        while (cas_release_sys(theirs, 0u, 1u) != 0u) {}
-        while (cas_acquire_sys(mine, 1u, 0u) != 1u) {}
+        SpinGuard guard(state);
+        while (cas_release_sys(theirs, 0u, 1u) != 0u && guard.keep_waiting()) {}
+        while (cas_acquire_sys(mine, 1u, 0u) != 1u && guard.keep_waiting()) {}
     }
 }
 
@@ -41,15 +71,16 @@ __device__ __forceinline__ void peer_handshake(unsigned int* const* pads, int ra
 __device__ __forceinline__ void exchange_begin(unsigned int* const* pads, unsigned int* state, int rank, int world)
 {
     if (blockIdx.x == 0) {
-        peer_handshake(pads, rank, world);
+        peer_handshake(pads, state, rank, world);
         __syncthreads();
         if (threadIdx.x == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(state), "r"(1u) : "memory");
     } else {
         if (threadIdx.x == 0) {
             unsigned int v;
+            SpinGuard guard(state);
             do {
                 asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(state) : "memory");
-            } while (v != 1u);
+            } while (v != 1u && guard.keep_waiting());
         }
         __syncthreads();
     }
@@ -72,7 +103,7 @@ __device__ __forceinline__ void exchange_end(unsigned int* const* pads, unsigned
         }
     }
     __syncthreads();
-    if (s_last) peer_handshake(pads, rank, world);
+    if (s_last) peer_handshake(pads, state, rank, world);
 }
 
 __device__ __forceinline__ float4 ld_sys(const float4* p)
@@ -169,9 +200,10 @@ __device__ __forceinline__ void exchange_role(const ExchangeArgs& ex)
             if (threadIdx.x == 0) {
                 const unsigned int want = (unsigned int)min(ex.chunk_ctas, ex.n_compute - k * ex.chunk_ctas);
                 unsigned int v;
+                SpinGuard guard(ex.state);
                 do {
                     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ex.state + 2 + k) : "memory");
-                } while (v != want);
+                } while (v != want && guard.keep_waiting());
                 __threadfence_system();
             }
             __syncthreads();
@@ -188,9 +220,10 @@ __device__ __forceinline__ void exchange_role(const ExchangeArgs& ex)
         for (int k = 0; k < ex.n_chunks; k++) {
             if ((int)threadIdx.x < W) {
                 unsigned int v;
+                SpinGuard guard(ex.state);
                 do {
                     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(my_flags + (size_t)k * W + threadIdx.x) : "memory");
-                } while (v != 1u);
+                } while (v != 1u && guard.keep_waiting());
             }
             __syncthreads();
             const long long c_lo = (long long)k * ex.chunk_f4;
@@ -214,7 +247,7 @@ __device__ __forceinline__ void exchange_role(const ExchangeArgs& ex)
         for (int i = threadIdx.x; i < 2 + ex.n_chunks; i += blockDim.x) ex.state[i] = 0u;
         __threadfence_system();
         __syncthreads();
-        peer_handshake(ex.pads, ex.rank, W);
+        peer_handshake(ex.pads, ex.state, ex.rank, W);
     }
 }
 

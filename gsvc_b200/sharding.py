@@ -177,7 +177,7 @@ class SwitchAllReduce:
         # CTAs — more requests in flight only contend in the fabric), the peer path needs ~64 to cover the link latency
         self.n_ctas = int(n_ctas) if n_ctas else ((16 if self.world >= 8 else 32) if self.mode == "multicast" else 64)
         # where the CTAs of a launch meet: go, done, and the chunk counters of a backward that carries the exchange
-        self.state = torch.zeros(2 + _lib.EXCHANGE_MAX_CHUNKS, dtype=torch.int32, device=self.device)
+        self.state = torch.zeros(_lib.EXCHANGE_STATE_WORDS, dtype=torch.int32, device=self.device)
         self.fused_launches = 0
         self._xstruct = None
 
@@ -204,6 +204,14 @@ class SwitchAllReduce:
 
     def buffer(self) -> torch.Tensor:
         return self.t
+
+    def timeouts(self, reset: bool = False) -> int:
+        """Waits of this exchange that gave up (every wait is bounded at ~20 s: a rank that never arrives leaves a wrong
+        buffer and a count here instead of a spinning GPU).  Synchronises the device."""
+        n = int(self.state[-1].item())
+        if reset and n:
+            self.state[-1].zero_()
+        return n
 
     def exchange_struct(self, n_ctas: int = 0, chunk_rows: int = 0):
         """struct gsvc_rast_exchange for gsvc_rast_backward_views_exchange (kept alive by this object)."""

@@ -251,14 +251,18 @@ GSVC_RAST_API int gsvc_rast_densify_stats(int32_t n_views, int32_t P, const floa
  *                 (handle.buffer_ptrs_dev); may be NULL when multicast is given
  *   signal_pads   device array of `world` pointers: signal_pads[q] = rank q's zero-initialised signal pad as mapped
  *                 into THIS process (handle.signal_pad_ptrs_dev), each at least world * 4 bytes
- *   state         two zeroed 32-bit words of this rank's OWN device memory, private to this buffer (the CTAs of the
- *                 launch meet there); zero again when the kernel has completed
+ *   state         GSVC_RAST_EXCHANGE_STATE_WORDS zeroed 32-bit words of this rank's OWN device memory, private to this
+ *                 buffer (the CTAs of the launch meet there); zero again when the kernel has completed — except the
+ *                 LAST word, which counts waits that gave up: every wait of the exchange is bounded (~20 s), so a
+ *                 rank that never arrives leaves a wrong buffer and a non-zero count instead of a spinning GPU
  *   numel         floats in the buffer, a multiple of 4
  *   n_ctas        CTAs of the launch (all of them must be co-resident: <= 4 * SM count)
  * On return of the kernel every rank's buffer holds the sum over the ranks, bit-identical on all of them (one adder
  * per element).  Every rank must make the call (it is a collective); the pad words are back to zero afterwards, so
  * the launch can be captured in a CUDA graph and replayed.
  */
+#define GSVC_RAST_EXCHANGE_MAX_CHUNKS 62
+#define GSVC_RAST_EXCHANGE_STATE_WORDS (2 + GSVC_RAST_EXCHANGE_MAX_CHUNKS + 1)
 GSVC_RAST_API int gsvc_rast_switch_allreduce(void *multicast, void *buffers, void *signal_pads, void *state, int32_t rank,
                                int32_t world, int64_t numel, int32_t n_ctas, void *stream);
 
@@ -270,12 +274,11 @@ GSVC_RAST_API int gsvc_rast_switch_allreduce(void *multicast, void *buffers, voi
  * hidden under the computation.  dL_packed must be this rank's part of a symmetric allocation as for
  * gsvc_rast_switch_allreduce (same meaning of multicast / buffers / signal_pads / rank / world; the pads must hold
  * world * (1 + chunks) words); P must be even.
- *   state        2 + GSVC_RAST_EXCHANGE_MAX_CHUNKS zeroed 32-bit words of this rank's own device memory
+ *   state        GSVC_RAST_EXCHANGE_STATE_WORDS zeroed 32-bit words of this rank's own device memory (as above)
  *   n_ctas       CTAs of the exchange role (128 threads each: one coordinator + the movers; 0 selects 65)
  *   chunk_rows   Gaussians per chunk, a multiple of 128 (0 selects ~1/4 of P); the same on every rank
  * Every rank must make the call with the same P.  All other arguments as gsvc_rast_backward_views.
  */
-#define GSVC_RAST_EXCHANGE_MAX_CHUNKS 62
 typedef struct gsvc_rast_exchange {
     void *multicast;     /* dL_packed through the multicast mapping, or NULL: peer loads and stores */
     void *buffers;       /* device array of `world` pointers: every rank's dL_packed as mapped here */

@@ -32,7 +32,7 @@ def test_switch_allreduce_rejects_bad_arguments(cuda_device):
     from gsvc_b200 import _lib
     lib = _lib.lib()
     buf = torch.zeros(16, device=cuda_device)
-    st = torch.zeros(2, dtype=torch.int32, device=cuda_device)
+    st = torch.zeros(_lib.EXCHANGE_STATE_WORDS, dtype=torch.int32, device=cuda_device)
     p = buf.data_ptr()
     assert lib.gsvc_rast_switch_allreduce(None, None, p, st.data_ptr(), 0, 2, 16, 1, None) < 0     # no buffers at all
     assert lib.gsvc_rast_switch_allreduce(None, p, p, st.data_ptr(), 2, 2, 16, 1, None) < 0        # rank outside world
