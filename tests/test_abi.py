@@ -107,3 +107,55 @@ def test_header_is_plain_c_and_the_c_host_links():
                         "-I" + os.path.join(cuda, "include"), os.path.join(root, "examples", "c_host.c"),
                         "-o", os.path.join(tmp, "c_host"), "-L" + os.path.dirname(L.LIB_PATH), "-lgsvc_rast",
                         "-L" + os.path.join(cuda, "lib64"), "-lcudart"], check=True)
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """ctypes mirrors of the header's structs have the C compiler's sizes and field offsets (gcc, no CUDA needed)."""
+    fields = {"gsvc_rast_exchange": (_lib.Exchange, ["multicast", "buffers", "signal_pads", "state", "rank", "world",
+                                                     "n_ctas", "chunk_rows"]),
+              "gsvc_rast_view": (_lib.View, ["viewmatrix", "vm_stride_r", "vm_stride_c", "campos", "out_image", "flip_x",
+                                             "weight"]),
+              "gsvc_rast_settings": (_lib.Settings, [f for f, _ in _lib.Settings._fields_])}
+    lines = ["#include <stdio.h>", "#include <stddef.h>", f'#include "{HEADER}"', "int main(void) {"]
+    for name, (_, fs) in fields.items():
+        lines.append(f'printf("{name} %zu", sizeof({name}));')
+        for f in fs:
+            lines.append(f'printf(" %zu", offsetof({name}, {f}));')
+        lines.append('printf("\\n");')
+    lines.append(f'printf("consts %d %d %d\\n", GSVC_RAST_ABI_VERSION, GSVC_RAST_EXCHANGE_MAX_CHUNKS, GSVC_RAST_EXCHANGE_STATE_WORDS);')
+    lines += ["return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    for line in out[:-1]:
+        name, size, *offs = line.split()
+        ct, fs = fields[name]
+        assert C.sizeof(ct) == int(size), name
+        assert [getattr(ct, f).offset for f in fs] == [int(o) for o in offs], name
+    consts = [int(x) for x in out[-1].split()[1:]]
+    assert consts == [_lib.ABI_VERSION, _lib.EXCHANGE_MAX_CHUNKS, _lib.EXCHANGE_STATE_WORDS]
+
+
+def test_exchange_entry_points_validate_before_any_cuda_work(lib):
+    p = 0x1000                                     # never dereferenced: validation fails first
+    assert lib.gsvc_rast_switch_allreduce(None, None, p, p, 0, 2, 16, 1, None) == _lib.ERR_INVALID
+    assert b"multicast / buffers" in lib.gsvc_rast_last_error()
+    assert lib.gsvc_rast_switch_allreduce(None, p, p, p, 0, 2, 18, 1, None) == _lib.ERR_INVALID
+    assert b"multiple of 4" in lib.gsvc_rast_last_error()
+    assert lib.gsvc_rast_switch_allreduce(None, p, p, p, 0, 3, 16, 1, None) == _lib.ERR_INVALID
+    assert lib.gsvc_rast_switch_allreduce(None, p, p, None, 0, 2, 16, 1, None) == _lib.ERR_INVALID
+    assert lib.gsvc_rast_switch_allreduce(p + 4, p, p, p, 0, 2, 16, 1, None) == _lib.ERR_INVALID      # misaligned
+    args = [None, 1, None, 1, 100, 0, 1] + [None] * 11 + [0, None, None]
+    x = _lib.Exchange(None, p, p, p, 0, 2, 0, 0)
+    assert lib.gsvc_rast_backward_views_exchange(*args, p, None, None) == _lib.ERR_INVALID
+    assert lib.gsvc_rast_backward_views_exchange(*args, None, C.byref(x), None) == _lib.ERR_INVALID
+    assert b"dL_packed" in lib.gsvc_rast_last_error()
+    odd = list(args); odd[4] = 101
+    assert lib.gsvc_rast_backward_views_exchange(*odd, p, C.byref(x), None) == _lib.ERR_INVALID
+    assert b"even" in lib.gsvc_rast_last_error()
+    x = _lib.Exchange(None, p, p, p, 0, 2, 1, 0)
+    assert lib.gsvc_rast_backward_views_exchange(*args, p, C.byref(x), None) == _lib.ERR_INVALID      # no mover CTA
+    x = _lib.Exchange(None, p, p, p, 0, 16, 0, 0)
+    assert lib.gsvc_rast_backward_views_exchange(*args, p, C.byref(x), None) == _lib.ERR_INVALID      # peer path > 8 ranks

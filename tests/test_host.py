@@ -434,3 +434,38 @@ def test_dp_view_assignment_and_single_rank_statistics():
     den[combined] += 1
     for a, b in zip(deltas, (opacity_accum, anchor_demon, acc, den)):
         assert torch.allclose(a, b, atol=1e-6)
+
+
+def test_packed_backward_hands_the_exchange_to_exactly_one_backward():
+    """Host logic of sharding.packed_backward(buf, exchange=): the buffer must be the exchange's own, the first backward
+    that fits takes both, a second one inside the same context gets neither, and the context restores what was set."""
+    import torch
+    from gsvc_b200 import rasterizer as R
+    from gsvc_b200.sharding import packed_backward
+
+    class FakeExchange:
+        def __init__(self, P):
+            self.t = torch.zeros(P * 14)
+            self.numel = P * 14
+            self.fused_launches = 0
+
+        def buffer(self):
+            return self.t
+
+    P = 6
+    x = FakeExchange(P)
+    buf = x.buffer().view(P, 14)
+    with pytest.raises(ValueError):
+        with packed_backward(torch.zeros(P, 14), exchange=x):
+            pass
+    assert R._packed_target.buf is None and R._packed_target.exchange is None
+    with packed_backward(buf, exchange=x):
+        assert R._packed_target.take_with_exchange(P + 1, buf.device, True) == (None, None)      # shape does not fit
+        got, ex = R._packed_target.take_with_exchange(P, buf.device, True)
+        assert got is buf and ex is x and x.fused_launches == 1
+        assert R._packed_target.take_with_exchange(P, buf.device, True) == (None, None)          # single use
+        with packed_backward(torch.zeros(P, 14)):                                                 # nested: its own target
+            inner, inner_ex = R._packed_target.take_with_exchange(P, buf.device, True)
+            assert inner is not None and inner_ex is None
+        assert R._packed_target.taken and R._packed_target.exchange is x
+    assert R._packed_target.buf is None and R._packed_target.exchange is None
