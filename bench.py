@@ -628,10 +628,14 @@ def run_product_arm(args, rank, local_rank, world):
         step3x = None
         if ar3 is not None and ar3.mode == "multicast" and world >= 4 and graphs is not None and \
                 os.environ.get("GSVC_BENCH_C3_FUSED", "1") == "1":
-            step3x = GraphedStep(batch3, g3, dL3, exchange=ar3)
-            ar3_note = ("sharding.SwitchAllReduce carried by the per-Gaussian backward's own launch "
-                        "(gsvc_rast_backward_views_exchange: multimem.ld_reduce / multimem.st through the NVSwitch by the "
-                        "kernel's first CTAs, chunk by chunk under the computation of the later rows)")
+            try:
+                step3x = GraphedStep(batch3, g3, dL3, exchange=ar3)
+                ar3_note = ("sharding.SwitchAllReduce carried by the per-Gaussian backward's own launch "
+                            "(gsvc_rast_backward_views_exchange: multimem.ld_reduce / multimem.st through the NVSwitch by "
+                            "the kernel's first CTAs, chunk by chunk under the computation of the later rows)")
+            except Exception as e:   # the separate launch below still works
+                step3x = None
+                ar3_note += f"; the carried exchange was unavailable: {type(e).__name__}: {e}"
 
         def c3_compute():
             if step3 is not None:
