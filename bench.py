@@ -669,6 +669,9 @@ def run_product_arm(args, rank, local_rank, world):
                    "compute_only_window_ms": c_ms / n3, "exposed_collective_us": 1000.0 * (w_ms - c_ms) / n3,
                    "allreduce_bytes": c3["P"] * 14 * 4 if world > 1 else 0,
                    "allreduce": None if world == 1 else ar3_note,
+                   # every wait of the exchange kernels is bounded; a non-zero count would mean a rank did not arrive in
+                   # time and the timed windows are void
+                   "exchange_waits_that_gave_up": None if ar3 is None else ar3.timeouts(),
                    "timing": "max over ranks; the all-reduce is issued on the compute stream after the backward and the "
                              "step's end event follows it"}
         del g3, step3, step3x, buf3, dL3, ar3
