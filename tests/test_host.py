@@ -364,21 +364,35 @@ def _dp_fake_iteration(model, rank, it):
     return grads, [d_op, d_dem, d_acc, d_den]
 
 
-def _dp_worker(rank, world, port, out_dir):
+class _GlooCollective:
+    """Stand-in with the interface dp_train expects of sharding.SwitchAllReduce (`sum_(flat)` in place, any size),
+    backed by gloo: the plumbing of `collective=` is covered on the CPU, the CUDA kernel itself by the GPU tests."""
+    def __init__(self):
+        self.calls = 0
+
+    def sum_(self, flat):
+        self.calls += 1
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        return flat
+
+
+def _dp_worker(rank, world, port, out_dir, use_collective=False):
     from gsvc_b200.dp_train import allreduce_iteration
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     model = _dp_model()
     history = []
+    collective = _GlooCollective() if use_collective else None
     for it in range(1, 41):
         grads, deltas = _dp_fake_iteration(model, rank, it)
-        g_avg = allreduce_iteration(model, grads, deltas, n_views_total=4, world=world)
+        g_avg = allreduce_iteration(model, grads, deltas, n_views_total=4, world=world, collective=collective)
         model.optimizer_step(g_avg)
         if it % 4 == 0:                                                      # ten densification rounds
             gen = torch.Generator().manual_seed(77 + it)                     # the same seed on every rank
             added, pruned = model.adjust_anchor(gen, check_interval=4, success_threshold=0.8, grad_threshold=4e-4,
                                                 min_opacity=0.05)
             history.append((added, pruned, model.n_anchors))
+    assert collective is None or collective.calls == 40          # every iteration's exchange went through it
     torch.save((history, model.state_hash(), model.p["anchor"], model.offset_denom.shape[0]),
                os.path.join(out_dir, f"dp{rank}.pt"))
     dist.destroy_process_group()
@@ -395,6 +409,20 @@ def test_dp_densification_is_identical_on_every_rank(tmp_path):
     assert h0 == h1 and torch.equal(s0, s1) and torch.equal(a0, a1) and n0 == n1 == a0.shape[0] * 4
     assert sum(h[0] for h in h0) > 0 and sum(h[1] for h in h0) > 0, h0      # grew and pruned
     assert a0.shape[0] != 400
+
+
+def test_dp_loop_through_a_caller_supplied_collective(tmp_path):
+    """The `collective=` hook of the DP loop (what examples/dp_train.py --switch passes: sharding.SwitchAllReduce): the
+    iteration's one exchange goes through it and the ranks end up exactly where the built-in all-reduce takes them."""
+    port = _free_port()
+    mp.spawn(_dp_worker, args=(2, port, str(tmp_path), True), nprocs=2, join=True)
+    (h0, s0, a0, n0), (h1, s1, a1, n1) = torch.load(tmp_path / "dp0.pt"), torch.load(tmp_path / "dp1.pt")
+    assert h0 == h1 and torch.equal(s0, s1) and torch.equal(a0, a1) and n0 == n1
+    ref = tmp_path / "ref"
+    ref.mkdir()
+    mp.spawn(_dp_worker, args=(2, _free_port(), str(ref), False), nprocs=2, join=True)
+    hr, sr, ar_, nr = torch.load(ref / "dp0.pt")
+    assert hr == h0 and torch.equal(sr, s0) and torch.equal(ar_, a0) and nr == n0
 
 
 def test_dp_view_assignment_and_single_rank_statistics():
