@@ -50,6 +50,7 @@ class GraphedStep:
             if packed is not None:
                 raise RasterizerError("with `exchange` the packed buffer is the exchange's own")
             packed = exchange.buffer().view(self.P, GRAD_WIDTH)
+            self._exchange_generation = exchange.generation
         if self.backward and packed is None:
             packed = torch.empty((self.P, GRAD_WIDTH), dtype=torch.float32, device=self.device)
         self.packed = packed
@@ -101,6 +102,9 @@ class GraphedStep:
         self.capacity = R._captured_caps.get(key + ((self.batch.n_views,) if self.batch is not None else ()))
 
     def __call__(self):
+        if self.exchange is not None and self.exchange.generation != self._exchange_generation:
+            raise RasterizerError("the exchange's symmetric buffer was reallocated after this step was captured "
+                                  "(SwitchAllReduce.sum_ outgrew it): build a new GraphedStep")
         self.graph.replay()
         return self.color, self.radii, self.packed
 

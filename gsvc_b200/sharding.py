@@ -182,7 +182,9 @@ class SwitchAllReduce:
         self._xstruct = None
 
     def _allocate(self, numel: int):
-        """(Re)allocate the symmetric buffer: a collective — every rank calls it with the same size."""
+        """(Re)allocate the symmetric buffer: a collective — every rank calls it with the same size.  Addresses captured
+        in a CUDA graph (GraphedStep(exchange=...)) die with the old buffer: `generation` tells them apart."""
+        self.generation = getattr(self, "generation", -1) + 1
         import torch.distributed._symmetric_memory as symm
         _lib, mode = self._lib, self._mode_req
         self.numel = numel
